@@ -1,0 +1,85 @@
+// A1: CLIP ViT-L/14@448 tower forward = a fixed sequence of the kernels in gemm.cu / attention.cu / rowwise.cu.
+// Residual stream in fp32 (LayerNorm statistics, residual adds); GEMM operands and attention in bf16.
+#include "internal.h"
+
+namespace wg {
+namespace {
+
+struct ClipBuffers {
+    void* patches;   // bf16 [B*L, kpad]
+    float* patch_emb;  // fp32 [B*L, D]
+    float* x;        // fp32 [B*T, D]  residual stream
+    void* ln;        // bf16 [B*T, D]
+    void* qkv;       // bf16 [B*T, 3D]
+    void* attn;      // bf16 [B*T, D]
+    void* h1;        // bf16 [B*T, mlp]
+};
+
+bool carve(Workspace& ws, const wg_clip_weights* w, int B, ClipBuffers& b) {
+    const size_t g = w->image / w->patch, L = g * g, T = L + 1, D = w->hidden;
+    b.patches = ws.take((size_t)B * L * w->kpad * 2);
+    b.patch_emb = static_cast<float*>(ws.take((size_t)B * L * D * 4));
+    b.x = static_cast<float*>(ws.take((size_t)B * T * D * 4));
+    b.ln = ws.take((size_t)B * T * D * 2);
+    b.qkv = ws.take((size_t)B * T * 3 * D * 2);
+    b.attn = ws.take((size_t)B * T * D * 2);
+    b.h1 = ws.take((size_t)B * T * w->mlp * 2);
+    return b.patches && b.patch_emb && b.x && b.ln && b.qkv && b.attn && b.h1;
+}
+
+}  // namespace
+}  // namespace wg
+
+extern "C" size_t wg_clip_workspace_bytes(const wg_clip_weights* w, int B) {
+    using namespace wg;
+    if (!w || B <= 0) return 0;
+    Workspace ws(nullptr, 0);
+    ClipBuffers b;
+    carve(ws, w, B, b);
+    return ws.used();
+}
+
+extern "C" int wg_clip_forward(const wg_clip_weights* w, const void* pixels, int pixels_is_bf16, const uint8_t* key_valid, int B, int n_run,
+                               int mid_index, void* out_last, void* out_mid, int out_is_bf16, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+    using namespace wg;
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    WG_REQUIRE(w && pixels && out_last && workspace, "wg_clip_forward: null pointer");
+    WG_REQUIRE(B > 0, "wg_clip_forward: B=%d", B);
+    WG_REQUIRE(w->hidden == 1024 && w->heads * 64 == w->hidden, "wg_clip_forward: only hidden=1024 / head_dim=64 is built (got %d/%d)",
+               w->hidden, w->heads);
+    WG_REQUIRE(w->image % w->patch == 0 && w->kpad % 64 == 0 && w->kpad >= 3 * w->patch * w->patch, "wg_clip_forward: bad patch geometry");
+    WG_REQUIRE(n_run >= 0 && n_run <= w->n_layers, "wg_clip_forward: n_run=%d exceeds the %d layers supplied", n_run, w->n_layers);
+    WG_REQUIRE(out_mid == nullptr || (mid_index >= 0 && mid_index <= n_run), "wg_clip_forward: mid_index=%d out of range", mid_index);
+    if (!device_is_sm100()) {
+        set_error("wg_clip_forward: this library only runs on sm_100 (B200) devices; there is no fallback");
+        return WG_ERR_UNSUPPORTED;
+    }
+    const int g = w->image / w->patch, L = g * g, T = L + 1, D = w->hidden;
+    Workspace ws(workspace, workspace_bytes);
+    ClipBuffers b;
+    WG_REQUIRE(carve(ws, w, B, b), "wg_clip_forward: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+               wg_clip_workspace_bytes(w, B));
+    const int M = B * T;
+    const float scale = 0.125f;  // head_dim^-0.5, head_dim = 64
+
+    // embeddings: conv-as-GEMM, + CLS, + position embedding, pre_layrnorm
+    WG_TRY(launch_im2col_patch(pixels, pixels_is_bf16, b.patches, B, w->image, w->patch, w->kpad, s));
+    WG_TRY(gemm_f32_out(b.patches, w->kpad, w->patch_w, B * L, D, w->kpad, nullptr, WG_ACT_NONE, b.patch_emb, D, nullptr, s));
+    WG_TRY(launch_embed_ln(b.patch_emb, w->cls_emb, w->pos_emb, w->pre_ln_g, w->pre_ln_b, 1e-5f, b.x, B, T, D, s));
+    if (out_mid && mid_index == 0) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s));
+
+    for (int i = 0; i < n_run; ++i) {
+        const wg_clip_layer& ly = w->layers[i];
+        WG_TRY(wg_layernorm(b.x, 0, D, ly.ln1_g, ly.ln1_b, 1e-5f, b.ln, D, M, D, s));
+        WG_TRY(gemm_bf16_out(b.ln, D, ly.w_qkv, M, 3 * D, D, ly.b_qkv, WG_ACT_NONE, b.qkv, 3 * D, s));
+        WG_TRY(wg_attention_d64(b.qkv, b.attn, key_valid, B, T, w->heads, scale, s));
+        WG_TRY(gemm_f32_out(b.attn, D, ly.w_o, M, D, D, ly.b_o, WG_ACT_NONE, b.x, D, b.x, s));
+        WG_TRY(wg_layernorm(b.x, 0, D, ly.ln2_g, ly.ln2_b, 1e-5f, b.ln, D, M, D, s));
+        WG_TRY(gemm_bf16_out(b.ln, D, ly.w_fc1, M, w->mlp, D, ly.b_fc1, WG_ACT_QUICK_GELU, b.h1, w->mlp, s));
+        WG_TRY(gemm_f32_out(b.h1, w->mlp, ly.w_fc2, M, D, w->mlp, ly.b_fc2, WG_ACT_NONE, b.x, D, b.x, s));
+        if (out_mid && mid_index == i + 1) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s));
+    }
+    WG_TRY(launch_drop_cls_cast(b.x, out_last, out_is_bf16, B, T, D, s));
+    return WG_OK;
+}

@@ -1,0 +1,114 @@
+// Host-side plumbing: error strings, device queries, TMA tensor-map encoding.
+#include "host.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace wg {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || sym == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver (%s)", cudaGetErrorString(e));
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, const void* gptr, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return WG_ERR_CUDA;
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5];
+    cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank=%d dims=%llu,%llu stride0=%llu box=%u,%u ptr=%p)", (int)r,
+                  rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                  (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0, gptr);
+        return WG_ERR_CUDA;
+    }
+    return WG_OK;
+}
+
+struct DevInfo {
+    int sm_count = 0;
+    int is_sm100 = 0;
+    bool valid = false;
+};
+
+static DevInfo& dev_info() {
+    static thread_local DevInfo info;
+    static thread_local int cached_dev = -1;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        info = DevInfo();
+        return info;
+    }
+    if (dev != cached_dev || !info.valid) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+            info.sm_count = prop.multiProcessorCount;
+            info.is_sm100 = (prop.major == 10 && prop.minor == 0) ? 1 : 0;
+            info.valid = true;
+            cached_dev = dev;
+        } else {
+            info = DevInfo();
+        }
+    }
+    return info;
+}
+
+int device_sm_count() { return dev_info().sm_count; }
+int device_is_sm100() { return dev_info().is_sm100; }
+
+}  // namespace wg
+
+extern "C" int wg_version(void) { return WG_ABI_VERSION; }
+extern "C" const char* wg_last_error(void) { return wg::g_err; }
+extern "C" int wg_device_check(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        wg::set_error("wg_device_check: no CUDA device %d (count=%d); this library has no CPU fallback", device, n);
+        (void)cudaGetLastError();
+        return WG_ERR_UNSUPPORTED;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        wg::set_error("wg_device_check: cudaGetDeviceProperties failed");
+        return WG_ERR_CUDA;
+    }
+    if (!(prop.major == 10 && prop.minor == 0)) {
+        wg::set_error("wg_device_check: device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+        return WG_ERR_UNSUPPORTED;
+    }
+    return WG_OK;
+}

@@ -1,0 +1,56 @@
+// Host-side helpers shared by all translation units: error reporting across the C ABI,
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency,
+// so the library still loads on a machine without a GPU driver).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/walkgpt_b200.h"
+
+namespace wg {
+
+void set_error(const char* fmt, ...);  // thread-local message for wg_last_error()
+
+#define WG_CHECK_CUDA(expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::wg::set_error("%s:%d CUDA error %d (%s) in %s", __FILE__, __LINE__, (int)_e,        \
+                            cudaGetErrorString(_e), #expr);                                       \
+            return WG_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+#define WG_REQUIRE(cond, ...)                        \
+    do {                                             \
+        if (!(cond)) {                               \
+            ::wg::set_error(__VA_ARGS__);            \
+            return WG_ERR_INVALID;                   \
+        }                                            \
+    } while (0)
+
+#define WG_TRY(expr)                 \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != WG_OK) return _rc;\
+    } while (0)
+
+// 2-D / 3-D bf16 (or fp32) row-major tensor maps with 128B swizzle.  dims/box innermost-first.
+// strides_bytes has rank-1 entries (stride of dim1, dim2).
+int make_tensor_map(CUtensorMap* out, const void* gptr, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
+
+inline int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                             uint32_t box_rows, uint32_t box_cols) {
+    uint64_t dims[2] = {cols, rows};
+    uint64_t strides[1] = {ld_elems * 2};
+    uint32_t box[2] = {box_cols, box_rows};
+    return make_tensor_map(out, gptr, 2, 2, dims, strides, box);
+}
+
+int device_sm_count();
+int device_is_sm100();
+
+}  // namespace wg

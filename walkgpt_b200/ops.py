@@ -1,0 +1,92 @@
+"""Tensor-level wrappers over the C ABI kernels (device tensors in, device tensors out).
+
+These are plumbing: they validate shapes/dtypes, allocate outputs with torch, and pass raw device
+pointers plus the current CUDA stream to ``libwalkgpt_b200.so``.  No arithmetic happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, ACT_RELU, OUT_BF16, OUT_BF16_LN, OUT_F32  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.WalkGPTB200Error("walkgpt_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         out_mode: int = OUT_BF16, out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+         bias_period: int = 1, ln_gamma: Optional[torch.Tensor] = None, ln_beta: Optional[torch.Tensor] = None,
+         ln_eps: float = 1e-5) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16 (row stride may exceed K); see include/walkgpt_b200.h."""
+    _need_cuda(a, w, bias, out, resid)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_mode == OUT_F32 else torch.bfloat16)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    assert out.dtype == (torch.float32 if out_mode == OUT_F32 else torch.bfloat16)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+        assert bias.numel() == (N if bias_period <= 1 else bias_period * N)
+    if resid is not None:
+        assert resid.shape == (M, N) and resid.stride(0) == out.stride(0) and resid.stride(1) == 1
+        assert resid.dtype == (torch.float32 if out_mode == OUT_F32 else torch.bfloat16)
+    args = _lib.GemmArgs()
+    args.A, args.lda, args.W, args.ldw = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
+    args.M, args.N, args.K = M, N, K
+    args.bias, args.bias_period, args.act, args.out_mode = _ptr(bias), bias_period, act, out_mode
+    args.out, args.ldo, args.resid = out.data_ptr(), out.stride(0), _ptr(resid)
+    if out_mode == OUT_BF16_LN:
+        assert ln_gamma is not None and ln_beta is not None and ln_gamma.dtype == torch.float32
+    args.ln_gamma, args.ln_beta, args.ln_eps = _ptr(ln_gamma), _ptr(ln_beta), ln_eps
+    if M == 0:
+        return out
+    _lib.check(_lib.lib().wg_gemm(C.byref(args), _stream()), "wg_gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 LayerNorm over the last dim of a 2-D fp32/bf16 tensor."""
+    _need_cuda(x, gamma, beta, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty(rows, D, device=x.device, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.shape == (rows, D) and out.stride(1) == 1
+    _lib.check(_lib.lib().wg_layernorm(x.data_ptr(), int(x.dtype == torch.bfloat16), x.stride(0), _ptr(gamma), _ptr(beta), eps,
+                                       out.data_ptr(), out.stride(0), rows, D, _stream()), "wg_layernorm")
+    return out
+
+
+def attention_d64(qkv: torch.Tensor, heads: int, scale: float, key_valid: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv bf16 [B,T,3*heads*64] -> bf16 [B,T,heads*64]; key_valid uint8 [B,T] (0 = padded key)."""
+    _need_cuda(qkv, key_valid, out)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.dim() == 3 and qkv.shape[2] == 3 * heads * 64
+    B, T, _ = qkv.shape
+    if out is None:
+        out = torch.empty(B, T, heads * 64, device=qkv.device, dtype=torch.bfloat16)
+    assert out.is_contiguous() and out.dtype == torch.bfloat16
+    if key_valid is not None:
+        assert key_valid.dtype == torch.uint8 and key_valid.shape == (B, T) and key_valid.is_contiguous()
+    _lib.check(_lib.lib().wg_attention_d64(qkv.data_ptr(), out.data_ptr(), _ptr(key_valid), B, T, heads, scale, _stream()),
+               "wg_attention_d64")
+    return out
