@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .specs import Spec, init_tensor
 
 
 # --------------------------------------------------------------------------------------------------
@@ -37,40 +38,12 @@ def _add_tensor(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool
         mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
 
 
-def _default_init(name: str, shape: Sequence[int], gen: torch.Generator) -> torch.Tensor:
-    """Deterministic random init used when no checkpoint is loaded (synthetic benchmarks / tests)."""
-    leaf = name.split(".")[-1]
-    n = 1
-    for s in shape:
-        n *= s
-    r = torch.randn(n, generator=gen, dtype=torch.float32).reshape(tuple(shape))
-    if name.endswith("positional_encoding_gaussian_matrix"):
-        return r
-    if leaf == "log_temp":
-        return 0.1 * r
-    if len(shape) == 1 and leaf == "weight":  # LayerNorm / LayerNorm2d scale
-        return 1.0 + 0.1 * r
-    if len(shape) == 1:  # biases, class_embedding
-        return 0.02 * r if leaf == "bias" else 0.5 * r
-    fan_in = n // shape[0]
-    if len(shape) == 4:  # convolutions
-        if "upscaling" in name or "upsample_2x" in name:
-            fan_in = shape[0]  # ConvTranspose2d weight is [Cin, Cout, kh, kw]
-        return r / math.sqrt(max(fan_in, 1))
-    if "position_embedding" in name:
-        return 0.1 * r
-    if any(k in name for k in ("token", "embed", "q_x", "q_global", "text_type")):
-        return 0.5 * r
-    return r / math.sqrt(max(fan_in, 1))
-
-
 class _SpecModule(nn.Module):
     """Base: parameters from ``self._spec()``; packed device weights cached until the parameters change."""
 
     def _build(self, spec: Dict[str, Tuple[Sequence[int], bool]], seed: int = 0) -> None:
         for name, (shape, is_buffer) in spec.items():
-            gen = torch.Generator().manual_seed((hash_name(name) + 1000003 * seed) % (2 ** 31))
-            _add_tensor(self, name, _default_init(name, shape, gen), buffer=is_buffer)
+            _add_tensor(self, name, init_tensor(name, shape, seed), buffer=is_buffer)
         self._packed = None
         self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
 
@@ -89,13 +62,6 @@ class _SpecModule(nn.Module):
 
     def _sd(self) -> Dict[str, torch.Tensor]:
         return {k: v.detach() for k, v in self.state_dict().items()}
-
-
-def hash_name(name: str) -> int:
-    h = 2166136261
-    for ch in name.encode():
-        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
-    return h
 
 
 def _bf16(t: torch.Tensor) -> torch.Tensor:
