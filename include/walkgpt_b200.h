@@ -138,6 +138,162 @@ WG_API int wg_clip_forward(const wg_clip_weights* w, const void* pixels, int pix
                     int n_run, int mid_index, void* out_last, void* out_mid, int out_is_bf16, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* A2 -- Multi-Scale Query Projector.  Replaces MultiScaleQFormerProjector.forward (utils/utils_walkgpt.py:259-300). */
+typedef struct wg_msqp_block {                 /* one CrossAttnBlock (utils_walkgpt.py:163-185) */
+    const float* qn_g; const float* qn_b;      /* q_norm */
+    const void* w_q;   const float* b_q;       /* bf16 [d,d] = attn.in_proj_weight rows [0,d) */
+    const void* w_o;   const float* b_o;       /* attn.out_proj */
+    const float* ffn_ln_g; const float* ffn_ln_b;
+    const void* w_f1;  const float* b_f1;      /* bf16 [4d,d] */
+    const void* w_f2;  const float* b_f2;      /* bf16 [d,4d] */
+} wg_msqp_block;
+
+typedef struct wg_msqp_scale {
+    const float* queries;                      /* fp32 [nq, d] learned queries (q_x1 / q_x2 / q_x4 / q_global) */
+    int32_t nq; int32_t reserved;
+    /* bf16 [4d, d] = (K_layer0 | V_layer0 | K_layer1 | V_layer1) rows of the two blocks' in_proj, with each block's
+       kv_norm affine folded in:  W' = W diag(gamma),  b' = b + W beta   (the kernel normalises kv without affine). */
+    const void* w_kv;  const float* b_kv;
+    wg_msqp_block blocks[2];
+} wg_msqp_scale;
+
+typedef struct wg_msqp_weights {
+    int32_t sam_dim, llama_dim, d, heads;      /* d = 1024, heads = 8 */
+    int32_t n_tokens;                          /* s*s after padding (36 when target_square_side = 6) */
+    int32_t reserved;
+    const void* w_in;  const float* b_in;      /* sam_to_proj: bf16 [d, sam_dim] */
+    const float* gate_ln_g; const float* gate_ln_b;   /* gate.net.0 */
+    const void* w_g1;  const float* b_g1;      /* gate.net.1: bf16 [128, d] */
+    const float* w_g2; const float* b_g2;      /* gate.net.3: fp32 [128], [1] */
+    const float* pad_token;                    /* fp32 [d] */
+    const void* w_out; const float* b_out;     /* to_llama: bf16 [llama_dim, d] */
+    wg_msqp_scale scales[4];                   /* x1, x2, x4, global */
+} wg_msqp_weights;
+
+WG_API size_t wg_msqp_workspace_bytes(const wg_msqp_weights* w, int B, int L);
+/* feats bf16 [B, L, sam_dim] (L a perfect square) -> out [B, n_tokens, llama_dim] (bf16 or fp32). */
+WG_API int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16, int B, int L, void* out, int out_is_bf16,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* A5 -- Calibrated Text Projector.  Replaces CalibratedTextProjector.forward (utils/utils_walkgpt.py:321-327),
+ * widen = 2, use_residual = False (model/walkgpt.py:141). */
+typedef struct wg_ctp_weights {
+    int32_t in_dim, mid_dim, out_dim, reserved; /* H, 512, 256 */
+    const float* ln0_g; const float* ln0_b;     /* net.0 */
+    const void* w1; const float* b1;            /* net.1: bf16 [mid, in] */
+    const void* w2; const float* b2;            /* net.3: bf16 [out, mid] */
+    const float* ln4_g; const float* ln4_b;     /* net.4 */
+    const float* text_type;                     /* fp32 [out] */
+    const float* log_temp;                      /* fp32 [1] */
+} wg_ctp_weights;
+
+WG_API size_t wg_ctp_workspace_bytes(int rows, int in_dim);
+/* x [rows, in_dim] fp32 or bf16 -> out [rows, 256] fp32 or bf16 (row-wise; gather-then-project == project-then-gather). */
+WG_API int wg_ctp_forward(const wg_ctp_weights* w, const void* x, int x_is_bf16, int rows, void* out, int out_is_bf16,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* A3 + A4 -- out_mm_projector MLP (llava_arch.py:38-42, used at :197-208) followed by image_feature_neck
+ * (model/walkgpt.py:97-113, LayerNorm2d = segment_anything/modeling/common.py:31-43). */
+typedef struct wg_proj_neck_weights {
+    int32_t mm_hidden, hidden, out_chans, reserved;  /* 1024, H, 256 */
+    const void* w_fc1; const float* b_fc1;      /* bf16 [2H, mm_hidden] */
+    const void* w_fc2; const float* b_fc2;      /* bf16 [H, 2H] */
+    const void* w_conv1;                        /* bf16 [256, H]           (1x1 conv, no bias) */
+    const float* ln1_g; const float* ln1_b;
+    const void* w_conv3;                        /* bf16 [256, 9*256]: column (ky*3+kx)*256 + ci  (3x3 conv, pad 1, no bias) */
+    const float* ln2_g; const float* ln2_b;
+} wg_proj_neck_weights;
+
+WG_API size_t wg_proj_neck_workspace_bytes(const wg_proj_neck_weights* w, int rows);
+/* feats bf16 [B*g*g, mm_hidden] -> proj_out bf16 [B*g*g, H] (nullable) and the image embedding as TOKENS
+ * emb_tokens bf16 [B*g*g, 256] (channels-last; nullable = projector only). */
+WG_API int wg_proj_neck_forward(const wg_proj_neck_weights* w, const void* feats_bf16, int B, int grid_side,
+                                void* proj_out_bf16, void* emb_tokens_bf16, void* workspace, size_t workspace_bytes,
+                                void* stream);
+WG_API size_t wg_neck_workspace_bytes(int rows);
+/* image_feature_neck alone: proj tokens bf16 [B*g*g, H] (channels-last view of the NCHW input) -> emb tokens bf16 [B*g*g, 256]. */
+WG_API int wg_neck_forward(const wg_proj_neck_weights* w, const void* proj_tokens_bf16, int B, int grid_side,
+                           void* emb_tokens_bf16, void* workspace, size_t workspace_bytes, void* stream);
+/* tokens bf16 [B, L, C] -> NCHW [B, C, L] (fp32 or bf16): the layout the reference modules exchange. */
+WG_API int wg_tokens_to_nchw(const void* tokens_bf16, void* out, int out_is_bf16, int B, int L, int C, void* stream);
+
+/* A6 + A7 -- PromptEncoder (text_embeds path, prompt_encoder.py:140-186) + MaskDecoderMultiScale.forward
+ * (mask_decoder_multi_scale.py:87-213, level_num = 0) with its TwoWayTransformer (transformer.py:62-242),
+ * batched over all P prompts of a batch of images.
+ * "_t" matrices are TRANSPOSED bf16 [in_features][out_features] (token-side linears, read column-wise);
+ * the others keep the nn.Linear layout bf16 [out_features][in_features] (image-side GEMMs). */
+typedef struct wg_twoway_layer {
+    const void* sa_wq_t; const float* sa_bq; const void* sa_wk_t; const float* sa_bk;   /* self_attn: [256][256] */
+    const void* sa_wv_t; const float* sa_bv; const void* sa_wo_t; const float* sa_bo;
+    const float* n1_g; const float* n1_b;
+    const void* t2i_wq_t; const float* t2i_bq;      /* cross_attn_token_to_image.q_proj  [256][128] */
+    const void* t2i_wo_t; const float* t2i_bo;      /* cross_attn_token_to_image.out_proj [128][256] */
+    const float* n2_g; const float* n2_b;
+    const void* mlp_w1_t; const float* mlp_b1;      /* [256][2048] */
+    const void* mlp_w2_t; const float* mlp_b2;      /* [2048][256] */
+    const float* n3_g; const float* n3_b;
+    const void* i2t_wk_t; const float* i2t_bk;      /* cross_attn_image_to_token.k_proj [256][128] */
+    const void* i2t_wv_t; const float* i2t_bv;      /* cross_attn_image_to_token.v_proj [256][128] */
+    const void* w_img;                              /* bf16 [384][256] = t2i.k_proj | t2i.v_proj | i2t.q_proj */
+    const float* b_img;                             /* fp32 [hw][384] = (pe Wk^T + bk | bv | pe Wq^T + bq): dense PE folded in */
+    const void* i2t_wo; const float* i2t_bo;        /* cross_attn_image_to_token.out_proj: bf16 [256][128] */
+    const float* n4_g; const float* n4_b;
+} wg_twoway_layer;
+
+typedef struct wg_mask_decoder_weights {
+    int32_t grid_h, grid_w, n_mask_tokens, up_stages;   /* 32, 32, 4, 1 */
+    const float* out_tokens;     /* fp32 [1 + n_mask_tokens][256] = (iou_token ; mask_tokens) + level_embed[0] */
+    const float* sparse_add;     /* fp32 [256] added to each text embedding (level_embed[0]); NULL = none */
+    const float* no_mask;        /* fp32 [256] PromptEncoder.no_mask_embed (dense prompt embedding) */
+    wg_twoway_layer layers[2];
+    const void* fin_wq_t; const float* fin_bq;      /* final_attn_token_to_image.q_proj [256][128] */
+    const void* fin_wo_t; const float* fin_bo;      /* final_attn_token_to_image.out_proj [128][256] */
+    const float* nf_g; const float* nf_b;           /* norm_final_attn */
+    const void* w_img_fin;                          /* bf16 [256][256] = final.k_proj | final.v_proj */
+    const float* b_img_fin;                         /* fp32 [hw][256] = (pe Wk^T + bk | bv) */
+    const void* w_up;                               /* bf16 [4*32][256]: row (dy*2+dx)*32 + co = ConvT.weight[ci, co, dy, dx] */
+    const float* b_up;                              /* fp32 [128] = ConvT.bias tiled over the 4 sub-pixels */
+    const float* up_ln_g; const float* up_ln_b;     /* output_upscaling.1 (LayerNorm2d over 32 channels) */
+    const void* hyp_w0_t; const float* hyp_b0;      /* hypernetwork MLPs: bf16 [4][256][256], fp32 [4][256] */
+    const void* hyp_w1_t; const float* hyp_b1;      /* [4][256][256] */
+    const void* hyp_w2_t; const float* hyp_b2;      /* [4][256][32], fp32 [4][32] */
+    const void* iou_w0_t; const float* iou_b0;      /* iou_prediction_head: [256][256] */
+    const void* iou_w1_t; const float* iou_b1;
+    const void* iou_w2_t; const float* iou_b2;      /* [256][4] */
+} wg_mask_decoder_weights;
+
+WG_API size_t wg_mask_decoder_workspace_bytes(int P, int hw);
+/* img_emb_tokens bf16 [B, hw, 256] (channels-last image embeddings), txt_emb fp32 [P, 256] (CTP outputs = sparse prompt
+ * embeddings), prompt_img int32 [P] (image index of each prompt; prompts of one image are contiguous).
+ * low_res_out fp32 [P, n_out, 2*grid_h, 2*grid_w], iou_out fp32 [P, n_out]; n_out = 1 (multimask_output = 0) or 4.
+ * depth_pool_out (nullable) fp32 [P, 33]: sigmoid(logit)-weighted sums of the 32 upscaled channels + the weight sum
+ * (input of this repo's relative-depth extension; not part of the reference). */
+WG_API int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, const float* txt_emb,
+                                   const int32_t* prompt_img, int P, int multimask_output, float* low_res_out, float* iou_out,
+                                   float* depth_pool_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* A6 -- PromptEncoder.get_dense_pe / PositionEmbeddingRandom.forward (prompt_encoder.py:67-76, 216-229).
+ * gauss fp32 [2, F]; out_chw fp32 [2F, h, w] (reference layout, nullable); out_tokens fp32 [h*w, 2F] (nullable). */
+WG_API int wg_dense_pe(const float* gauss, int num_pos_feats, int h, int w, float* out_chw, float* out_tokens, void* stream);
+
+/* A8 + A9 -- postprocess_masks (model/walkgpt.py:749-790, vision_tower_for_mask=True; Sam.postprocess_masks,
+ * segment_anything/modeling/sam.py:137-172) fused with the `> 0` threshold (evaluation_walkgpt.py:937) and the
+ * mask_score expression (model/walkgpt.py:541 == :742).
+ *   low_res fp32 [n_masks, Hm, Wm] -> bilinear(align_corners=False) to target x target -> crop [:in_h, :in_w]
+ *   -> bilinear to (out_h, out_w).  logits_out fp32 [n_masks, out_h, out_w]; mask_out uint8 (0/1, nullable);
+ *   score_out fp32 [n_masks] (nullable). */
+WG_API size_t wg_postprocess_workspace_bytes(int n_masks, int in_h, int in_w);
+WG_API int wg_postprocess_masks(const float* low_res, int n_masks, int Hm, int Wm, int target, int in_h, int in_w, int out_h,
+                                int out_w, float* logits_out, uint8_t* mask_out, float* score_out, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* A10 -- relative-depth head.  NOT PART OF THE REFERENCE (it emits depth as LLM text, utils/PAVE_dataset.py:181-188);
+ * this repo's own extension, defined in oracle/path_a.py:depth_head.  pooled fp32 [P,33] comes from
+ * wg_mask_decoder_forward; seg_offsets int32 [B+1] (device); w1 fp32 [256,32], b1 [256], w2 [256], b2 [1];
+ * depth_out fp32 [P] in [0,1], min-max normalised over the prompts of each image. */
+WG_API int wg_depth_head(const float* pooled, const int32_t* seg_offsets, int B, int max_S, const float* w1, const float* b1,
+                         const float* w2, const float* b2, float* depth_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,178 @@
+"""Generate tests/golden/*.pt by EXECUTING THE REFERENCE (run in the build container only; /root/reference and HF
+transformers must be importable).  TEST INFRASTRUCTURE ONLY.
+
+For every hot-path module: build the reference nn.Module, load this repo's seeded synthetic state_dict with
+``load_state_dict(strict=True)`` (which also pins parameter names and shapes), run it on seeded inputs in fp32 on
+the CPU and save inputs + outputs.  tests/test_oracle_golden.py then checks oracle/path_a.py against these files,
+and the GPU tests check the CUDA path against the same files and against the oracle.
+
+    python -m oracle.make_golden            # writes tests/golden/
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("WALKGPT_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from walkgpt_b200 import specs  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def save(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".pt")
+    torch.save(obj, path)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+@torch.no_grad()
+def main():
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    from utils.utils_walkgpt import CalibratedTextProjector, MultiScaleQFormerProjector
+    from model.segment_anything.modeling import MaskDecoder, MaskDecoderMultiScale, PromptEncoder, Sam, TwoWayTransformer
+    from model.segment_anything.modeling.common import LayerNorm2d
+
+    # ---- A5 CTP
+    for in_dim in (256, 4096):
+        ref = CalibratedTextProjector(in_dim, 256, widen=2, use_residual=False).eval()
+        ref.load_state_dict(specs.make_state_dict(specs.ctp_spec(in_dim, 256), seed=11), strict=True)
+        x3 = rnd((2, 5, in_dim), 101)
+        x2 = rnd((3, in_dim), 102)
+        save(f"ctp_{in_dim}", {"seed": 11, "in_dim": in_dim, "x3": x3, "y3": ref(x3), "x2": x2, "y2": ref(x2)})
+
+    # ---- A2 MSQP (Path B width, small grid) and (Path A width, 32x32 grid)
+    for tag, sam_dim, llama, B, L in (("b_small", 256, 64, 2, 64), ("a_32", 1024, 128, 1, 1024)):
+        ref = MultiScaleQFormerProjector(sam_dim=sam_dim, llama_dim=llama, pad_to_square=True, target_square_side=6).eval()
+        ref.load_state_dict(specs.make_state_dict(specs.msqp_spec(sam_dim, llama), seed=12), strict=True)
+        x = rnd((B, L, sam_dim), 201)
+        save(f"msqp_{tag}", {"seed": 12, "sam_dim": sam_dim, "llama_dim": llama, "x_shape": (B, L, sam_dim), "x_seed": 201, "y": ref(x)})
+
+    # ---- A3 out_mm_projector MLP (llava_arch.py:38-42) and A4 neck (walkgpt.py:97-113)
+    mm, hid = 128, 64
+    proj = nn.Sequential(nn.Linear(mm, hid * 2), nn.GELU(), nn.Linear(hid * 2, hid)).eval()
+    proj.load_state_dict(specs.make_state_dict(specs.out_mm_projector_spec(mm, hid), seed=13), strict=True)
+    neck = nn.Sequential(nn.Conv2d(hid, 256, kernel_size=1, bias=False), LayerNorm2d(256),
+                         nn.Conv2d(256, 256, kernel_size=3, padding=1, bias=False), LayerNorm2d(256)).eval()
+    neck.load_state_dict(specs.make_state_dict(specs.neck_spec(hid, 256), seed=13), strict=True)
+    x = rnd((2, 64, mm), 301)
+    p = proj(x)
+    e = neck(p.permute(0, 2, 1).reshape(2, hid, 8, 8))
+    save("proj_neck_small", {"seed": 13, "mm": mm, "hidden": hid, "x": x, "proj": p, "emb": e})
+
+    # ---- A6 prompt encoder + A7 decoders
+    for g in (8, 32):
+        pe_mod = PromptEncoder(embed_dim=256, image_embedding_size=(g, g), input_image_size=(g * 14, g * 14), mask_in_chans=16).eval()
+        pe_mod.load_state_dict(specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=14), strict=True)
+        dec = MaskDecoderMultiScale(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                                    transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256, image_feature_scale_num=1).eval()
+        dec.load_state_dict(specs.make_state_dict(specs.mask_decoder_multiscale_spec(), seed=15), strict=True)
+        S = 3 if g == 8 else 2
+        emb = rnd((1, 256, g, g), 401)
+        txt = rnd((S, 1, 256), 402, 0.5)
+        sparse, dense = pe_mod(points=None, boxes=None, masks=None, text_embeds=txt)
+        pe = pe_mod.get_dense_pe()
+        m1, i1 = dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                     multimask_output=False, level_num=0)
+        m4, i4 = dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                     multimask_output=True, level_num=0)
+        save(f"decoder_ms_g{g}", {"seed_prompt": 14, "seed_dec": 15, "grid": g, "emb_shape": (1, 256, g, g), "emb_seed": 401, "txt": txt,
+                                  "dense_pe": pe if g == 8 else pe[:, ::8],
+                                  "masks1": m1, "iou1": i1, "masks4": m4, "iou4": i4})
+    # standard SAM decoder (Path B shapes of the shared two-way transformer)
+    g = 8
+    pe_mod = PromptEncoder(embed_dim=256, image_embedding_size=(g, g), input_image_size=(g * 16, g * 16), mask_in_chans=16).eval()
+    pe_mod.load_state_dict(specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=14), strict=True)
+    dec = MaskDecoder(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                      transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256).eval()
+    dec.load_state_dict(specs.make_state_dict(specs.mask_decoder_sam_spec(), seed=16), strict=True)
+    emb = rnd((1, 256, g, g), 411)
+    txt = rnd((2, 1, 256), 412, 0.5)
+    sparse, dense = pe_mod(points=None, boxes=None, masks=None, text_embeds=txt)
+    m1, i1 = dec(image_embeddings=emb, image_pe=pe_mod.get_dense_pe(), sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                 multimask_output=False)
+    m3, i3 = dec(image_embeddings=emb, image_pe=pe_mod.get_dense_pe(), sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                 multimask_output=True)
+    save("decoder_sam_g8", {"seed_prompt": 14, "seed_dec": 16, "grid": g, "emb": emb, "txt": txt, "masks1": m1, "iou1": i1, "masks3": m3, "iou3": i3})
+
+    # ---- A8 postprocess (walkgpt.py:771-789 restated with the same two F.interpolate calls; Sam.postprocess_masks executed)
+    low = rnd((3, 1, 64, 64), 501, 3.0)
+    cases = {}
+    for name, inp, orig in (("full", (448, 448), (448, 448)), ("pad169", (252, 448), (360, 640)), ("odd", (448, 301), (517, 347))):
+        T = max(inp)
+        m = F.interpolate(low.float(), (T, T), mode="bilinear", align_corners=False)
+        m = m[..., : inp[0], : inp[1]]
+        m = F.interpolate(m, orig, mode="bilinear", align_corners=False)
+        score = (m[:, 0].sigmoid().flatten(1) * (m[:, 0] > 0).flatten(1)).sum(1) / ((m[:, 0] > 0).flatten(1).sum(1) + 1e-6)  # walkgpt.py:541
+        cases[name] = {"input_size": inp, "original_size": orig, "logits_sub": m[:, 0, ::7, ::5].clone(), "score": score,
+                       "pos_count": (m[:, 0] > 0).flatten(1).sum(1), "sum": m.double().sum(dim=(1, 2, 3))}
+    sam_self = types.SimpleNamespace(image_encoder=types.SimpleNamespace(img_size=1024))
+    low_b = rnd((2, 1, 256, 256), 502, 3.0)
+    mb = Sam.postprocess_masks(sam_self, low_b, (768, 1024), (480, 640))
+    cases["sam_1024"] = {"input_size": (768, 1024), "original_size": (480, 640), "logits_sub": mb[:, 0, ::7, ::5].clone(),
+                         "sum": mb.double().sum(dim=(1, 2, 3))}
+    save("postprocess", {"low": low, "low_b_seed": 502, "cases": cases})
+
+    # ---- A1 CLIP tower (HF transformers is where the reference's arithmetic lives; clip_encoder.py:61-98)
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    L = 3
+    cfg = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=L, num_attention_heads=16, image_size=448, patch_size=14)
+    cfg._attn_implementation = "eager"
+    hf = CLIPVisionModel(cfg).eval()
+    sd = specs.make_state_dict({k: v for k, v in __import__("walkgpt_b200.modules", fromlist=["x"]).clip_param_spec(layers=L).items()}, seed=17)
+    hf.load_state_dict({k[len("vision_tower."):]: v for k, v in sd.items()}, strict=True)
+    px = rnd((2, 3, 448, 448), 601)
+    out = hf(px, output_hidden_states=True)
+    hs = out.hidden_states
+    assert len(hs) == L + 1
+    # masked variant: drive the layers by hand with the additive key mask of custom_clip.py:27-38 / llava_arch.py:160-193
+    sizes = [(252, 448), (448, 300)]
+    valid = torch.zeros(2, 448, 448)
+    for i, (h, w) in enumerate(sizes):
+        valid[i, :h, :w] = 1
+    kv = F.interpolate(valid[:, None], size=(32, 32), mode="nearest")[:, 0].flatten(1)
+    kv = torch.cat([torch.ones(2, 1), kv], dim=-1)
+    inv = 1.0 - kv[:, None, None, :].expand(2, 1, 1025, 1025)
+    mask4d = inv.masked_fill(inv.bool(), torch.finfo(torch.float32).min)
+    vm = hf.vision_model
+    h = vm.pre_layrnorm(vm.embeddings(px))
+    hs_m = [h]
+    for layer in vm.encoder.layers:
+        h = layer(h, mask4d)
+        if isinstance(h, tuple):
+            h = h[0]
+        hs_m.append(h)
+    save("clip_3layer", {"seed": 17, "layers": L, "px_seed": 601, "sizes": sizes, "key_valid": kv,
+                         "hs_sub": [t[:, ::41, ::13].clone() for t in hs], "hs_mean": [t.double().mean() for t in hs],
+                         "hs_std": [t.double().std() for t in hs],
+                         "hs_masked_sub": [t[:, ::41, ::13].clone() for t in hs_m]})
+
+    # ---- scoring helper (utils/utils.py:192-204), executed if importable
+    try:
+        from utils.utils import intersectionAndUnionGPU
+        o = (rnd((64, 64), 701) > 0).float()
+        t = (rnd((64, 64), 702) > 0).float()
+        t[:4] = 255
+        ai, au, at = intersectionAndUnionGPU(o.clone(), t.clone(), 2, ignore_index=255)
+        save("iou_hist", {"output": o, "target": t, "inter": ai, "union": au, "target_area": at})
+    except Exception as e:  # noqa: BLE001
+        print("intersectionAndUnionGPU not importable here:", repr(e))
+
+
+if __name__ == "__main__":
+    main()

@@ -149,12 +149,152 @@ def t_clip():
     ms = e0.elapsed_time(e1) / 3
     print(f"time clip tower B64 (23 layers): {ms:.2f} ms -> {64/ms*1e3:.1f} img/s, {64*693.5/ms:.1f} TFLOP/s", flush=True)
 
+
+def _sd_cpu(m):
+    return {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+
+def t_ctp():
+    from walkgpt_b200.modules import CalibratedTextProjector
+    from oracle import path_a
+    for H, rows in [(4096, 192), (5120, 33), (256, 7)]:
+        m = CalibratedTextProjector(H, 256, seed=3).cuda()
+        x = torch.randn(rows, H, device=dev)
+        y = m(x[None])[0]
+        ref = path_a.ctp_forward(_sd_cpu(m), x.cpu()[None])[0]
+        torch.cuda.synchronize(); stats(f"ctp H{H} rows{rows} fp32-in", y.cpu(), ref, 1e-2)
+        yb = m(x.bfloat16()[None])[0]
+        stats(f"ctp H{H} rows{rows} bf16-in", yb.float().cpu(), ref, 2e-2)
+    y2 = m(x)
+    print("ctp 2-D input shape", tuple(y2.shape))
+
+def t_msqp():
+    from walkgpt_b200.modules import MultiScaleQFormerProjector
+    from oracle import path_a
+    for sam_dim, H, B, L in [(256, 64, 2, 64), (1024, 4096, 2, 1024), (256, 128, 1, 4096)]:
+        m = MultiScaleQFormerProjector(sam_dim, H, pad_to_square=True, target_square_side=6, seed=4).cuda()
+        x = torch.randn(B, L, sam_dim, device=dev)
+        y = m(x)
+        torch.cuda.synchronize()
+        ref = path_a.msqp_forward(_sd_cpu(m), x.bfloat16().float().cpu(), target_square_side=6)
+        stats(f"msqp sam{sam_dim} H{H} B{B} L{L}", y.reshape(-1, H).cpu(), ref.reshape(-1, H), 2e-2)
+
+def t_projneck():
+    from walkgpt_b200.modules import ProjectorNeck
+    from oracle import path_a
+    for mm, H, B, g in [(128, 64, 2, 8), (1024, 4096, 2, 32)]:
+        m = ProjectorNeck(mm, H, 256, seed=5).cuda()
+        x = torch.randn(B, g * g, mm, device=dev)
+        sd = _sd_cpu(m)
+        sdp = {k[len("out_mm_projector."):]: v for k, v in sd.items() if k.startswith("out_mm_projector.")}
+        sdn = {k[len("image_feature_neck."):]: v for k, v in sd.items() if k.startswith("image_feature_neck.")}
+        p = m.project(x); e = m(x)
+        torch.cuda.synchronize()
+        pr = path_a.out_mm_projector_mlp(sdp, x.bfloat16().float().cpu())
+        er = path_a.image_feature_neck(sdn, pr, g)
+        stats(f"projector mm{mm} H{H}", p.reshape(-1, H).cpu(), pr.reshape(-1, H), 2e-2)
+        stats(f"proj+neck mm{mm} H{H}", e.reshape(B * 256, -1).cpu(), er.reshape(B * 256, -1), 3e-2)
+        e2 = m.neck(pr.permute(0, 2, 1).reshape(B, H, g, g).to(dev))
+        stats(f"neck alone H{H}", e2.reshape(B * 256, -1).cpu(), er.reshape(B * 256, -1), 3e-2)
+
+def t_decoder():
+    from walkgpt_b200.modules import PromptEncoder, MaskDecoderMultiScale
+    from oracle import path_a
+    for g, S in [(8, 3), (32, 2), (32, 12)]:
+        pe_m = PromptEncoder(256, (g, g), (g * 14, g * 14), 16, seed=6).cuda()
+        dec = MaskDecoderMultiScale(seed=7).cuda()
+        emb = torch.randn(1, 256, g, g, device=dev)
+        txt = torch.randn(S, 1, 256, device=dev) * 0.5
+        sparse, dense = pe_m(None, None, None, txt)
+        pe = pe_m.get_dense_pe()
+        sdp, sdd = _sd_cpu(pe_m), _sd_cpu(dec)
+        pe_ref = path_a.dense_pe(sdp["pe_layer.positional_encoding_gaussian_matrix"], g, g)[None]
+        stats(f"dense_pe g{g}", pe.reshape(256, -1).cpu(), pe_ref.reshape(256, -1), 1e-4)
+        for mm in (False, True):
+            masks, iou = dec(emb, pe, sparse, dense, mm, 0)
+            torch.cuda.synchronize()
+            rm, ri = path_a.mask_decoder_multiscale(sdd, emb.bfloat16().float().cpu(), pe_ref, sparse.cpu(), dense.cpu(), mm, 0)
+            stats(f"decoder g{g} S{S} multimask={mm} masks", masks.reshape(masks.shape[0] * masks.shape[1], -1).cpu(), rm.reshape(rm.shape[0] * rm.shape[1], -1), 2e-2)
+            stats(f"decoder g{g} S{S} multimask={mm} iou", iou.cpu(), ri, 2e-2)
+
+def t_post():
+    from walkgpt_b200.modules import postprocess_masks_fused, postprocess_masks
+    from oracle import path_a
+    low = torch.randn(5, 1, 64, 64, device=dev) * 3
+    for inp, orig in [((448, 448), (448, 448)), ((252, 448), (360, 640)), ((448, 301), (517, 347))]:
+        lg, mk, sc = postprocess_masks_fused(low[:, 0].contiguous(), inp, orig)
+        torch.cuda.synchronize()
+        ref = path_a.postprocess_masks(low.cpu(), inp, orig)[:, 0]
+        stats(f"postprocess {inp}->{orig} logits", lg.reshape(5, -1).cpu(), ref.reshape(5, -1), 1e-5)
+        stats(f"postprocess {inp}->{orig} score", sc.cpu()[None], path_a.mask_score(ref)[None], 1e-4)
+        mism = (mk.cpu().bool() != (ref > 0)).sum().item()
+        print(f"     mask mismatches: {mism} / {mk.numel()}")
+    low_b = torch.randn(2, 1, 256, 256, device=dev) * 3
+    lg, _, _ = postprocess_masks_fused(low_b[:, 0].contiguous(), (768, 1024), (480, 640), target_size=1024)
+    ref = path_a.postprocess_masks(low_b.cpu(), (768, 1024), (480, 640), target_size=1024, cast_back=False)[:, 0]
+    stats("postprocess SAM 256->1024->crop->480x640", lg.reshape(2, -1).cpu(), ref.reshape(2, -1), 1e-5)
+    low = torch.randn(64 * 12, 64, 64, device=dev)
+    for _ in range(3): postprocess_masks_fused(low, (448, 448), (448, 448))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): postprocess_masks_fused(low, (448, 448), (448, 448))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    byts = 768 * (64 * 64 * 4 + 448 * 448 * 5)
+    print(f"time postprocess 768 masks (incl. torch.empty): {ms:.3f} ms -> {byts/ms/1e6:.1f} GB/s", flush=True)
+
+def t_path():
+    from walkgpt_b200.modules import GroundingPath
+    from oracle import path_a
+    B, S, H = 2, 3, 4096
+    m = GroundingPath(hidden_size=H, clip_layers=24, seed=1).cuda()
+    px = torch.randn(B, 3, 448, 448, device=dev)
+    seg = torch.randn(B * S, H, device=dev)
+    offs = [0, S, 2 * S]
+    out = m(px, seg, offs)
+    torch.cuda.synchronize()
+    def sub(prefix):
+        mod = dict(m.named_children())
+        return None
+    W = {
+        "clip": _sd_cpu(m.vision_tower), "msqp": _sd_cpu(m.msqp),
+        "proj": {k[len("out_mm_projector."):]: v for k, v in _sd_cpu(m.proj_neck).items() if k.startswith("out_mm_projector.")},
+        "neck": {k[len("image_feature_neck."):]: v for k, v in _sd_cpu(m.proj_neck).items() if k.startswith("image_feature_neck.")},
+        "ctp": _sd_cpu(m.text_hidden_fcs[0]), "prompt": _sd_cpu(m.prompt_encoder), "decoder": _sd_cpu(m.mask_decoder),
+    }
+    ref = path_a.path_a_forward(W, px.bfloat16().float().cpu(), seg.cpu(), offs)
+    stats("path vis_tokens", out["vis_tokens"].reshape(-1, H).float().cpu(), ref["vis_tokens"].reshape(-1, H), 3e-2)
+    stats("path txt_emb", out["txt_emb"].cpu(), ref["txt_emb"], 2e-2)
+    emb_ref = ref["img_emb"].flatten(2).permute(0, 2, 1).reshape(-1, 256)
+    stats("path img_emb", out["img_emb_tokens"].reshape(-1, 256).float().cpu(), emb_ref, 3e-2)
+    stats("path low_res", out["low_res"].reshape(B * S, -1).cpu(), ref["low_res"].reshape(B * S, -1), 3e-2)
+    stats("path iou", out["iou"].cpu(), ref["iou"], 3e-2)
+    stats("path logits", out["logits"].reshape(B * S, -1).cpu(), ref["logits"].reshape(B * S, -1), 3e-2)
+    err = (out["logits"].cpu() - ref["logits"]).abs().max().item()
+    a, b = out["masks"].cpu().bool(), ref["logits"] > 0
+    iou = ((a & b).flatten(1).sum(1).float() / ((a | b).flatten(1).sum(1).float() + 1e-9))
+    print(f"     logits max-abs err {err:.4e} (gate 2e-2); logit absmax {ref['logits'].abs().max().item():.3f}; per-mask IoU {iou.tolist()} (gate 0.995)")
+    print("     scores", out["scores"].cpu().tolist(), ref["scores"].tolist())
+    print("     depth", out["depth"].cpu().tolist())
+    # throughput, config 2: B=64, S=3
+    B, S = 64, 3
+    px = torch.randn(B, 3, 448, 448, device=dev).bfloat16(); seg = torch.randn(B * S, H, device=dev).bfloat16()
+    offs = list(range(0, B * S + 1, S))
+    for _ in range(2): m(px, seg, offs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3): m(px, seg, offs)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"time full path B64 S3: {ms:.2f} ms -> {B/ms*1e3:.1f} img/s ({B*800.7/ms:.1f} TFLOP/s)", flush=True)
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "ln", "attn", "clip"]
     print(torch.cuda.get_device_name(0), flush=True)
     for w in which:
         print(f"===== {w} =====", flush=True)
         try:
-            {"gemm": t_gemm, "ln": t_ln, "attn": t_attn, "clip": t_clip}[w]()
+            {"gemm": t_gemm, "ln": t_ln, "attn": t_attn, "clip": t_clip, "ctp": t_ctp, "msqp": t_msqp, "projneck": t_projneck, "decoder": t_decoder, "post": t_post, "path": t_path}[w]()
         except Exception as e:
             print("EXC in", w, repr(e)); traceback.print_exc()

@@ -1,60 +1,92 @@
 """ctypes binding of the C ABI in ``include/walkgpt_b200.h`` (``libwalkgpt_b200.so``).
 
-There is deliberately no fallback: if the shared library is missing, or the device is not an
+The struct layouts and function prototypes are PARSED FROM THE HEADER at import time, so the Python side cannot
+drift from the ABI.  There is deliberately no fallback: if the shared library is missing, or the device is not an
 sm_100 GPU, every op raises.
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional
+import re
+from typing import Dict, List, Optional, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwalkgpt_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "walkgpt_b200.h")
 
 WG_OK = 0
-ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
-OUT_BF16, OUT_F32, OUT_BF16_LN = 0, 1, 2
 
-vp = C.c_void_p
-fp = C.c_void_p  # const float* (device) -- passed as raw address
+_SCALARS = {"int32_t": C.c_int32, "int": C.c_int, "int64_t": C.c_int64, "size_t": C.c_size_t, "float": C.c_float,
+            "uint8_t": C.c_uint8}
 
-
-class GemmArgs(C.Structure):
-    _fields_ = [
-        ("A", vp), ("lda", C.c_int64), ("W", vp), ("ldw", C.c_int64),
-        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
-        ("bias", fp), ("bias_period", C.c_int32), ("act", C.c_int32), ("out_mode", C.c_int32),
-        ("out", vp), ("ldo", C.c_int64), ("resid", vp), ("ln_gamma", fp), ("ln_beta", fp),
-        ("ln_eps", C.c_float), ("reserved", C.c_int32),
-    ]
+STRUCTS: Dict[str, type] = {}
+CONSTANTS: Dict[str, int] = {}
+_PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {}
 
 
-class ClipLayer(C.Structure):
-    _fields_ = [(n, vp) for n in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b",
-                                  "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+def _strip_comments(src: str) -> str:
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    return re.sub(r"//[^\n]*", " ", src)
 
 
-class ClipWeights(C.Structure):
-    _fields_ = [
-        ("hidden", C.c_int32), ("heads", C.c_int32), ("mlp", C.c_int32), ("image", C.c_int32), ("patch", C.c_int32),
-        ("kpad", C.c_int32), ("n_layers", C.c_int32), ("reserved", C.c_int32),
-        ("patch_w", vp), ("cls_emb", fp), ("pos_emb", fp), ("pre_ln_g", fp), ("pre_ln_b", fp),
-        ("layers", C.POINTER(ClipLayer)),
-    ]
+def _parse_header(path: str) -> None:
+    src = _strip_comments(open(path).read())
+    for m in re.finditer(r"#define\s+(WG_\w+)\s+\(?(-?\d+)\)?\s*$", src, flags=re.M):
+        CONSTANTS[m.group(1)] = int(m.group(2))
+    for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", src, flags=re.S):
+        name, body = m.group(3), m.group(2)
+        fields: List[Tuple[str, object]] = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            if "*" in decl:  # pointer field(s): "const T* a" (one per declaration in this header)
+                fname = decl.split("*")[-1].strip()
+                fields.append((fname, C.c_void_p))
+                continue
+            am = re.match(r"(\w+)\s+(\w+)\[(\d+)\]$", decl)
+            if am:  # nested struct array
+                fields.append((am.group(2), STRUCTS[am.group(1)] * int(am.group(3))))
+                continue
+            parts = decl.split(" ", 1)
+            ctype = _SCALARS[parts[0]]
+            for fname in parts[1].split(","):
+                fields.append((fname.strip(), ctype))
+        STRUCTS[name] = type(name, (C.Structure,), {"_fields_": fields})
+    for m in re.finditer(r"WG_API\s+([\w\s\*]+?)\s*(wg_\w+)\s*\((.*?)\)\s*;", src, flags=re.S):
+        ret_s, fname, args_s = " ".join(m.group(1).split()), m.group(2), " ".join(m.group(3).split())
+        if "*" in ret_s:
+            ret = C.c_char_p
+        else:
+            ret = _SCALARS[ret_s]
+        args: List[object] = []
+        if args_s and args_s != "void":
+            for a in args_s.split(","):
+                a = a.strip()
+                if "*" in a:
+                    args.append(C.c_void_p)
+                else:
+                    args.append(_SCALARS[a.replace("const ", "").split(" ")[0]])
+        _PROTOTYPES[fname] = (ret, args)
 
 
-_PROTOTYPES = {
-    "wg_version": (C.c_int, []),
-    "wg_last_error": (C.c_char_p, []),
-    "wg_device_check": (C.c_int, [C.c_int]),
-    "wg_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
-    "wg_layernorm": (C.c_int, [vp, C.c_int, C.c_int64, fp, fp, C.c_float, vp, C.c_int64, C.c_int64, C.c_int, vp]),
-    "wg_attention_d64": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]),
-    "wg_clip_workspace_bytes": (C.c_size_t, [C.POINTER(ClipWeights), C.c_int]),
-    "wg_clip_forward": (C.c_int, [C.POINTER(ClipWeights), vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int,
-                                  vp, C.c_size_t, vp]),
-}
+_parse_header(HEADER_PATH)
+
+ACT_NONE, ACT_QUICK_GELU = CONSTANTS["WG_ACT_NONE"], CONSTANTS["WG_ACT_QUICK_GELU"]
+ACT_GELU_ERF, ACT_RELU = CONSTANTS["WG_ACT_GELU_ERF"], CONSTANTS["WG_ACT_RELU"]
+OUT_BF16, OUT_F32, OUT_BF16_LN = CONSTANTS["WG_OUT_BF16"], CONSTANTS["WG_OUT_F32"], CONSTANTS["WG_OUT_BF16_LN"]
+
+GemmArgs = STRUCTS["wg_gemm_args"]
+ClipLayer = STRUCTS["wg_clip_layer"]
+ClipWeights = STRUCTS["wg_clip_weights"]
+MsqpBlock = STRUCTS["wg_msqp_block"]
+MsqpScale = STRUCTS["wg_msqp_scale"]
+MsqpWeights = STRUCTS["wg_msqp_weights"]
+CtpWeights = STRUCTS["wg_ctp_weights"]
+ProjNeckWeights = STRUCTS["wg_proj_neck_weights"]
+TwoWayLayer = STRUCTS["wg_twoway_layer"]
+MaskDecoderWeights = STRUCTS["wg_mask_decoder_weights"]
 
 _lib: Optional[C.CDLL] = None
 
@@ -73,14 +105,15 @@ def lib() -> C.CDLL:
                 "(or `make -C walkgpt_b200/csrc`).  walkgpt_b200 has no CPU / PyTorch fallback.")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _PROTOTYPES.items():
-            fn = getattr(handle, name)
+            fn = getattr(handle, name)  # AttributeError here == header declares a symbol the library lacks
             fn.restype = res
             fn.argtypes = args
         _lib = handle
     return _lib
 
 
-def exported_symbols():
+def exported_symbols() -> List[str]:
+    """Every function the header declares."""
     return sorted(_PROTOTYPES)
 
 

@@ -1,0 +1,254 @@
+// Bandwidth-bound tails:
+//   A8  postprocess_masks: bilinear(align_corners=False) low-res logits -> T x T, crop to input_size, bilinear -> original_size
+//       (model/walkgpt.py:749-790 with vision_tower_for_mask=True; segment_anything/modeling/sam.py:137-172)
+//   A9  binary mask = logits > 0 and mask_score = sum(sigmoid(m) * [m>0]) / (sum([m>0]) + 1e-6)  (model/walkgpt.py:541,742)
+//   A10 relative-depth head -- THIS REPO'S EXTENSION (no reference implementation exists; see oracle/path_a.py:depth_head).
+// The last resize is fused with the threshold, the u8 mask write and the score reduction: each logit is written once
+// (16-byte stores) and never re-read.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace wg {
+namespace {
+
+// PyTorch upsample_bilinear2d source index (align_corners = False)
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+    float s = fmaxf(scale * (dst + 0.5f) - 0.5f, 0.f);
+    i0 = (int)s;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = s - (float)i0;
+}
+
+// dst[n, y, x] = bilinear(src[n]) for y < dh, x < dw, where the virtual full output is (full_h, full_w) (crop = top-left).
+// VEC consecutive x per thread.  SCORE: also write the u8 mask and accumulate (sum sigmoid*[>0], count [>0]) per mask.
+template <int VEC, bool SCORE>
+__global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__ src, int sh, int sw, float* __restrict__ dst, int dh, int dw,
+                                                       float scale_y, float scale_x, uint8_t* __restrict__ mask, float* __restrict__ accum) {
+    const int n = blockIdx.z;
+    const int y = blockIdx.y;
+    const int xg = blockIdx.x * blockDim.x + threadIdx.x;  // group of VEC pixels
+    const int x0 = xg * VEC;
+    float ssum = 0.f, scnt = 0.f;
+    if (x0 < dw) {
+        int y0, y1;
+        float ly;
+        src_index(y, scale_y, sh, y0, y1, ly);
+        const float* r0 = src + ((size_t)n * sh + y0) * sw;
+        const float* r1 = src + ((size_t)n * sh + y1) * sw;
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int x = x0 + v;
+            int xa, xb;
+            float lx;
+            src_index(x < dw ? x : dw - 1, scale_x, sw, xa, xb, lx);
+            const float top = (1.f - lx) * __ldg(r0 + xa) + lx * __ldg(r0 + xb);
+            const float bot = (1.f - lx) * __ldg(r1 + xa) + lx * __ldg(r1 + xb);
+            o[v] = (1.f - ly) * top + ly * bot;
+        }
+        const size_t off = ((size_t)n * dh + y) * dw + x0;
+        if (VEC == 4 && x0 + 3 < dw) {
+            *reinterpret_cast<float4*>(dst + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (SCORE && mask) {
+                uchar4 m;
+                m.x = o[0] > 0.f; m.y = o[1] > 0.f; m.z = o[2] > 0.f; m.w = o[3] > 0.f;
+                *reinterpret_cast<uchar4*>(mask + off) = m;
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (x0 + v < dw) {
+                    dst[off + v] = o[v];
+                    if (SCORE && mask) mask[off + v] = o[v] > 0.f;
+                }
+        }
+        if (SCORE) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (x0 + v < dw && o[v] > 0.f) {
+                    ssum += 1.0f / (1.0f + __expf(-o[v]));
+                    scnt += 1.f;
+                }
+        }
+    }
+    if (SCORE) {
+        __shared__ float red[2][8];
+        ssum = warp_sum(ssum);
+        scnt = warp_sum(scnt);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) {
+            red[0][warp] = ssum;
+            red[1][warp] = scnt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+                a += red[0][i];
+                b += red[1][i];
+            }
+            if (b > 0.f) {
+                atomicAdd(accum + 2 * n, a);
+                atomicAdd(accum + 2 * n + 1, b);
+            }
+        }
+    }
+}
+
+__global__ void finalize_score_kernel(const float* __restrict__ accum, float* __restrict__ score, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) score[i] = accum[2 * i] / (accum[2 * i + 1] + 1e-6f);
+}
+
+// depth extension: pooled [P][33] -> raw[p] = W2 . gelu(W1 . pooled_c + b1) + b2 ; min-max normalised inside each image
+__global__ void __launch_bounds__(256) depth_head_kernel(const float* __restrict__ pooled, const int* __restrict__ seg_offsets, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         float* __restrict__ depth) {
+    extern __shared__ float raw[];  // [S]
+    __shared__ float red[8];
+    const int img = blockIdx.x;
+    const int p0 = seg_offsets[img], p1 = seg_offsets[img + 1];
+    const int S = p1 - p0;
+    if (S <= 0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int sidx = 0; sidx < S; ++sidx) {
+        const float* pp = pooled + (size_t)(p0 + sidx) * 33;
+        const float inv = 1.0f / (pp[32] + 1e-6f);
+        float h = b1[tid];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) h = fmaf(w1[tid * 32 + c], pp[c] * inv, h);
+        float part = warp_sum(gelu_erf(h) * w2[tid]);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            float t = b2[0];
+            for (int i = 0; i < 8; ++i) t += red[i];
+            raw[sidx] = t;
+        }
+        __syncthreads();
+    }
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = 0; i < S; ++i) {
+        lo = fminf(lo, raw[i]);
+        hi = fmaxf(hi, raw[i]);
+    }
+    for (int i = tid; i < S; i += 256) depth[p0 + i] = (raw[i] - lo) / (hi - lo + 1e-6f);
+}
+
+
+// PositionEmbeddingRandom.forward((h,w)) (prompt_encoder.py:216-229): out[c, y, x], c < 2F: sin | cos of 2*pi*((2*coord-1) @ gauss)
+__global__ void dense_pe_kernel(const float* __restrict__ gauss, int F, int h, int w, float* __restrict__ out_chw, float* __restrict__ out_tok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * h * w) return;
+    const int f = i / (h * w), pos = i % (h * w);
+    const int y = pos / w, x = pos % w;
+    const float cx = 2.f * ((x + 0.5f) / w) - 1.f, cy = 2.f * ((y + 0.5f) / h) - 1.f;
+    const float a = 6.283185307179586f * (cx * gauss[f] + cy * gauss[F + f]);
+    const float sv = sinf(a), cv = cosf(a);
+    if (out_chw) {
+        out_chw[(size_t)f * h * w + pos] = sv;
+        out_chw[(size_t)(F + f) * h * w + pos] = cv;
+    }
+    if (out_tok) {
+        out_tok[(size_t)pos * 2 * F + f] = sv;
+        out_tok[(size_t)pos * 2 * F + F + f] = cv;
+    }
+}
+
+template <bool SCORE>
+int launch_bilinear(const float* src, int n, int sh, int sw, float* dst, int dh, int dw, int full_h, int full_w, uint8_t* mask, float* accum,
+                    cudaStream_t s) {
+    const float sy = (float)sh / (float)full_h, sx = (float)sw / (float)full_w;
+    if (dw % 4 == 0) {
+        const int groups = dw / 4;
+        const int threads = groups >= 128 ? 128 : ((groups + 31) / 32) * 32;
+        dim3 grid((groups + threads - 1) / threads, dh, n);
+        bilinear_kernel<4, SCORE><<<grid, threads, 0, s>>>(src, sh, sw, dst, dh, dw, sy, sx, mask, accum);
+    } else {
+        const int threads = dw >= 256 ? 256 : ((dw + 31) / 32) * 32;
+        dim3 grid((dw + threads - 1) / threads, dh, n);
+        bilinear_kernel<1, SCORE><<<grid, threads, 0, s>>>(src, sh, sw, dst, dh, dw, sy, sx, mask, accum);
+    }
+    WG_CHECK_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+}  // namespace
+}  // namespace wg
+
+using namespace wg;
+
+extern "C" size_t wg_postprocess_workspace_bytes(int n_masks, int in_h, int in_w) {
+    Workspace ws(nullptr, 0);
+    ws.take((size_t)n_masks * 2 * sizeof(float));
+    ws.take((size_t)n_masks * in_h * in_w * sizeof(float));
+    return ws.used();
+}
+
+extern "C" int wg_postprocess_masks(const float* low_res, int n_masks, int Hm, int Wm, int target, int in_h, int in_w, int out_h, int out_w,
+                                    float* logits_out, uint8_t* mask_out, float* score_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    if (n_masks == 0) return WG_OK;
+    WG_REQUIRE(low_res && logits_out && workspace, "wg_postprocess_masks: null pointer");
+    WG_REQUIRE(n_masks > 0 && n_masks <= 65535 && Hm > 0 && Wm > 0, "wg_postprocess_masks: bad sizes");
+    WG_REQUIRE(in_h > 0 && in_w > 0 && in_h <= target && in_w <= target, "wg_postprocess_masks: input_size (%d,%d) must fit target %d", in_h, in_w,
+               target);  // asserts at model/walkgpt.py:781-782
+    WG_REQUIRE(out_h > 0 && out_w > 0 && out_h <= 65535 && in_h <= 65535, "wg_postprocess_masks: bad output size");
+    if (!device_is_sm100()) {
+        set_error("wg_postprocess_masks: this library only runs on sm_100 (B200) devices; there is no fallback");
+        return WG_ERR_UNSUPPORTED;
+    }
+    Workspace ws(workspace, workspace_bytes);
+    float* accum = static_cast<float*>(ws.take((size_t)n_masks * 2 * sizeof(float)));
+    float* mid = static_cast<float*>(ws.take((size_t)n_masks * in_h * in_w * sizeof(float)));
+    WG_REQUIRE(accum && mid, "wg_postprocess_masks: workspace too small");
+    const bool want_score = score_out != nullptr || mask_out != nullptr;
+    if (want_score) WG_CHECK_CUDA(cudaMemsetAsync(accum, 0, (size_t)n_masks * 2 * sizeof(float), s));
+    if (in_h == out_h && in_w == out_w) {
+        // the second interpolation is the identity (scale 1 => lambda 0): one fused pass
+        if (want_score)
+            WG_TRY(launch_bilinear<true>(low_res, n_masks, Hm, Wm, logits_out, in_h, in_w, target, target, mask_out, accum, s));
+        else
+            WG_TRY(launch_bilinear<false>(low_res, n_masks, Hm, Wm, logits_out, in_h, in_w, target, target, nullptr, nullptr, s));
+    } else {
+        WG_TRY(launch_bilinear<false>(low_res, n_masks, Hm, Wm, mid, in_h, in_w, target, target, nullptr, nullptr, s));
+        if (want_score)
+            WG_TRY(launch_bilinear<true>(mid, n_masks, in_h, in_w, logits_out, out_h, out_w, out_h, out_w, mask_out, accum, s));
+        else
+            WG_TRY(launch_bilinear<false>(mid, n_masks, in_h, in_w, logits_out, out_h, out_w, out_h, out_w, nullptr, nullptr, s));
+    }
+    if (score_out) {
+        finalize_score_kernel<<<(n_masks + 255) / 256, 256, 0, s>>>(accum, score_out, n_masks);
+        WG_CHECK_CUDA(cudaGetLastError());
+    }
+    return WG_OK;
+}
+
+extern "C" int wg_depth_head(const float* pooled, const int32_t* seg_offsets, int B, int max_S, const float* w1, const float* b1, const float* w2,
+                             const float* b2, float* depth_out, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    if (B == 0) return WG_OK;
+    WG_REQUIRE(pooled && seg_offsets && w1 && b1 && w2 && b2 && depth_out, "wg_depth_head: null pointer");
+    WG_REQUIRE(max_S >= 0 && max_S <= 8192, "wg_depth_head: max_S=%d out of range", max_S);
+    if (!device_is_sm100()) {
+        set_error("wg_depth_head: this library only runs on sm_100 (B200) devices; there is no fallback");
+        return WG_ERR_UNSUPPORTED;
+    }
+    depth_head_kernel<<<B, 256, (size_t)(max_S > 0 ? max_S : 1) * sizeof(float), s>>>(pooled, seg_offsets, w1, b1, w2, b2, depth_out);
+    WG_CHECK_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+extern "C" int wg_dense_pe(const float* gauss, int num_pos_feats, int h, int w, float* out_chw, float* out_tokens, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    WG_REQUIRE(gauss && (out_chw || out_tokens) && num_pos_feats > 0 && h > 0 && w > 0, "wg_dense_pe: bad arguments");
+    if (!device_is_sm100()) {
+        set_error("wg_dense_pe: this library only runs on sm_100 (B200) devices; there is no fallback");
+        return WG_ERR_UNSUPPORTED;
+    }
+    const int n = num_pos_feats * h * w;
+    dense_pe_kernel<<<(n + 255) / 256, 256, 0, s>>>(gauss, num_pos_feats, h, w, out_chw, out_tokens);
+    WG_CHECK_CUDA(cudaGetLastError());
+    return WG_OK;
+}

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import specs
 from .specs import Spec, init_tensor
 
 
@@ -218,7 +219,7 @@ class CLIPVisionTower(_SpecModule):
         w.cls_emb = hold(_f32(sd[p + "embeddings.class_embedding"]))
         w.pos_emb = hold(_f32(sd[p + "embeddings.position_embedding.weight"]))
         w.pre_ln_g, w.pre_ln_b = hold(_f32(sd[p + "pre_layrnorm.weight"])), hold(_f32(sd[p + "pre_layrnorm.bias"]))
-        w.layers = C.cast(layers, C.POINTER(_lib.ClipLayer))
+        w.layers = C.cast(layers, C.c_void_p)
         self._packed = (w, layers, keep)
         return self._packed
 
@@ -267,3 +268,614 @@ class CLIPVisionTower(_SpecModule):
         else:
             last, mid = out_lo, out_hi
         return last.to(out_dtype), [mid.to(out_dtype)]
+
+
+class _Holder:
+    """Keeps repacked device tensors alive for as long as a ctypes weight struct points at them."""
+
+    def __init__(self):
+        self.keep: List[torch.Tensor] = []
+
+    def __call__(self, t: torch.Tensor) -> int:
+        self.keep.append(t)
+        return t.data_ptr()
+
+    def bf16(self, t):
+        return self(_bf16(t))
+
+    def f32(self, t):
+        return self(_f32(t))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, who: str) -> None:
+    if not t.is_cuda:
+        raise _lib.WalkGPTB200Error(f"{who} needs CUDA tensors (walkgpt_b200 has no CPU fallback)")
+
+
+def _as_kernel_input(x: torch.Tensor) -> torch.Tensor:
+    """fp32/bf16 contiguous (other float types are widened to fp32)."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return x.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# A2  MSQP
+# --------------------------------------------------------------------------------------------------
+class MultiScaleQFormerProjector(_SpecModule):
+    """Drop-in for ``MultiScaleQFormerProjector`` (utils/utils_walkgpt.py:220-300)."""
+
+    _GROUPS = (("q_x1", "cross_x1"), ("q_x2", "cross_x2"), ("q_x4", "cross_x4"), ("q_global", "cross_glb"))
+
+    def __init__(self, sam_dim, llama_dim, grid_size=None, num_heads=8, pad_to_square: bool = True,
+                 target_square_side: Optional[int] = None, *, seed=0):
+        super().__init__()
+        if num_heads != 8:
+            raise ValueError("MultiScaleQFormerProjector: the CUDA path is built for num_heads=8")
+        self.grid_size = grid_size
+        self.d_proj = 1024
+        self.num_layers = 2
+        self.pad_to_square = pad_to_square
+        self.target_square_side = target_square_side
+        self.sam_dim, self.llama_dim = sam_dim, llama_dim
+        self._build(specs.msqp_spec(sam_dim, llama_dim), seed)
+        self._ws = _Workspace()
+
+    def n_tokens(self) -> int:
+        q = 32
+        if not self.pad_to_square:
+            return q
+        s = int(math.ceil(math.sqrt(q))) if self.target_square_side is None else self.target_square_side
+        assert s * s >= q, "target_square_side too small"  # utils_walkgpt.py:294
+        return s * s
+
+    def _pack(self):
+        sd, hold, d = self._sd(), _Holder(), self.d_proj
+        w = _lib.MsqpWeights()
+        w.sam_dim, w.llama_dim, w.d, w.heads, w.n_tokens = self.sam_dim, self.llama_dim, d, 8, self.n_tokens()
+        w.w_in, w.b_in = hold.bf16(sd["sam_to_proj.weight"]), hold.f32(sd["sam_to_proj.bias"])
+        w.gate_ln_g, w.gate_ln_b = hold.f32(sd["gate.net.0.weight"]), hold.f32(sd["gate.net.0.bias"])
+        w.w_g1, w.b_g1 = hold.bf16(sd["gate.net.1.weight"]), hold.f32(sd["gate.net.1.bias"])
+        w.w_g2, w.b_g2 = hold.f32(sd["gate.net.3.weight"].reshape(-1)), hold.f32(sd["gate.net.3.bias"])
+        w.pad_token = hold.f32(sd["pad_token"].reshape(-1))
+        w.w_out, w.b_out = hold.bf16(sd["to_llama.weight"]), hold.f32(sd["to_llama.bias"])
+        for si, (qn, cn) in enumerate(self._GROUPS):
+            S = w.scales[si]
+            S.queries, S.nq = hold.f32(sd[qn][0]), sd[qn].shape[1]
+            wk, bk = [], []
+            for l in range(2):
+                pre = f"{cn}.{l}."
+                W, b = sd[pre + "attn.in_proj_weight"].float(), sd[pre + "attn.in_proj_bias"].float()
+                g, be = sd[pre + "kv_norm.weight"].float(), sd[pre + "kv_norm.bias"].float()
+                Wkv = W[d:]                       # K rows then V rows
+                wk.append(Wkv * g[None, :])       # fold kv_norm scale into the columns
+                bk.append(b[d:] + Wkv @ be)       # and its shift into the bias
+                Bk = S.blocks[l]
+                Bk.qn_g, Bk.qn_b = hold.f32(sd[pre + "q_norm.weight"]), hold.f32(sd[pre + "q_norm.bias"])
+                Bk.w_q, Bk.b_q = hold.bf16(W[:d]), hold.f32(b[:d])
+                Bk.w_o, Bk.b_o = hold.bf16(sd[pre + "attn.out_proj.weight"]), hold.f32(sd[pre + "attn.out_proj.bias"])
+                Bk.ffn_ln_g, Bk.ffn_ln_b = hold.f32(sd[pre + "ffn.0.weight"]), hold.f32(sd[pre + "ffn.0.bias"])
+                Bk.w_f1, Bk.b_f1 = hold.bf16(sd[pre + "ffn.1.weight"]), hold.f32(sd[pre + "ffn.1.bias"])
+                Bk.w_f2, Bk.b_f2 = hold.bf16(sd[pre + "ffn.3.weight"]), hold.f32(sd[pre + "ffn.3.bias"])
+            S.w_kv, S.b_kv = hold.bf16(torch.cat(wk, 0)), hold.f32(torch.cat(bk, 0))
+        self._packed = (w, hold)
+        return self._packed
+
+    def run(self, feats_bf16: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+        """feats bf16 [B, L, sam_dim] contiguous -> [B, n_tokens, llama_dim]."""
+        B, L, _ = feats_bf16.shape
+        w, _ = self._packed or self._pack()
+        out = torch.empty(B, self.n_tokens(), self.llama_dim, device=feats_bf16.device, dtype=out_dtype)
+        ws = self._ws.get(_lib.lib().wg_msqp_workspace_bytes(C.byref(w), B, L), feats_bf16.device)
+        _lib.check(_lib.lib().wg_msqp_forward(C.byref(w), feats_bf16.data_ptr(), B, L, out.data_ptr(), int(out_dtype == torch.bfloat16),
+                                              ws.data_ptr(), ws.numel(), _stream()), "wg_msqp_forward")
+        return out
+
+    @torch.no_grad()
+    def forward(self, sam_feats, grid_size=None):
+        _need_cuda(sam_feats, "MultiScaleQFormerProjector.forward")
+        B, L, _ = sam_feats.shape
+        hw = grid_size or self.grid_size
+        if hw is not None and (hw[0] != hw[1] or hw[0] * hw[1] != L):
+            raise ValueError("MultiScaleQFormerProjector: only square token grids are built")
+        if int(math.isqrt(L)) ** 2 != L:
+            raise ValueError(f"Token length {L} is not a perfect square.")  # utils_walkgpt.py:188-192
+        out_dtype = sam_feats.dtype if sam_feats.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        with torch.cuda.device(sam_feats.device):
+            out = self.run(sam_feats.to(torch.bfloat16).contiguous(), out_dtype)
+        return out.to(sam_feats.dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# A5  CTP
+# --------------------------------------------------------------------------------------------------
+class CalibratedTextProjector(_SpecModule):
+    """Drop-in for ``CalibratedTextProjector`` (utils/utils_walkgpt.py:302-327)."""
+
+    def __init__(self, in_dim: int, out_dim: int, widen: int = 2, use_residual: bool = False, *, seed=0):
+        super().__init__()
+        if out_dim != 256 or widen != 2:
+            raise ValueError("CalibratedTextProjector: the CUDA path is built for out_dim=256, widen=2 (model/walkgpt.py:141)")
+        self.use_residual = use_residual and (in_dim == out_dim)
+        if self.use_residual:
+            raise ValueError("CalibratedTextProjector: use_residual=True is not on the reference's path")
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self._build(specs.ctp_spec(in_dim, out_dim, widen), seed)
+        self._ws = _Workspace()
+
+    def _pack(self):
+        sd, hold = self._sd(), _Holder()
+        w = _lib.CtpWeights()
+        w.in_dim, w.mid_dim, w.out_dim = self.in_dim, 2 * self.out_dim, self.out_dim
+        w.ln0_g, w.ln0_b = hold.f32(sd["net.0.weight"]), hold.f32(sd["net.0.bias"])
+        w.w1, w.b1 = hold.bf16(sd["net.1.weight"]), hold.f32(sd["net.1.bias"])
+        w.w2, w.b2 = hold.bf16(sd["net.3.weight"]), hold.f32(sd["net.3.bias"])
+        w.ln4_g, w.ln4_b = hold.f32(sd["net.4.weight"]), hold.f32(sd["net.4.bias"])
+        w.text_type, w.log_temp = hold.f32(sd["text_type"].reshape(-1)), hold.f32(sd["log_temp"])
+        self._packed = (w, hold)
+        return self._packed
+
+    def run(self, x2d: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
+        """x [rows, in_dim] fp32/bf16 contiguous -> [rows, 256]."""
+        rows = x2d.shape[0]
+        w, _ = self._packed or self._pack()
+        out = torch.empty(rows, self.out_dim, device=x2d.device, dtype=out_dtype)
+        if rows == 0:
+            return out
+        ws = self._ws.get(_lib.lib().wg_ctp_workspace_bytes(rows, self.in_dim), x2d.device)
+        _lib.check(_lib.lib().wg_ctp_forward(C.byref(w), x2d.data_ptr(), int(x2d.dtype == torch.bfloat16), rows, out.data_ptr(),
+                                             int(out_dtype == torch.bfloat16), ws.data_ptr(), ws.numel(), _stream()), "wg_ctp_forward")
+        return out
+
+    @torch.no_grad()
+    def forward(self, x):
+        _need_cuda(x, "CalibratedTextProjector.forward")
+        xin = _as_kernel_input(x)
+        lead = xin.shape[:-1]
+        with torch.cuda.device(x.device):
+            y = self.run(xin.reshape(-1, self.in_dim), xin.dtype)
+        # text_type is [1,1,out]: a 2-D input comes back 3-D, exactly like the reference (SURVEY §0)
+        shape = torch.broadcast_shapes(tuple(lead) + (self.out_dim,), (1, 1, self.out_dim))
+        return y.reshape(shape).to(x.dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# A3 + A4  out_mm_projector MLP and image_feature_neck
+# --------------------------------------------------------------------------------------------------
+class ProjectorNeck(_SpecModule):
+    """``out_mm_projector`` (llava_arch.py:38-42) + ``image_feature_neck`` (model/walkgpt.py:97-113) as one module.
+
+    Parameters live under ``out_mm_projector.*`` and ``image_feature_neck.*`` with the reference's names."""
+
+    def __init__(self, mm_hidden: int, hidden: int, out_chans: int = 256, *, seed=0):
+        super().__init__()
+        self.mm_hidden, self.hidden, self.out_chans = mm_hidden, hidden, out_chans
+        spec: Spec = {}
+        spec.update({"out_mm_projector." + k: v for k, v in specs.out_mm_projector_spec(mm_hidden, hidden).items()})
+        spec.update({"image_feature_neck." + k: v for k, v in specs.neck_spec(hidden, out_chans).items()})
+        self._build(spec, seed)
+        self._ws = _Workspace()
+
+    def _pack(self):
+        sd, hold = self._sd(), _Holder()
+        w = _lib.ProjNeckWeights()
+        w.mm_hidden, w.hidden, w.out_chans = self.mm_hidden, self.hidden, self.out_chans
+        w.w_fc1, w.b_fc1 = hold.bf16(sd["out_mm_projector.0.weight"]), hold.f32(sd["out_mm_projector.0.bias"])
+        w.w_fc2, w.b_fc2 = hold.bf16(sd["out_mm_projector.2.weight"]), hold.f32(sd["out_mm_projector.2.bias"])
+        w.w_conv1 = hold.bf16(sd["image_feature_neck.0.weight"].reshape(self.out_chans, self.hidden))
+        w.ln1_g, w.ln1_b = hold.f32(sd["image_feature_neck.1.weight"]), hold.f32(sd["image_feature_neck.1.bias"])
+        # [co, ci, ky, kx] -> [co, (ky, kx, ci)]: matches the channels-last im2col column order
+        w.w_conv3 = hold.bf16(sd["image_feature_neck.2.weight"].permute(0, 2, 3, 1).reshape(self.out_chans, -1))
+        w.ln2_g, w.ln2_b = hold.f32(sd["image_feature_neck.3.weight"]), hold.f32(sd["image_feature_neck.3.bias"])
+        self._packed = (w, hold)
+        return self._packed
+
+    def run(self, feats_bf16: torch.Tensor, want_proj: bool = False, want_emb: bool = True):
+        """feats bf16 [B, L, mm_hidden] -> (proj bf16 [B,L,H] | None, emb tokens bf16 [B,L,256] | None)."""
+        B, L, _ = feats_bf16.shape
+        g = int(math.isqrt(L))
+        assert g * g == L
+        w, _ = self._packed or self._pack()
+        proj = torch.empty(B, L, self.hidden, device=feats_bf16.device, dtype=torch.bfloat16) if want_proj else None
+        emb = torch.empty(B, L, self.out_chans, device=feats_bf16.device, dtype=torch.bfloat16) if want_emb else None
+        ws = self._ws.get(_lib.lib().wg_proj_neck_workspace_bytes(C.byref(w), B * L), feats_bf16.device)
+        _lib.check(_lib.lib().wg_proj_neck_forward(C.byref(w), feats_bf16.data_ptr(), B, g, None if proj is None else proj.data_ptr(),
+                                                   None if emb is None else emb.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                   "wg_proj_neck_forward")
+        return proj, emb
+
+    @torch.no_grad()
+    def project(self, feats):
+        """out_mm_projector(feats): [B, L, mm_hidden] -> [B, L, hidden] (input dtype)."""
+        _need_cuda(feats, "ProjectorNeck.project")
+        with torch.cuda.device(feats.device):
+            proj, _ = self.run(feats.to(torch.bfloat16).contiguous(), want_proj=True, want_emb=False)
+        return proj.to(feats.dtype)
+
+    @torch.no_grad()
+    def neck(self, x_nchw):
+        """image_feature_neck(x): [B, hidden, g, g] -> [B, 256, g, g] (input dtype)."""
+        _need_cuda(x_nchw, "ProjectorNeck.neck")
+        B, Hd, gh, gw = x_nchw.shape
+        assert gh == gw and Hd == self.hidden
+        tokens = x_nchw.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()  # layout change only
+        w, _ = self._packed or self._pack()
+        emb = torch.empty(B, gh * gw, self.out_chans, device=x_nchw.device, dtype=torch.bfloat16)
+        with torch.cuda.device(x_nchw.device):
+            ws = self._ws.get(_lib.lib().wg_neck_workspace_bytes(B * gh * gw), x_nchw.device)
+            _lib.check(_lib.lib().wg_neck_forward(C.byref(w), tokens.data_ptr(), B, gh, emb.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                       "wg_neck_forward")
+            return tokens_to_nchw(emb, gh, gw, x_nchw.dtype)
+
+    @torch.no_grad()
+    def forward(self, feats):
+        """feats [B, L, mm_hidden] -> image embedding [B, 256, g, g] (input dtype)."""
+        _need_cuda(feats, "ProjectorNeck.forward")
+        g = int(math.isqrt(feats.shape[1]))
+        with torch.cuda.device(feats.device):
+            _, emb = self.run(feats.to(torch.bfloat16).contiguous())
+            return tokens_to_nchw(emb, g, g, feats.dtype)
+
+
+def tokens_to_nchw(tokens_bf16: torch.Tensor, h: int, w: int, dtype=torch.float32) -> torch.Tensor:
+    """[B, h*w, C] bf16 -> [B, C, h, w]."""
+    B, L, Cc = tokens_bf16.shape
+    kd = torch.bfloat16 if dtype == torch.bfloat16 else torch.float32
+    out = torch.empty(B, Cc, h, w, device=tokens_bf16.device, dtype=kd)
+    _lib.check(_lib.lib().wg_tokens_to_nchw(tokens_bf16.data_ptr(), out.data_ptr(), int(kd == torch.bfloat16), B, L, Cc, _stream()),
+               "wg_tokens_to_nchw")
+    return out.to(dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# A6  Prompt encoder
+# --------------------------------------------------------------------------------------------------
+class PromptEncoder(_SpecModule):
+    """Drop-in for ``PromptEncoder`` (segment_anything/modeling/prompt_encoder.py:16-186), text-prompt path only:
+    the reference only ever calls it with ``points=boxes=masks=None`` (model/walkgpt.py:515-520, 724-729)."""
+
+    def __init__(self, embed_dim: int, image_embedding_size: Tuple[int, int], input_image_size: Tuple[int, int], mask_in_chans: int,
+                 activation=None, *, seed=0):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.input_image_size = input_image_size
+        self.image_embedding_size = image_embedding_size
+        self._build(specs.prompt_encoder_spec(embed_dim, mask_in_chans), seed)
+        self._pe_cache = None
+
+    def _invalidate(self):
+        super()._invalidate()
+        self._pe_cache = None
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._pe_cache = None
+        return out
+
+    def dense_pe_tokens(self, size: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(pe [1, C, h, w] fp32, pe tokens [h*w, C] fp32), computed by the wg_dense_pe kernel and cached."""
+        h, w = size or self.image_embedding_size
+        gauss = self.pe_layer.positional_encoding_gaussian_matrix
+        key = (gauss.data_ptr(), gauss._version, h, w)
+        if self._pe_cache is None or self._pe_cache[0] != key:
+            _need_cuda(gauss, "PromptEncoder.get_dense_pe")
+            F_ = gauss.shape[1]
+            g32 = _f32(gauss)
+            chw = torch.empty(1, 2 * F_, h, w, device=gauss.device, dtype=torch.float32)
+            tok = torch.empty(h * w, 2 * F_, device=gauss.device, dtype=torch.float32)
+            with torch.cuda.device(gauss.device):
+                _lib.check(_lib.lib().wg_dense_pe(g32.data_ptr(), F_, h, w, chw.data_ptr(), tok.data_ptr(), _stream()), "wg_dense_pe")
+            self._pe_cache = (key, chw, tok)
+        return self._pe_cache[1], self._pe_cache[2]
+
+    def get_dense_pe(self) -> torch.Tensor:
+        return self.dense_pe_tokens()[0]
+
+    @torch.no_grad()
+    def forward(self, points, boxes, masks, text_embeds):
+        if points is not None or boxes is not None or masks is not None:
+            raise NotImplementedError("PromptEncoder: point / box / mask prompts are not on WalkGPT's path (text_embeds only)")
+        if text_embeds is None:
+            raise ValueError("PromptEncoder.forward: text_embeds is required")
+        bs = text_embeds.shape[0]
+        sparse = text_embeds  # torch.cat([empty, text_embeds], dim=1) in the reference (:165-177)
+        dense = self.no_mask_embed.weight.reshape(1, -1, 1, 1).expand(bs, -1, self.image_embedding_size[0], self.image_embedding_size[1])
+        return sparse, dense
+
+
+# --------------------------------------------------------------------------------------------------
+# A7  Mask decoder (multi-scale variant, level 0)
+# --------------------------------------------------------------------------------------------------
+class MaskDecoderMultiScale(_SpecModule):
+    """Drop-in for ``MaskDecoderMultiScale`` (segment_anything/modeling/mask_decoder_multi_scale.py:16-213).
+
+    ``transformer`` is accepted for signature compatibility; the two-way transformer's dimensions are fixed to the
+    reference's (depth 2, dim 256, 8 heads, mlp 2048; model/walkgpt.py:81-93).  Only ``level_num == 0`` is built."""
+
+    def __init__(self, *, transformer_dim: int = 256, transformer=None, num_multimask_outputs: int = 3, activation=None,
+                 iou_head_depth: int = 3, iou_head_hidden_dim: int = 256, image_feature_scale_num: int = 1, seed=0):
+        super().__init__()
+        if transformer_dim != 256 or num_multimask_outputs != 3 or iou_head_depth != 3 or iou_head_hidden_dim != 256:
+            raise ValueError("MaskDecoderMultiScale: the CUDA path is built for the reference's dimensions (256 / 3 / 3 / 256)")
+        self.transformer_dim = transformer_dim
+        self.num_multimask_outputs = num_multimask_outputs
+        self.num_mask_tokens = num_multimask_outputs + 1
+        self.image_feature_scale_num = image_feature_scale_num
+        self._build(specs.mask_decoder_multiscale_spec(transformer_dim, num_multimask_outputs, image_feature_scale_num), seed)
+        self._ws = _Workspace()
+        self._pe_key = None
+
+    def _pack_static(self):
+        sd, hold = self._sd(), _Holder()
+        w = _lib.MaskDecoderWeights()
+        w.n_mask_tokens, w.up_stages = self.num_mask_tokens, 1
+        lvl = sd["level_embed.weight"][0].float()
+        w.out_tokens = hold.f32(torch.cat([sd["iou_token.weight"], sd["mask_tokens.weight"]], 0).float() + lvl[None])
+        w.sparse_add = hold.f32(lvl)
+        T = "transformer.0."
+
+        def lin_t(name):  # transposed bf16 weight + fp32 bias
+            return hold.bf16(sd[name + ".weight"].t()), hold.f32(sd[name + ".bias"])
+
+        for l in range(2):
+            L, lp = w.layers[l], T + f"layers.{l}."
+            L.sa_wq_t, L.sa_bq = lin_t(lp + "self_attn.q_proj")
+            L.sa_wk_t, L.sa_bk = lin_t(lp + "self_attn.k_proj")
+            L.sa_wv_t, L.sa_bv = lin_t(lp + "self_attn.v_proj")
+            L.sa_wo_t, L.sa_bo = lin_t(lp + "self_attn.out_proj")
+            L.n1_g, L.n1_b = hold.f32(sd[lp + "norm1.weight"]), hold.f32(sd[lp + "norm1.bias"])
+            L.t2i_wq_t, L.t2i_bq = lin_t(lp + "cross_attn_token_to_image.q_proj")
+            L.t2i_wo_t, L.t2i_bo = lin_t(lp + "cross_attn_token_to_image.out_proj")
+            L.n2_g, L.n2_b = hold.f32(sd[lp + "norm2.weight"]), hold.f32(sd[lp + "norm2.bias"])
+            L.mlp_w1_t, L.mlp_b1 = lin_t(lp + "mlp.lin1")
+            L.mlp_w2_t, L.mlp_b2 = lin_t(lp + "mlp.lin2")
+            L.n3_g, L.n3_b = hold.f32(sd[lp + "norm3.weight"]), hold.f32(sd[lp + "norm3.bias"])
+            L.i2t_wk_t, L.i2t_bk = lin_t(lp + "cross_attn_image_to_token.k_proj")
+            L.i2t_wv_t, L.i2t_bv = lin_t(lp + "cross_attn_image_to_token.v_proj")
+            L.w_img = hold.bf16(torch.cat([sd[lp + "cross_attn_token_to_image.k_proj.weight"], sd[lp + "cross_attn_token_to_image.v_proj.weight"],
+                                           sd[lp + "cross_attn_image_to_token.q_proj.weight"]], 0))
+            L.i2t_wo, L.i2t_bo = hold.bf16(sd[lp + "cross_attn_image_to_token.out_proj.weight"]), hold.f32(sd[lp + "cross_attn_image_to_token.out_proj.bias"])
+            L.n4_g, L.n4_b = hold.f32(sd[lp + "norm4.weight"]), hold.f32(sd[lp + "norm4.bias"])
+        w.fin_wq_t, w.fin_bq = lin_t(T + "final_attn_token_to_image.q_proj")
+        w.fin_wo_t, w.fin_bo = lin_t(T + "final_attn_token_to_image.out_proj")
+        w.nf_g, w.nf_b = hold.f32(sd[T + "norm_final_attn.weight"]), hold.f32(sd[T + "norm_final_attn.bias"])
+        w.w_img_fin = hold.bf16(torch.cat([sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.v_proj.weight"]], 0))
+        up = sd["output_upscaling.0.weight"]  # ConvTranspose2d weight [Cin, Cout, 2, 2] -> rows (dy, dx, co), cols ci
+        w.w_up = hold.bf16(up.permute(2, 3, 1, 0).reshape(-1, up.shape[0]))
+        w.b_up = hold.f32(sd["output_upscaling.0.bias"].float().repeat(4))
+        w.up_ln_g, w.up_ln_b = hold.f32(sd["output_upscaling.1.weight"]), hold.f32(sd["output_upscaling.1.bias"])
+        for j, (wn, bn) in enumerate((("hyp_w0_t", "hyp_b0"), ("hyp_w1_t", "hyp_b1"), ("hyp_w2_t", "hyp_b2"))):
+            ws_ = torch.stack([sd[f"output_hypernetworks_mlps.{i}.layers.{j}.weight"].t() for i in range(self.num_mask_tokens)], 0)
+            bs_ = torch.stack([sd[f"output_hypernetworks_mlps.{i}.layers.{j}.bias"] for i in range(self.num_mask_tokens)], 0)
+            setattr(w, wn, hold.bf16(ws_))
+            setattr(w, bn, hold.f32(bs_))
+        for j, (wn, bn) in enumerate((("iou_w0_t", "iou_b0"), ("iou_w1_t", "iou_b1"), ("iou_w2_t", "iou_b2"))):
+            setattr(w, wn, hold.bf16(sd[f"iou_prediction_head.layers.{j}.weight"].t()))
+            setattr(w, bn, hold.f32(sd[f"iou_prediction_head.layers.{j}.bias"]))
+        self._packed = (w, hold)
+        self._pe_key = None
+        return self._packed
+
+    _pack = _pack_static
+
+    def bind_prompt_constants(self, pe_tokens: torch.Tensor, no_mask: torch.Tensor, grid: Tuple[int, int]) -> None:
+        """Fold the dense positional encoding into per-position bias tables (pe W^T + b) with the library's own GEMM,
+        and record the dense (no-mask) prompt embedding.  Cached until the inputs or the weights change."""
+        w, hold = self._packed or self._pack()
+        key = (pe_tokens.data_ptr(), pe_tokens._version, no_mask.data_ptr(), no_mask._version, tuple(grid))
+        if self._pe_key == key:
+            return
+        from . import ops
+        sd = self._sd()
+        pe_bf16 = pe_tokens.to(torch.bfloat16).contiguous()
+        hw = pe_tokens.shape[0]
+        T = "transformer.0."
+        self._pe_keep = []
+
+        def table(wk, bk, bv, wq=None, bq=None):
+            parts = [ops.gemm(pe_bf16, _bf16(wk), _f32(bk), out_mode=ops.OUT_F32), _f32(bv)[None].expand(hw, -1)]
+            if wq is not None:
+                parts.append(ops.gemm(pe_bf16, _bf16(wq), _f32(bq), out_mode=ops.OUT_F32))
+            t = torch.cat(parts, dim=1).contiguous()
+            self._pe_keep.append(t)
+            return t.data_ptr()
+
+        for l in range(2):
+            lp = T + f"layers.{l}."
+            w.layers[l].b_img = table(sd[lp + "cross_attn_token_to_image.k_proj.weight"], sd[lp + "cross_attn_token_to_image.k_proj.bias"],
+                                      sd[lp + "cross_attn_token_to_image.v_proj.bias"],
+                                      sd[lp + "cross_attn_image_to_token.q_proj.weight"], sd[lp + "cross_attn_image_to_token.q_proj.bias"])
+        w.b_img_fin = table(sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.k_proj.bias"],
+                            sd[T + "final_attn_token_to_image.v_proj.bias"])
+        nm = _f32(no_mask.reshape(-1))
+        self._pe_keep.append(nm)
+        w.no_mask = nm.data_ptr()
+        w.grid_h, w.grid_w = grid
+        self._pe_key = key
+
+    def run(self, emb_tokens_bf16: torch.Tensor, txt_emb_f32: torch.Tensor, prompt_img_i32: torch.Tensor, multimask_output: bool = False,
+            want_depth_pool: bool = False):
+        """emb tokens bf16 [B, hw, 256], txt fp32 [P, 256], prompt_img int32 [P] ->
+        (low_res fp32 [P, n, 2h, 2w], iou fp32 [P, n], depth_pool fp32 [P, 33] | None).  bind_prompt_constants first."""
+        w, _ = self._packed
+        P = txt_emb_f32.shape[0]
+        hw = w.grid_h * w.grid_w
+        n_out = self.num_mask_tokens if multimask_output else 1
+        dev = emb_tokens_bf16.device
+        low = torch.empty(P, n_out, 2 * w.grid_h, 2 * w.grid_w, device=dev, dtype=torch.float32)
+        iou = torch.empty(P, n_out, device=dev, dtype=torch.float32)
+        pool = torch.empty(P, 33, device=dev, dtype=torch.float32) if want_depth_pool else None
+        if P == 0:
+            return low, iou, pool
+        ws = self._ws.get(_lib.lib().wg_mask_decoder_workspace_bytes(P, hw), dev)
+        _lib.check(_lib.lib().wg_mask_decoder_forward(C.byref(w), emb_tokens_bf16.data_ptr(), txt_emb_f32.data_ptr(), prompt_img_i32.data_ptr(), P,
+                                                      int(multimask_output), low.data_ptr(), iou.data_ptr(), None if pool is None else pool.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), _stream()), "wg_mask_decoder_forward")
+        return low, iou, pool
+
+    @torch.no_grad()
+    def forward(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, multimask_output: bool, level_num: int = 0,
+                previous_masks=None):
+        """Reference signature.  image_embeddings [1,256,h,w]; image_pe [1,256,h,w]; sparse [S,1,256]; dense [S,256,h,w]."""
+        if level_num != 0 or previous_masks is not None:
+            raise NotImplementedError("MaskDecoderMultiScale: only level_num=0 is built (image_feature_scale_num=1 in the released config)")
+        _need_cuda(image_embeddings, "MaskDecoderMultiScale.forward")
+        S = sparse_prompt_embeddings.shape[0]
+        if sparse_prompt_embeddings.shape[1] != 1:
+            raise NotImplementedError("MaskDecoderMultiScale: exactly one sparse (text) embedding per prompt is built")
+        _, Cc, h, wd = image_embeddings.shape
+        if image_embeddings.shape[0] != 1:
+            raise ValueError("image_embeddings must be [1, C, h, w] (one image per call, as in the reference)")
+        dt = image_embeddings.dtype
+        with torch.cuda.device(image_embeddings.device):
+            self._packed or self._pack()
+            pe_tok = image_pe.reshape(Cc, h * wd).t().contiguous().float()  # layout change only
+            # dense prompt embedding: the reference always passes no_mask_embed broadcast over (h, w)
+            dense_vec = dense_prompt_embeddings[0, :, 0, 0].float().contiguous()
+            self.bind_prompt_constants(pe_tok, dense_vec, (h, wd))
+            emb_tok = image_embeddings.reshape(1, Cc, h * wd).permute(0, 2, 1).to(torch.bfloat16).contiguous()
+            txt = sparse_prompt_embeddings.reshape(S, Cc).float().contiguous()
+            pimg = torch.zeros(S, dtype=torch.int32, device=image_embeddings.device)
+            low, iou, _ = self.run(emb_tok, txt, pimg, multimask_output)
+        return low.to(dt), iou.to(dt)
+
+
+# --------------------------------------------------------------------------------------------------
+# A8 + A9  postprocess / threshold / score,  A10 depth extension
+# --------------------------------------------------------------------------------------------------
+_pp_ws = _Workspace()
+
+
+@torch.no_grad()
+def postprocess_masks_fused(low_res: torch.Tensor, input_size: Tuple[int, int], original_size: Tuple[int, int], target_size: Optional[int] = None,
+                            want_mask: bool = True, want_score: bool = True):
+    """low_res fp32 [n, Hm, Wm] -> (logits fp32 [n, H0, W0], mask uint8 | None, score fp32 [n] | None)."""
+    _need_cuda(low_res, "postprocess_masks")
+    assert low_res.dim() == 3 and low_res.dtype == torch.float32 and low_res.is_contiguous()
+    n, Hm, Wm = low_res.shape
+    T = max(input_size) if target_size is None else target_size
+    H0, W0 = original_size
+    dev = low_res.device
+    logits = torch.empty(n, H0, W0, device=dev, dtype=torch.float32)
+    mask = torch.empty(n, H0, W0, device=dev, dtype=torch.uint8) if want_mask else None
+    score = torch.empty(n, device=dev, dtype=torch.float32) if want_score else None
+    if n == 0:
+        return logits, mask, score
+    with torch.cuda.device(dev):
+        ws = _pp_ws.get(_lib.lib().wg_postprocess_workspace_bytes(n, input_size[0], input_size[1]), dev)
+        _lib.check(_lib.lib().wg_postprocess_masks(low_res.data_ptr(), n, Hm, Wm, T, input_size[0], input_size[1], H0, W0, logits.data_ptr(),
+                                                   None if mask is None else mask.data_ptr(), None if score is None else score.data_ptr(),
+                                                   ws.data_ptr(), ws.numel(), _stream()), "wg_postprocess_masks")
+    return logits, mask, score
+
+
+@torch.no_grad()
+def postprocess_masks(masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...]) -> torch.Tensor:
+    """Drop-in for ``walkgptForCausalLM.postprocess_masks`` (model/walkgpt.py:749-790, vision_tower_for_mask=True):
+    masks [B, C, Hm, Wm] -> [B, C, H0, W0], cast back to the input dtype."""
+    b, c, Hm, Wm = masks.shape
+    logits, _, _ = postprocess_masks_fused(masks.reshape(b * c, Hm, Wm).float().contiguous(), tuple(input_size[:2]), tuple(original_size[:2]),
+                                           want_mask=False, want_score=False)
+    return logits.reshape(b, c, *logits.shape[-2:]).to(masks.dtype)
+
+
+class DepthHead(_SpecModule):
+    """Relative-depth head.  THIS REPO'S EXTENSION -- the reference has no depth head (it emits depth as text);
+    definition and checker: ``oracle/path_a.py:depth_head``.  Parity with the reference is therefore unpinned."""
+
+    def __init__(self, in_ch: int = 32, hidden: int = 256, *, seed=0):
+        super().__init__()
+        assert in_ch == 32 and hidden == 256
+        self._build(specs.depth_head_spec(in_ch, hidden), seed)
+
+    def _pack(self):
+        sd, hold = self._sd(), _Holder()
+        self._packed = ((hold.f32(sd["0.weight"]), hold.f32(sd["0.bias"]), hold.f32(sd["2.weight"].reshape(-1)), hold.f32(sd["2.bias"])), hold)
+        return self._packed
+
+    @torch.no_grad()
+    def forward(self, depth_pool: torch.Tensor, seg_offsets_i32: torch.Tensor, max_S: int) -> torch.Tensor:
+        _need_cuda(depth_pool, "DepthHead.forward")
+        (w1, b1, w2, b2), _ = self._packed or self._pack()
+        P = depth_pool.shape[0]
+        out = torch.empty(P, device=depth_pool.device, dtype=torch.float32)
+        if P == 0:
+            return out
+        with torch.cuda.device(depth_pool.device):
+            _lib.check(_lib.lib().wg_depth_head(depth_pool.data_ptr(), seg_offsets_i32.data_ptr(), seg_offsets_i32.numel() - 1, max_S, w1, b1, w2, b2,
+                                                out.data_ptr(), _stream()), "wg_depth_head")
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Path A composition (SURVEY §8): the batched grounding forward a caller uses instead of the reference's
+# per-image Python loops (model/walkgpt.py:511-541, 713-743).
+# --------------------------------------------------------------------------------------------------
+class GroundingPath(nn.Module):
+    """CLIP tower -> {MSQP, out_mm_projector+neck} ; [SEG] hidden states -> CTP -> prompt encoder -> mask decoder ->
+    postprocess / threshold / score (+ depth extension), batched over all images and prompts of a batch."""
+
+    def __init__(self, hidden_size: int = 4096, clip_layers: int = 24, select_layer: int = -2, image: int = 448, with_depth: bool = True,
+                 seed: int = 0):
+        super().__init__()
+        args = _ClipArgs()
+        args.mm_vision_select_layer = select_layer
+        self.vision_tower = CLIPVisionTower(None, args, layers=clip_layers, image=image, seed=seed)
+        g = image // 14
+        self.grid = g
+        self.image = image
+        self.msqp = MultiScaleQFormerProjector(sam_dim=1024, llama_dim=hidden_size, pad_to_square=True, target_square_side=6, seed=seed)
+        self.proj_neck = ProjectorNeck(1024, hidden_size, 256, seed=seed)
+        self.text_hidden_fcs = nn.ModuleList([CalibratedTextProjector(hidden_size, 256, widen=2, use_residual=False, seed=seed)])
+        self.prompt_encoder = PromptEncoder(256, (g, g), (image, image), 16, seed=seed)
+        self.mask_decoder = MaskDecoderMultiScale(transformer_dim=256, num_multimask_outputs=3, iou_head_depth=3, iou_head_hidden_dim=256,
+                                                  image_feature_scale_num=1, seed=seed)
+        self.depth_head = DepthHead(seed=seed) if with_depth else None
+        self.hidden_size = hidden_size
+
+    @torch.no_grad()
+    def forward(self, images_clip: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, attention_mask: Optional[torch.Tensor] = None,
+                input_size: Optional[Tuple[int, int]] = None, original_size: Optional[Tuple[int, int]] = None, want_vis_tokens: bool = True):
+        """images_clip [B,3,448,448]; seg_hidden [sum S, H] (LLM hidden states at the [SEG] positions);
+        seg_offsets: int sequence / tensor [B+1].  Returns a dict of device tensors."""
+        _need_cuda(images_clip, "GroundingPath.forward")
+        dev = images_clip.device
+        B = images_clip.shape[0]
+        input_size = input_size or (self.image, self.image)
+        original_size = original_size or input_size
+        if torch.is_tensor(seg_offsets):
+            offs_dev = seg_offsets.to(device=dev, dtype=torch.int32)
+            counts = (offs_dev[1:] - offs_dev[:-1]).long()
+            P = seg_hidden.shape[0]
+            max_S = P
+        else:
+            offs = [int(v) for v in seg_offsets]
+            assert len(offs) == B + 1 and offs[0] == 0 and offs[-1] == seg_hidden.shape[0]
+            offs_dev = torch.tensor(offs, dtype=torch.int32, device=dev)
+            counts = (offs_dev[1:] - offs_dev[:-1]).long()
+            P = offs[-1]
+            max_S = max([offs[i + 1] - offs[i] for i in range(B)] + [0])
+        out: Dict[str, torch.Tensor] = {}
+        with torch.cuda.device(dev):
+            feats, _ = self.vision_tower(images_clip.to(torch.bfloat16) if images_clip.dtype != torch.bfloat16 else images_clip, attention_mask)
+            if want_vis_tokens:
+                out["vis_tokens"] = self.msqp.run(feats, torch.bfloat16)
+            _, emb = self.proj_neck.run(feats)
+            out["img_emb_tokens"] = emb
+            txt = self.text_hidden_fcs[0].run(_as_kernel_input(seg_hidden), torch.float32)
+            out["txt_emb"] = txt
+            prompt_img = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), counts, output_size=P)
+            _, pe_tok = self.prompt_encoder.dense_pe_tokens()
+            self.mask_decoder._packed or self.mask_decoder._pack()
+            self.mask_decoder.bind_prompt_constants(pe_tok, self.prompt_encoder.no_mask_embed.weight, (self.grid, self.grid))
+            low, iou, pool = self.mask_decoder.run(emb, txt, prompt_img, False, want_depth_pool=self.depth_head is not None)
+            out["low_res"], out["iou"] = low, iou
+            logits, mask, score = postprocess_masks_fused(low[:, 0], input_size, original_size)
+            out["logits"], out["masks"], out["scores"] = logits, mask, score
+            if self.depth_head is not None:
+                out["depth"] = self.depth_head(pool, offs_dev, max_S)
+        return out
