@@ -44,6 +44,14 @@ WG_API const char* wg_last_error(void);
 /* WG_OK when `device` is an sm_100 (B200) GPU this library can run on. */
 WG_API int wg_device_check(int device);
 
+/* Launch accounting and an optional CUDA-event profiler (bench.py's roofline leg).
+ * wg_launch_count: kernels launched by this library since the last reset.
+ * wg_profile_enable(1): every launch is bracketed by CUDA events on its stream; wg_profile_collect synchronises them
+ * and writes "<kernel-family> <launches> <total_ms> <algorithmic_flops> <algorithmic_bytes>" lines into `out`. */
+WG_API long long wg_launch_count(int reset);
+WG_API int wg_profile_enable(int on);
+WG_API long long wg_profile_collect(char* out, long long cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Kernel-level entry points (used by the module-level functions below; exported so that each kernel
  * can be parity-tested on its own).

@@ -1,0 +1,112 @@
+"""CPU: host-side logic of the drop-in modules -- parameter names/shapes, weight re-layout and constant folding,
+reference error behaviour, sharding helpers."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from walkgpt_b200 import parallel, specs
+from walkgpt_b200 import modules as M
+
+REF = "/root/reference"
+
+
+def test_state_dict_keys_follow_the_specs():
+    m = M.GroundingPath(hidden_size=256, clip_layers=1)
+    sd = m.state_dict()
+    assert set(k for k in sd if k.startswith("msqp.")) == {"msqp." + k for k in specs.msqp_spec(1024, 256)}
+    assert set(k for k in sd if k.startswith("mask_decoder.")) == {"mask_decoder." + k for k in specs.mask_decoder_multiscale_spec()}
+    assert set(k for k in sd if k.startswith("text_hidden_fcs.0.")) == {"text_hidden_fcs.0." + k for k in specs.ctp_spec(256, 256)}
+    assert "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix" in sd
+    # buffers stay buffers (the random Gaussian PE matrix is part of the checkpoint, prompt_encoder.py:198-201)
+    assert "pe_layer.positional_encoding_gaussian_matrix" in dict(m.prompt_encoder.named_buffers())
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (build container only)")
+def test_reference_modules_load_our_state_dicts_strictly():
+    import sys
+    sys.path.insert(0, REF)
+    from utils.utils_walkgpt import CalibratedTextProjector, MultiScaleQFormerProjector
+    from model.segment_anything.modeling import MaskDecoderMultiScale, PromptEncoder, TwoWayTransformer
+
+    MultiScaleQFormerProjector(256, 64).load_state_dict(M.MultiScaleQFormerProjector(256, 64).state_dict(), strict=True)
+    CalibratedTextProjector(512, 256).load_state_dict(M.CalibratedTextProjector(512, 256).state_dict(), strict=True)
+    PromptEncoder(256, (32, 32), (448, 448), 16).load_state_dict(M.PromptEncoder(256, (32, 32), (448, 448), 16).state_dict(), strict=True)
+    MaskDecoderMultiScale(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                          transformer_dim=256, image_feature_scale_num=1).load_state_dict(M.MaskDecoderMultiScale().state_dict(), strict=True)
+
+
+def test_synthetic_init_is_deterministic_and_order_independent():
+    a = specs.make_state_dict(specs.ctp_spec(256, 256), seed=5)
+    b = specs.make_state_dict(dict(reversed(list(specs.ctp_spec(256, 256).items()))), seed=5)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert not torch.equal(a["net.1.weight"], specs.make_state_dict(specs.ctp_spec(256, 256), seed=6)["net.1.weight"])
+
+
+def test_kv_norm_folding_is_exact_algebra():
+    d = 64
+    g = torch.Generator().manual_seed(0)
+    W, b = torch.randn(3 * d, d, generator=g), torch.randn(3 * d, generator=g)
+    gamma, beta = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    x = torch.randn(10, d, generator=g)
+    xhat = F.layer_norm(x, (d,))
+    Wf, bf = M.fold_kv_norm(W, b, gamma, beta, d)
+    ref = F.linear(F.layer_norm(x, (d,), gamma, beta), W[d:], b[d:])
+    assert torch.allclose(F.linear(xhat, Wf, bf), ref, atol=1e-4)
+
+
+def test_conv_weight_relayouts_match_torch_convolutions():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 16, 5, 5, generator=g)
+    w = torch.randn(8, 16, 3, 3, generator=g)
+    ref = F.conv2d(x, w, padding=1)
+    xt = F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1))  # channels-last, zero padded
+    cols = torch.stack([xt[:, ky:ky + 5, kx:kx + 5] for ky in range(3) for kx in range(3)], dim=3).reshape(2, 5, 5, -1)
+    got = (cols @ M.pack_conv3x3(w).t()).permute(0, 3, 1, 2)
+    assert torch.allclose(got, ref, atol=1e-4)
+    wt, bt = torch.randn(16, 4, 2, 2, generator=g), torch.randn(4, generator=g)
+    ref = F.conv_transpose2d(x, wt, bt, stride=2)
+    wg, bg = M.pack_conv_transpose2x2(wt, bt)
+    u = x.permute(0, 2, 3, 1) @ wg.t() + bg  # [B, y, x, (dy, dx, co)]
+    got = u.reshape(2, 5, 5, 2, 2, 4).permute(0, 5, 1, 3, 2, 4).reshape(2, 4, 10, 10)
+    assert torch.allclose(got, ref, atol=1e-4)
+
+
+def test_reference_error_behaviour_is_preserved():
+    msqp = M.MultiScaleQFormerProjector(256, 64, pad_to_square=True, target_square_side=5)
+    with pytest.raises(AssertionError, match="target_square_side too small"):
+        msqp.n_tokens()
+    assert M.MultiScaleQFormerProjector(256, 64, target_square_side=6).n_tokens() == 36
+    assert M.MultiScaleQFormerProjector(256, 64, pad_to_square=False).n_tokens() == 32
+    assert M.MultiScaleQFormerProjector(256, 64).n_tokens() == 36  # ceil(sqrt(32))^2
+    with pytest.raises(ValueError, match="Unexpected select feature"):
+        args = M._ClipArgs()
+        args.mm_vision_select_feature = "bogus"
+        M.CLIPVisionTower(None, args, layers=1)
+    pe = M.PromptEncoder(256, (8, 8), (112, 112), 16)
+    with pytest.raises(NotImplementedError):
+        pe((torch.zeros(1, 1, 2), torch.zeros(1, 1)), None, None, None)
+    sparse, dense = pe(None, None, None, torch.zeros(3, 1, 256))
+    assert sparse.shape == (3, 1, 256) and dense.shape == (3, 256, 8, 8)
+
+
+def test_clip_hidden_state_selection():
+    t = M.CLIPVisionTower(layers=24)
+    assert t.hidden_state_indices() == (23, 14)  # hidden_states[-2], hidden_states[-11] of 25 states
+    a = M._ClipArgs()
+    a.mm_vision_select_layer = -1
+    assert M.CLIPVisionTower(None, a, layers=24).hidden_state_indices() == (24, 14)
+    assert t.num_patches == 1024 and t.hidden_size == 1024
+
+
+def test_shard_helpers():
+    assert [parallel.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert [parallel.shard_range(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    imgs = torch.arange(5)[:, None].float()
+    seg = torch.arange(9)[:, None].float()
+    offs = [0, 2, 2, 5, 8, 9]  # ragged, including an image with zero [SEG] tokens
+    got = [parallel.shard_batch(imgs, seg, offs, r, 2) for r in range(2)]
+    assert got[0][0].flatten().tolist() == [0, 1, 2] and got[0][1].flatten().tolist() == [0, 1, 2, 3, 4] and got[0][2] == [0, 2, 2, 5]
+    assert got[1][0].flatten().tolist() == [3, 4] and got[1][1].flatten().tolist() == [5, 6, 7, 8] and got[1][2] == [0, 3, 4]

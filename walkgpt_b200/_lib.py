@@ -18,7 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "walkgpt_b200.h")
 WG_OK = 0
 
 _SCALARS = {"int32_t": C.c_int32, "int": C.c_int, "int64_t": C.c_int64, "size_t": C.c_size_t, "float": C.c_float,
-            "uint8_t": C.c_uint8}
+            "uint8_t": C.c_uint8, "long long": C.c_longlong}
 
 STRUCTS: Dict[str, type] = {}
 CONSTANTS: Dict[str, int] = {}
@@ -67,7 +67,8 @@ def _parse_header(path: str) -> None:
                 if "*" in a:
                     args.append(C.c_void_p)
                 else:
-                    args.append(_SCALARS[a.replace("const ", "").split(" ")[0]])
+                    a = a.replace("const ", "")
+                    args.append(_SCALARS["long long" if a.startswith("long long") else a.split(" ")[0]])
         _PROTOTYPES[fname] = (ret, args)
 
 

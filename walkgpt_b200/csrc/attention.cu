@@ -303,6 +303,7 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
         attr_set = true;
     }
     dim3 grid((T + ATT_BQ - 1) / ATT_BQ, heads, B);
+    Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D);
     attention_d64_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const __nv_bfloat16
 
 int launch_tokens_to_nchw(const void* tokens_bf16, void* out, int out_is_bf16, int B, int L, int C, cudaStream_t s) {
     dim3 grid((L + 31) / 32, (C + 31) / 32, B);
+    Prof prof("tokens_to_nchw", s, 0.0, (double)B * L * C * (2.0 + (out_is_bf16 ? 2.0 : 4.0)));
     if (out_is_bf16)
         tokens_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(tokens_bf16), static_cast<__nv_bfloat16*>(out), L, C);
     else
@@ -139,6 +140,7 @@ extern "C" int wg_ctp_forward(const wg_ctp_weights* w, const void* x, int x_is_b
     WG_TRY(gemm_bf16_out(xn, w->in_dim, w->w1, rows, 512, w->in_dim, w->b1, WG_ACT_GELU_ERF, h1, 512, s));
     WG_TRY(gemm_f32_out(h1, 512, w->w2, rows, 256, 512, w->b2, WG_ACT_NONE, h2, 256, nullptr, s));
     const unsigned grid = (unsigned)((rows + 7) / 8);
+    Prof prof("ctp_tail", s, 0.0, (double)rows * 256 * (4.0 + (out_is_bf16 ? 2.0 : 4.0)));
     if (out_is_bf16)
         ctp_tail_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(h2, w->ln4_g, w->ln4_b, w->text_type, w->log_temp, static_cast<__nv_bfloat16*>(out), rows);
     else
@@ -162,6 +164,7 @@ static int neck_impl(const wg_proj_neck_weights* w, const void* pr, int B, int g
         const long long total = (long long)rows * (9 * 256 / 8);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
+        Prof prof("im2col3x3", s, 0.0, (double)rows * 256 * 2 * 10.0);
         im2col3x3_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(n1), static_cast<__nv_bfloat16*>(col), B, grid_side, 256);
         WG_CHECK_CUDA(cudaGetLastError());
     }

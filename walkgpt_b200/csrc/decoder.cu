@@ -11,6 +11,8 @@
 // Reference: segment_anything/modeling/transformer.py:62-106,151-182,220-242; mask_decoder_multi_scale.py:137-213;
 // prompt_encoder.py:140-186 (text_embeds passthrough + no_mask_embed dense embedding), :67-76 (dense PE, folded into
 // the bias tables at weight-pack time).
+#include <stdlib.h>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -540,7 +542,10 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
 
     long long blocks = (rows * (C / 8) + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
+    {
+        Prof prof("dec_expand_keys", s, 0.0, (double)rows * C * 4.0);
     expand_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(img_emb_tokens_bf16), prompt_img, w->no_mask, d.keysA, P, hw);
+    }
     WG_CHECK_CUDA(cudaGetLastError());
 
     const size_t tk_smem = (size_t)(6 * NT * C + NT * 2048 + NT * hw) * sizeof(float);
@@ -558,6 +563,15 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     ta.out_tokens = w->out_tokens; ta.sparse_add = w->sparse_add; ta.txt = txt_emb;
     ta.Tq = d.Tq; ta.Tpe = d.Tpe; ta.KT = d.KT; ta.VT = d.VT; ta.hyper = d.hyper; ta.iou = d.iou_all;
 
+    // bring-up aid: WG_DEBUG_DECODER_STOP=<n> returns after the n-th launch group so intermediates can be inspected
+    const char* dbg = getenv("WG_DEBUG_DECODER_STOP");
+    const int stop_at = dbg ? atoi(dbg) : 0;
+    int step = 0;
+#define WG_DBG_STEP()                         \
+    do {                                      \
+        if (stop_at && ++step == stop_at) return WG_OK; \
+    } while (0)
+
     __nv_bfloat16* keys = d.keysA;
     __nv_bfloat16* keys_next = d.keysB;
     for (int l = 0; l < 2; ++l) {
@@ -568,11 +582,20 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
             a.bias = L.b_img; a.bias_period = hw; a.out_mode = WG_OUT_BF16; a.out = d.kvq; a.ldo = 384;
             WG_TRY(wg_gemm(&a, s));
         }
+        WG_DBG_STEP();
         ta.phase = l; ta.L = L; ta.kv = d.kvq; ta.ldkv = 384;
-        decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+        {
+            Prof prof("dec_token", s, (double)P * 2.0 * 10.2e6, (double)P * (hw * 512.0 + 3.0e6));
+            decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+        }
         WG_CHECK_CUDA(cudaGetLastError());
-        i2t_attention_kernel<<<dim3((hw + 255) / 256, P), 256, 0, s>>>(d.kvq, 384, 256, d.KT, d.VT, d.a2, hw);
+        WG_DBG_STEP();
+        {
+            Prof prof("dec_i2t_attention", s, (double)rows * 8 * 6 * 16 * 4.0, (double)rows * 512.0);
+            i2t_attention_kernel<<<dim3((hw + 255) / 256, P), 256, 0, s>>>(d.kvq, 384, 256, d.KT, d.VT, d.a2, hw);
+        }
         WG_CHECK_CUDA(cudaGetLastError());
+        WG_DBG_STEP();
         {   // keys' = LayerNorm4(keys + attn W_o^T + b)
             wg_gemm_args a = {};
             a.A = d.a2; a.lda = CI; a.W = L.i2t_wo; a.ldw = CI; a.M = (int)rows; a.N = C; a.K = CI;
@@ -580,6 +603,7 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
             a.ln_gamma = L.n4_g; a.ln_beta = L.n4_b; a.ln_eps = 1e-5f;
             WG_TRY(wg_gemm(&a, s));
         }
+        WG_DBG_STEP();
         __nv_bfloat16* t = keys; keys = keys_next; keys_next = t;
     }
     {   // final token->image attention: [K | V]
@@ -589,13 +613,19 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
         WG_TRY(wg_gemm(&a, s));
     }
     ta.phase = 2; ta.kv = d.kvq; ta.ldkv = 256;
-    decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+    {
+        Prof prof("dec_token", s, (double)P * 2.0 * 3.0e6, (double)P * (hw * 512.0 + 1.5e6));
+        decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+    }
     WG_CHECK_CUDA(cudaGetLastError());
     // ConvTranspose2d(256 -> 32, k=2, s=2) as a GEMM over positions (N = 4 sub-pixels x 32 channels), fp32 out
     WG_TRY(gemm_f32_out(keys, C, w->w_up, (int)rows, 128, C, w->b_up, WG_ACT_NONE, d.U, 128, nullptr, s));
     if (depth_pool_out) WG_CHECK_CUDA(cudaMemsetAsync(depth_pool_out, 0, (size_t)P * 33 * sizeof(float), s));
+    {
+        Prof prof("dec_upscale_mask", s, (double)rows * 128 * 12.0, (double)rows * (512.0 + 16.0 * n_out));
     upscale_mask_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, s>>>(d.U, w->up_ln_g, w->up_ln_b, d.hyper, w->n_mask_tokens, mask_start, n_out,
                                                                   low_res_out, depth_pool_out, hw, w->grid_w, rows);
+    }
     WG_CHECK_CUDA(cudaGetLastError());
     // iou predictions for the selected masks
     WG_CHECK_CUDA(cudaMemcpy2DAsync(iou_out, n_out * sizeof(float), d.iou_all + mask_start, w->n_mask_tokens * sizeof(float), n_out * sizeof(float), P,

@@ -378,6 +378,10 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     }
     int sms = device_sm_count();
     int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    static const char* kname = EPI == WG_OUT_BF16 ? (BN == 256 ? "gemm_bf16_bn256" : "gemm_bf16_bn128")
+                               : EPI == WG_OUT_F32 ? (BN == 256 ? "gemm_f32_bn256" : "gemm_f32_bn128") : "gemm_bf16ln_bn256";
+    const double out_bytes = (double)a->M * a->N * (EPI == WG_OUT_F32 ? (a->resid ? 8.0 : 4.0) : (a->resid ? 4.0 : 2.0));
+    Prof prof(kname, stream, 2.0 * a->M * a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
     kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, p);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;

@@ -4,6 +4,12 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 namespace wg {
 
 static thread_local char g_err[1024] = "";
@@ -87,6 +93,45 @@ static DevInfo& dev_info() {
     return info;
 }
 
+// ---------------------------------------------------------------------------------------- profiler
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+struct ProfRec {
+    const char* name;
+    cudaEvent_t e0, e1;
+    double flops, bytes;
+    int launches;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t get_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+Prof::Prof(const char* name, cudaStream_t s, double flops, double bytes, int launches) : slot(-1), stream(s) {
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r{name, get_event(), get_event(), flops, bytes, launches};
+    cudaEventRecord(r.e0, s);
+    g_prof_recs.push_back(r);
+    slot = (int)g_prof_recs.size() - 1;
+}
+Prof::~Prof() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[slot].e1, stream);
+}
+
 int device_sm_count() { return dev_info().sm_count; }
 int device_is_sm100() { return dev_info().is_sm100; }
 
@@ -111,4 +156,43 @@ extern "C" int wg_device_check(int device) {
         return WG_ERR_UNSUPPORTED;
     }
     return WG_OK;
+}
+
+extern "C" long long wg_launch_count(int reset) {
+    long long v = wg::g_launches.load();
+    if (reset) wg::g_launches.store(0);
+    return v;
+}
+extern "C" int wg_profile_enable(int on) {
+    wg::g_prof_on.store(on ? 1 : 0);
+    return WG_OK;
+}
+// Synchronises the recorded events and writes one line per kernel family:
+//   "<name> <launches> <total_ms> <flops> <bytes>\n"; returns the number of bytes written (or needed if > cap).
+extern "C" long long wg_profile_collect(char* out, long long cap) {
+    using namespace wg;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess) cudaEventElapsedTime(&ms, r.e0, r.e1);
+        Agg& a = agg[r.name];
+        a.n += r.launches; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+        g_event_pool.push_back(r.e0);
+        g_event_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+    std::string text;
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+        text += line;
+    }
+    if (out && cap > 0) {
+        long long n = (long long)text.size() < cap - 1 ? (long long)text.size() : cap - 1;
+        memcpy(out, text.data(), (size_t)n);
+        out[n] = 0;
+    }
+    return (long long)text.size() + 1;
 }

@@ -50,6 +50,17 @@ inline int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, 
     return make_tensor_map(out, gptr, 2, 2, dims, strides, box);
 }
 
+// ---- launch accounting + optional CUDA-event profiler (used by bench.py's roofline leg) -------------------
+// Every kernel launch site creates a Prof scope: it counts the launch and, when profiling is enabled
+// (wg_profile_enable), brackets it with CUDA events on the launching stream and attributes the elapsed time,
+// algorithmic FLOPs and algorithmic bytes to `name`.
+struct Prof {
+    Prof(const char* name, cudaStream_t s, double flops = 0.0, double bytes = 0.0, int launches = 1);
+    ~Prof();
+    int slot;
+    cudaStream_t stream;
+};
+
 int device_sm_count();
 int device_is_sm100();
 

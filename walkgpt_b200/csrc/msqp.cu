@@ -335,14 +335,20 @@ extern "C" int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16,
     // 1. input projection -> x1 (first rows of XS)
     WG_TRY(gemm_bf16_out(feats_bf16, w->sam_dim, w->w_in, (int)m.rows[0], D, w->sam_dim, w->b_in, WG_ACT_NONE, m.xs, D, s));
     // 2. pooled scales + global token
+    {
+        Prof prof("msqp_pool", s, 0.0, (double)(m.rows[0] * 3 + m.rows[1] + m.rows[2] + m.rows[3]) * D * 2.0, 3);
     pool_grid_kernel<<<grid_for(m.rows[1] * (D / 8)), 256, 0, s>>>(m.xs, m.xs + m.row_off[1] * D, B, g, 2);
     pool_grid_kernel<<<grid_for(m.rows[2] * (D / 8)), 256, 0, s>>>(m.xs, m.xs + m.row_off[2] * D, B, g, 4);
     global_mean_kernel<<<dim3(D / 256, B), 256, 0, s>>>(m.xs, m.xs + m.row_off[3] * D, L);
+    }
     WG_CHECK_CUDA(cudaGetLastError());
     // 3-5. seg-aware gate over all kv tokens of all scales, then kv normalisation
     WG_TRY(wg_layernorm(m.xs, 1, D, w->gate_ln_g, w->gate_ln_b, 1e-5f, m.t, D, m.R, D, s));
     WG_TRY(gemm_bf16_out(m.t, D, w->w_g1, (int)m.R, 128, D, w->b_g1, WG_ACT_GELU_ERF, m.hg, 128, s));
+    {
+        Prof prof("msqp_gate_norm", s, 0.0, (double)m.R * (D * 4.0 + 256.0));
     gate_scale_norm_kernel<<<(unsigned)((m.R + 7) / 8), 256, 0, s>>>(m.xs, m.hg, w->w_g2, w->b_g2, m.t, m.R);
+    }
     WG_CHECK_CUDA(cudaGetLastError());
     // 6-7. per scale: K|V projections for both layers in one GEMM, then the two cross-attention blocks on the queries
     for (int sc = 0; sc < 4; ++sc) {
@@ -350,7 +356,10 @@ extern "C" int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16,
         const int Nkv = (int)(m.rows[sc] / B);
         const int Mq = B * S.nq;
         WG_TRY(gemm_bf16_out(m.t + m.row_off[sc] * D, D, S.w_kv, (int)m.rows[sc], 4 * D, D, S.b_kv, WG_ACT_NONE, m.kv[sc], 4 * D, s));
+        {
+            Prof prof("msqp_broadcast_q", s, 0.0, (double)Mq * D * 4.0);
         broadcast_queries_kernel<<<grid_for((long long)Mq * (D / 4)), 256, 0, s>>>(S.queries, m.q[sc], B, S.nq);
+        }
         WG_CHECK_CUDA(cudaGetLastError());
         const size_t smem = (size_t)(MAXQ * 128 + (size_t)S.nq * Nkv + 4 * MAXQ * 128) * sizeof(float);
         WG_REQUIRE(smem <= 227 * 1024, "wg_msqp_forward: %d kv tokens x %d queries exceed shared memory", Nkv, S.nq);
@@ -359,7 +368,10 @@ extern "C" int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16,
             const wg_msqp_block& Bk = S.blocks[l];
             WG_TRY(wg_layernorm(m.q[sc], 0, D, Bk.qn_g, Bk.qn_b, 1e-5f, m.qn, D, Mq, D, s));
             WG_TRY(gemm_bf16_out(m.qn, D, Bk.w_q, Mq, D, D, Bk.b_q, WG_ACT_NONE, m.qp, D, s));
+            {
+                Prof prof("msqp_attention", s, 4.0 * B * 8 * (double)S.nq * Nkv * 128, (double)B * Nkv * 2 * D * 2.0);
             msqp_attention_kernel<<<dim3(B, 8), 256, smem, s>>>(m.qp, m.kv[sc], 4 * D, l * 2 * D, l * 2 * D + D, m.ao, S.nq, Nkv);
+            }
             WG_CHECK_CUDA(cudaGetLastError());
             WG_TRY(gemm_f32_out(m.ao, D, Bk.w_o, Mq, D, D, Bk.b_o, WG_ACT_NONE, m.q[sc], D, m.q[sc], s));
             WG_TRY(wg_layernorm(m.q[sc], 0, D, Bk.ffn_ln_g, Bk.ffn_ln_b, 1e-5f, m.f, D, Mq, D, s));
@@ -373,7 +385,10 @@ extern "C" int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16,
         aa.q[i] = m.q[i];
         aa.nq[i] = w->scales[i].nq;
     }
+    {
+        Prof prof("msqp_assemble", s, 0.0, (double)B * w->n_tokens * D * 6.0);
     assemble_tokens_kernel<<<grid_for((long long)B * w->n_tokens * (D / 4)), 256, 0, s>>>(aa, w->pad_token, m.tok, B, w->n_tokens);
+    }
     WG_CHECK_CUDA(cudaGetLastError());
     const int Mt = B * w->n_tokens;
     if (out_is_bf16)

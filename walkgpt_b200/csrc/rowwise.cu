@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(256) drop_cls_cast_kernel(const float* __restr
 int launch_im2col_patch(const void* pixels, int is_bf16, void* out_bf16, int B, int IMG, int P, int KPAD, cudaStream_t s) {
     const int G = IMG / P;
     const long long rows = (long long)B * G * G;
+    Prof prof("im2col_patch", s, 0.0, (double)B * 3 * IMG * IMG * (is_bf16 ? 2 : 4) + (double)rows * KPAD * 2);
     if (is_bf16)
         im2col_patch_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(pixels),
                                                                          static_cast<__nv_bfloat16*>(out_bf16), B, IMG, P, KPAD);
@@ -215,6 +216,7 @@ int launch_embed_ln(const float* patch_emb, const float* cls, const float* pos, 
                     int B, int T, int D, cudaStream_t s) {
     WG_REQUIRE(D == 1024, "embed_ln: hidden size %d not supported (1024 only)", D);
     const long long rows = (long long)B * T;
+    Prof prof("embed_ln", s, 0.0, (double)rows * D * 12.0);
     embed_ln_kernel<8><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(patch_emb, cls, pos, gamma, beta, eps, x, B, T);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
@@ -224,6 +226,7 @@ int launch_drop_cls_cast(const float* x, void* out, int out_is_bf16, int B, int 
     const long long n4 = (long long)B * (T - 1) * (D / 4);
     long long blocks = (n4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    Prof prof("drop_cls_cast", s, 0.0, (double)n4 * 4 * (out_is_bf16 ? 6.0 : 8.0));
     if (out_is_bf16)
         drop_cls_cast_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out), B, T, D);
     else
@@ -248,6 +251,7 @@ extern "C" int wg_layernorm(const void* x, int x_is_bf16, int64_t ldx, const flo
     }
     const unsigned grid = (unsigned)((rows + 7) / 8);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+    Prof prof("layernorm", s, 0.0, (double)rows * D * ((x_is_bf16 ? 2.0 : 4.0) + 2.0));
 #define WG_LN_CASE(CHN)                                                                                                         \
     case CHN:                                                                                                                   \
         if (x_is_bf16)                                                                                                          \

@@ -160,6 +160,9 @@ template <bool SCORE>
 int launch_bilinear(const float* src, int n, int sh, int sw, float* dst, int dh, int dw, int full_h, int full_w, uint8_t* mask, float* accum,
                     cudaStream_t s) {
     const float sy = (float)sh / (float)full_h, sx = (float)sw / (float)full_w;
+    // algorithmic bytes: read the source once, write fp32 logits (+ u8 mask)
+    Prof prof(SCORE ? "postprocess_bilinear_score" : "postprocess_bilinear", s, 0.0,
+              (double)n * ((double)sh * sw * 4.0 + (double)dh * dw * (SCORE && mask ? 5.0 : 4.0)));
     if (dw % 4 == 0) {
         const int groups = dw / 4;
         const int threads = groups >= 128 ? 128 : ((groups + 31) / 32) * 32;
@@ -219,6 +222,7 @@ extern "C" int wg_postprocess_masks(const float* low_res, int n_masks, int Hm, i
             WG_TRY(launch_bilinear<false>(mid, n_masks, in_h, in_w, logits_out, out_h, out_w, out_h, out_w, nullptr, nullptr, s));
     }
     if (score_out) {
+        Prof prof("finalize_score", s);
         finalize_score_kernel<<<(n_masks + 255) / 256, 256, 0, s>>>(accum, score_out, n_masks);
         WG_CHECK_CUDA(cudaGetLastError());
     }
@@ -235,6 +239,7 @@ extern "C" int wg_depth_head(const float* pooled, const int32_t* seg_offsets, in
         set_error("wg_depth_head: this library only runs on sm_100 (B200) devices; there is no fallback");
         return WG_ERR_UNSUPPORTED;
     }
+    Prof prof("depth_head", s);
     depth_head_kernel<<<B, 256, (size_t)(max_S > 0 ? max_S : 1) * sizeof(float), s>>>(pooled, seg_offsets, w1, b1, w2, b2, depth_out);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
@@ -248,6 +253,7 @@ extern "C" int wg_dense_pe(const float* gauss, int num_pos_feats, int h, int w, 
         return WG_ERR_UNSUPPORTED;
     }
     const int n = num_pos_feats * h * w;
+    Prof prof("dense_pe", s);
     dense_pe_kernel<<<(n + 255) / 256, 256, 0, s>>>(gauss, num_pos_feats, h, w, out_chw, out_tokens);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;

@@ -270,6 +270,27 @@ class CLIPVisionTower(_SpecModule):
         return last.to(out_dtype), [mid.to(out_dtype)]
 
 
+
+# --------------------------------------------------------------------------------------------------
+# weight re-layout helpers (pure re-indexing / constant folding done once at load time; unit-tested on CPU)
+# --------------------------------------------------------------------------------------------------
+def fold_kv_norm(in_proj_weight: torch.Tensor, in_proj_bias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, d: int):
+    """K|V rows of a packed nn.MultiheadAttention in_proj with the preceding LayerNorm's affine folded in:
+    W (g*xhat + b) + c  ==  (W diag(g)) xhat + (c + W b).  Returns (W' [2d, d], b' [2d])."""
+    W, b = in_proj_weight.float()[d:], in_proj_bias.float()[d:]
+    return W * gamma.float()[None, :], b + W @ beta.float()
+
+
+def pack_conv3x3(weight: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [co, ci, 3, 3] -> GEMM weight [co, (ky, kx, ci)] matching the channels-last im2col column order."""
+    return weight.permute(0, 2, 3, 1).reshape(weight.shape[0], -1)
+
+
+def pack_conv_transpose2x2(weight: torch.Tensor, bias: torch.Tensor):
+    """ConvTranspose2d(k=2, s=2) weight [ci, co, 2, 2] -> GEMM weight [(dy, dx, co), ci] and bias tiled over the 4 sub-pixels."""
+    return weight.permute(2, 3, 1, 0).reshape(-1, weight.shape[0]), bias.float().repeat(4)
+
+
 class _Holder:
     """Keeps repacked device tensors alive for as long as a ctypes weight struct points at them."""
 
@@ -350,10 +371,9 @@ class MultiScaleQFormerProjector(_SpecModule):
             for l in range(2):
                 pre = f"{cn}.{l}."
                 W, b = sd[pre + "attn.in_proj_weight"].float(), sd[pre + "attn.in_proj_bias"].float()
-                g, be = sd[pre + "kv_norm.weight"].float(), sd[pre + "kv_norm.bias"].float()
-                Wkv = W[d:]                       # K rows then V rows
-                wk.append(Wkv * g[None, :])       # fold kv_norm scale into the columns
-                bk.append(b[d:] + Wkv @ be)       # and its shift into the bias
+                wf, bf = fold_kv_norm(W, b, sd[pre + "kv_norm.weight"], sd[pre + "kv_norm.bias"], d)
+                wk.append(wf)
+                bk.append(bf)
                 Bk = S.blocks[l]
                 Bk.qn_g, Bk.qn_b = hold.f32(sd[pre + "q_norm.weight"]), hold.f32(sd[pre + "q_norm.bias"])
                 Bk.w_q, Bk.b_q = hold.bf16(W[:d]), hold.f32(b[:d])
@@ -469,7 +489,7 @@ class ProjectorNeck(_SpecModule):
         w.w_conv1 = hold.bf16(sd["image_feature_neck.0.weight"].reshape(self.out_chans, self.hidden))
         w.ln1_g, w.ln1_b = hold.f32(sd["image_feature_neck.1.weight"]), hold.f32(sd["image_feature_neck.1.bias"])
         # [co, ci, ky, kx] -> [co, (ky, kx, ci)]: matches the channels-last im2col column order
-        w.w_conv3 = hold.bf16(sd["image_feature_neck.2.weight"].permute(0, 2, 3, 1).reshape(self.out_chans, -1))
+        w.w_conv3 = hold.bf16(pack_conv3x3(sd["image_feature_neck.2.weight"]))
         w.ln2_g, w.ln2_b = hold.f32(sd["image_feature_neck.3.weight"]), hold.f32(sd["image_feature_neck.3.bias"])
         self._packed = (w, hold)
         return self._packed
@@ -644,9 +664,8 @@ class MaskDecoderMultiScale(_SpecModule):
         w.fin_wo_t, w.fin_bo = lin_t(T + "final_attn_token_to_image.out_proj")
         w.nf_g, w.nf_b = hold.f32(sd[T + "norm_final_attn.weight"]), hold.f32(sd[T + "norm_final_attn.bias"])
         w.w_img_fin = hold.bf16(torch.cat([sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.v_proj.weight"]], 0))
-        up = sd["output_upscaling.0.weight"]  # ConvTranspose2d weight [Cin, Cout, 2, 2] -> rows (dy, dx, co), cols ci
-        w.w_up = hold.bf16(up.permute(2, 3, 1, 0).reshape(-1, up.shape[0]))
-        w.b_up = hold.f32(sd["output_upscaling.0.bias"].float().repeat(4))
+        w_up, b_up = pack_conv_transpose2x2(sd["output_upscaling.0.weight"], sd["output_upscaling.0.bias"])
+        w.w_up, w.b_up = hold.bf16(w_up), hold.f32(b_up)
         w.up_ln_g, w.up_ln_b = hold.f32(sd["output_upscaling.1.weight"]), hold.f32(sd["output_upscaling.1.bias"])
         for j, (wn, bn) in enumerate((("hyp_w0_t", "hyp_b0"), ("hyp_w1_t", "hyp_b1"), ("hyp_w2_t", "hyp_b2"))):
             ws_ = torch.stack([sd[f"output_hypernetworks_mlps.{i}.layers.{j}.weight"].t() for i in range(self.num_mask_tokens)], 0)

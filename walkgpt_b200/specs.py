@@ -210,8 +210,11 @@ def init_tensor(name: str, shape: Sequence[int], seed: int = 0) -> torch.Tensor:
         return r / math.sqrt(max(fan_in, 1))
     if "position_embedding" in name:
         return 0.1 * r
-    if any(k in name for k in ("token", "embed", "q_x", "q_global", "text_type")):
-        return 0.5 * r
+    parent = name.split(".")[-2] if "." in name else name
+    if leaf in ("pad_token", "q_x1", "q_x2", "q_x4", "q_global", "text_type") or (
+            leaf == "weight" and (parent.endswith("_token") or parent.endswith("_tokens") or parent.endswith("_embed")
+                                  or name.startswith("point_embeddings."))):
+        return 0.5 * r  # embedding tables / learned tokens
     return r / math.sqrt(max(fan_in, 1))
 
 
