@@ -84,6 +84,12 @@ typedef struct wg_gemm_args {
     const float* ln_gamma; /* WG_OUT_BF16_LN only */
     const float* ln_beta;
     float ln_eps;
+    /* "split-bf16" = an fp32-accurate matrix X stored as bf16 [rows, 2C]: hi = bf16(X) in columns [0,C), lo = bf16(X - hi) in
+     * [C,2C).  Used where the path needs near-fp32 accuracy at negligible cost (neck, mask decoder).
+     * a_k_wrap = 2C: A is split-bf16 and K = 3C walks [hi | lo | hi] against W' = [W_hi | W_hi | W_lo] (0 = plain A).
+     * split_out != 0: bf16 output modes write split-bf16 [M, 2N] (ldo >= 2N); in WG_OUT_BF16_LN `resid` is then split-bf16 too. */
+    int32_t a_k_wrap;
+    int32_t split_out;
     int32_t reserved;
 } wg_gemm_args;
 
@@ -203,33 +209,36 @@ WG_API int wg_ctp_forward(const wg_ctp_weights* w, const void* x, int x_is_bf16,
 /* A3 + A4 -- out_mm_projector MLP (llava_arch.py:38-42, used at :197-208) followed by image_feature_neck
  * (model/walkgpt.py:97-113, LayerNorm2d = segment_anything/modeling/common.py:31-43). */
 typedef struct wg_proj_neck_weights {
-    int32_t mm_hidden, hidden, out_chans, reserved;  /* 1024, H, 256 */
+    int32_t mm_hidden, hidden, out_chans;  /* 1024, H, 256 */
+    int32_t split_terms;                   /* neck GEMMs run on split-bf16 operands: 2 = W' is [W|W] (weights exactly bf16), 3 = [W_hi|W_hi|W_lo] */
     const void* w_fc1; const float* b_fc1;      /* bf16 [2H, mm_hidden] */
     const void* w_fc2; const float* b_fc2;      /* bf16 [H, 2H] */
-    const void* w_conv1;                        /* bf16 [256, H]           (1x1 conv, no bias) */
+    const void* w_conv1;                        /* bf16 [256, split_terms*H]   (1x1 conv, no bias), see wg_gemm_args.a_k_wrap */
     const float* ln1_g; const float* ln1_b;
-    const void* w_conv3;                        /* bf16 [256, 9*256]: column (ky*3+kx)*256 + ci  (3x3 conv, pad 1, no bias) */
+    const void* w_conv3;                        /* bf16 [256, split_terms*2304]: per term, column (ky*3+kx)*256 + ci  (3x3 conv, pad 1, no bias) */
     const float* ln2_g; const float* ln2_b;
 } wg_proj_neck_weights;
 
 WG_API size_t wg_proj_neck_workspace_bytes(const wg_proj_neck_weights* w, int rows);
-/* feats bf16 [B*g*g, mm_hidden] -> proj_out bf16 [B*g*g, H] (nullable) and the image embedding as TOKENS
- * emb_tokens bf16 [B*g*g, 256] (channels-last; nullable = projector only). */
+/* feats bf16 [B*g*g, mm_hidden] -> proj_out split-bf16 [B*g*g, 2H] (hi | lo; nullable) and the image embedding as TOKENS
+ * emb_tokens split-bf16 [B*g*g, 512] (channels-last, hi | lo; nullable = projector only). */
 WG_API int wg_proj_neck_forward(const wg_proj_neck_weights* w, const void* feats_bf16, int B, int grid_side,
                                 void* proj_out_bf16, void* emb_tokens_bf16, void* workspace, size_t workspace_bytes,
                                 void* stream);
 WG_API size_t wg_neck_workspace_bytes(int rows);
-/* image_feature_neck alone: proj tokens bf16 [B*g*g, H] (channels-last view of the NCHW input) -> emb tokens bf16 [B*g*g, 256]. */
+/* image_feature_neck alone: proj tokens split-bf16 [B*g*g, 2H] (channels-last view of the NCHW input) -> emb tokens split-bf16 [B*g*g, 512]. */
 WG_API int wg_neck_forward(const wg_proj_neck_weights* w, const void* proj_tokens_bf16, int B, int grid_side,
                            void* emb_tokens_bf16, void* workspace, size_t workspace_bytes, void* stream);
-/* tokens bf16 [B, L, C] -> NCHW [B, C, L] (fp32 or bf16): the layout the reference modules exchange. */
-WG_API int wg_tokens_to_nchw(const void* tokens_bf16, void* out, int out_is_bf16, int B, int L, int C, void* stream);
+/* tokens bf16 [B, L, C] (split != 0: split-bf16 [B, L, 2C]) -> NCHW [B, C, L] (fp32 or bf16): the layout the reference modules exchange. */
+WG_API int wg_tokens_to_nchw(const void* tokens_bf16, int split, void* out, int out_is_bf16, int B, int L, int C, void* stream);
 
 /* A6 + A7 -- PromptEncoder (text_embeds path, prompt_encoder.py:140-186) + MaskDecoderMultiScale.forward
  * (mask_decoder_multi_scale.py:87-213, level_num = 0) with its TwoWayTransformer (transformer.py:62-242),
  * batched over all P prompts of a batch of images.
- * "_t" matrices are TRANSPOSED bf16 [in_features][out_features] (token-side linears, read column-wise);
- * the others keep the nn.Linear layout bf16 [out_features][in_features] (image-side GEMMs). */
+ * "_t" matrices are TRANSPOSED fp32 [in_features][out_features] (token-side linears, read column-wise by CUDA cores);
+ * the image-side GEMM weights are bf16 [out_features][split_terms * in_features] = [W_hi | W_hi | W_lo] (split_terms = 3) or
+ * [W | W] (split_terms = 2, weights exactly representable in bf16): the image-side activations are split-bf16 (hi | lo),
+ * see wg_gemm_args.a_k_wrap, which gives this stage near-fp32 accuracy on the bf16 tensor cores. */
 typedef struct wg_twoway_layer {
     const void* sa_wq_t; const float* sa_bq; const void* sa_wk_t; const float* sa_bk;   /* self_attn: [256][256] */
     const void* sa_wv_t; const float* sa_bv; const void* sa_wo_t; const float* sa_bo;
@@ -242,14 +251,15 @@ typedef struct wg_twoway_layer {
     const float* n3_g; const float* n3_b;
     const void* i2t_wk_t; const float* i2t_bk;      /* cross_attn_image_to_token.k_proj [256][128] */
     const void* i2t_wv_t; const float* i2t_bv;      /* cross_attn_image_to_token.v_proj [256][128] */
-    const void* w_img;                              /* bf16 [384][256] = t2i.k_proj | t2i.v_proj | i2t.q_proj */
+    const void* w_img;                              /* bf16 [384][T*256]: rows = t2i.k_proj | t2i.v_proj | i2t.q_proj */
     const float* b_img;                             /* fp32 [hw][384] = (pe Wk^T + bk | bv | pe Wq^T + bq): dense PE folded in */
-    const void* i2t_wo; const float* i2t_bo;        /* cross_attn_image_to_token.out_proj: bf16 [256][128] */
+    const void* i2t_wo; const float* i2t_bo;        /* cross_attn_image_to_token.out_proj: bf16 [256][T*128] */
     const float* n4_g; const float* n4_b;
 } wg_twoway_layer;
 
 typedef struct wg_mask_decoder_weights {
     int32_t grid_h, grid_w, n_mask_tokens, up_stages;   /* 32, 32, 4, 1 */
+    int32_t split_terms, reserved;                      /* T = 2 or 3 (see above) */
     const float* out_tokens;     /* fp32 [1 + n_mask_tokens][256] = (iou_token ; mask_tokens) + level_embed[0] */
     const float* sparse_add;     /* fp32 [256] added to each text embedding (level_embed[0]); NULL = none */
     const float* no_mask;        /* fp32 [256] PromptEncoder.no_mask_embed (dense prompt embedding) */
@@ -257,12 +267,12 @@ typedef struct wg_mask_decoder_weights {
     const void* fin_wq_t; const float* fin_bq;      /* final_attn_token_to_image.q_proj [256][128] */
     const void* fin_wo_t; const float* fin_bo;      /* final_attn_token_to_image.out_proj [128][256] */
     const float* nf_g; const float* nf_b;           /* norm_final_attn */
-    const void* w_img_fin;                          /* bf16 [256][256] = final.k_proj | final.v_proj */
+    const void* w_img_fin;                          /* bf16 [256][T*256]: rows = final.k_proj | final.v_proj */
     const float* b_img_fin;                         /* fp32 [hw][256] = (pe Wk^T + bk | bv) */
-    const void* w_up;                               /* bf16 [4*32][256]: row (dy*2+dx)*32 + co = ConvT.weight[ci, co, dy, dx] */
+    const void* w_up;                               /* bf16 [4*32][T*256]: row (dy*2+dx)*32 + co = ConvT.weight[ci, co, dy, dx] */
     const float* b_up;                              /* fp32 [128] = ConvT.bias tiled over the 4 sub-pixels */
     const float* up_ln_g; const float* up_ln_b;     /* output_upscaling.1 (LayerNorm2d over 32 channels) */
-    const void* hyp_w0_t; const float* hyp_b0;      /* hypernetwork MLPs: bf16 [4][256][256], fp32 [4][256] */
+    const void* hyp_w0_t; const float* hyp_b0;      /* hypernetwork MLPs: fp32 [4][256][256], fp32 [4][256] */
     const void* hyp_w1_t; const float* hyp_b1;      /* [4][256][256] */
     const void* hyp_w2_t; const float* hyp_b2;      /* [4][256][32], fp32 [4][32] */
     const void* iou_w0_t; const float* iou_b0;      /* iou_prediction_head: [256][256] */
@@ -271,7 +281,7 @@ typedef struct wg_mask_decoder_weights {
 } wg_mask_decoder_weights;
 
 WG_API size_t wg_mask_decoder_workspace_bytes(int P, int hw);
-/* img_emb_tokens bf16 [B, hw, 256] (channels-last image embeddings), txt_emb fp32 [P, 256] (CTP outputs = sparse prompt
+/* img_emb_tokens split-bf16 [B, hw, 512] (channels-last image embeddings, hi | lo), txt_emb fp32 [P, 256] (CTP outputs = sparse prompt
  * embeddings), prompt_img int32 [P] (image index of each prompt; prompts of one image are contiguous).
  * low_res_out fp32 [P, n_out, 2*grid_h, 2*grid_w], iou_out fp32 [P, n_out]; n_out = 1 (multimask_output = 0) or 4.
  * depth_pool_out (nullable) fp32 [P, 33]: sigmoid(logit)-weighted sums of the 32 upscaled channels + the weight sum

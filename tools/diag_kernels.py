@@ -244,7 +244,7 @@ def t_post():
     print(f"time postprocess 768 masks (incl. torch.empty): {ms:.3f} ms -> {byts/ms/1e6:.1f} GB/s", flush=True)
 
 def t_path():
-    from walkgpt_b200.modules import GroundingPath
+    from walkgpt_b200.modules import GroundingPath, merge_split
     from oracle import path_a
     B, S, H = 2, 3, 4096
     m = GroundingPath(hidden_size=H, clip_layers=24, seed=1).cuda()
@@ -266,7 +266,7 @@ def t_path():
     stats("path vis_tokens", out["vis_tokens"].reshape(-1, H).float().cpu(), ref["vis_tokens"].reshape(-1, H), 3e-2)
     stats("path txt_emb", out["txt_emb"].cpu(), ref["txt_emb"], 2e-2)
     emb_ref = ref["img_emb"].flatten(2).permute(0, 2, 1).reshape(-1, 256)
-    stats("path img_emb", out["img_emb_tokens"].reshape(-1, 256).float().cpu(), emb_ref, 3e-2)
+    stats("path img_emb", merge_split(out["img_emb_split"]).reshape(-1, 256).cpu(), emb_ref, 3e-2)
     stats("path low_res", out["low_res"].reshape(B * S, -1).cpu(), ref["low_res"].reshape(B * S, -1), 3e-2)
     stats("path iou", out["iou"].cpu(), ref["iou"], 3e-2)
     stats("path logits", out["logits"].reshape(B * S, -1).cpu(), ref["logits"].reshape(B * S, -1), 3e-2)

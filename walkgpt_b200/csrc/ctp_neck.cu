@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(256) ctp_tail_kernel(const float* __restrict__
     }
 }
 
-// 3x3 / pad 1 im2col on a channels-last token grid: in [B, g, g, C] bf16 -> out [B*g*g, 9*C], column = (ky*3+kx)*C + c
-__global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int g, int C) {
+// 3x3 / pad 1 im2col on a channels-last token grid: in [B, g, g, in_ld] (C channels starting at the pointer) bf16 ->
+// out [B*g*g, out_ld] (9*C columns starting at the pointer), column = (ky*3+kx)*C + c
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, __nv_bfloat16* __restrict__ out, int out_ld,
+                                                        int B, int g, int C) {
     const int vec_per_row = 9 * C / 8;
     const long long total = (long long)B * g * g * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -71,21 +73,27 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __r
         const int y = pos / g + ky - 1, x = pos % g + kx - 1;
         uint4 val = make_uint4(0, 0, 0, 0);
         if (y >= 0 && y < g && x >= 0 && x < g)
-            val = *reinterpret_cast<const uint4*>(in + (((size_t)b * g + y) * g + x) * C + c8 * 8);
-        *reinterpret_cast<uint4*>(out + tok * (9 * C) + v * 8) = val;
+            val = *reinterpret_cast<const uint4*>(in + (((size_t)b * g + y) * g + x) * in_ld + c8 * 8);
+        *reinterpret_cast<uint4*>(out + tok * out_ld + v * 8) = val;
     }
 }
 
-// token-major [B, L, C] bf16 -> NCHW [B, C, L] (fp32 or bf16); 32x32 smem tile transpose
+// token-major [B, L, C] bf16 (or split-bf16 [B, L, 2C]: value = hi + lo) -> NCHW [B, C, L] (fp32 or bf16); 32x32 smem tile transpose
 template <typename TOut>
-__global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, TOut* __restrict__ out, int L, int C) {
+__global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, TOut* __restrict__ out, int L, int C, int split) {
+    const int ld = split ? 2 * C : C;
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     for (int j = ty; j < 32; j += 8) {
         int l = l0 + j, c = c0 + tx;
-        tile[j][tx] = (l < L && c < C) ? __bfloat162float(in[((size_t)b * L + l) * C + c]) : 0.f;
+        float v = 0.f;
+        if (l < L && c < C) {
+            const __nv_bfloat16* pr = in + ((size_t)b * L + l) * ld + c;
+            v = __bfloat162float(pr[0]) + (split ? __bfloat162float(pr[C]) : 0.f);
+        }
+        tile[j][tx] = v;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -96,13 +104,13 @@ __global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const __nv_bfloat16
 
 }  // namespace
 
-int launch_tokens_to_nchw(const void* tokens_bf16, void* out, int out_is_bf16, int B, int L, int C, cudaStream_t s) {
+int launch_tokens_to_nchw(const void* tokens_bf16, int split, void* out, int out_is_bf16, int B, int L, int C, cudaStream_t s) {
     dim3 grid((L + 31) / 32, (C + 31) / 32, B);
     Prof prof("tokens_to_nchw", s, 0.0, (double)B * L * C * (2.0 + (out_is_bf16 ? 2.0 : 4.0)));
     if (out_is_bf16)
-        tokens_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(tokens_bf16), static_cast<__nv_bfloat16*>(out), L, C);
+        tokens_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(tokens_bf16), static_cast<__nv_bfloat16*>(out), L, C, split);
     else
-        tokens_to_nchw_kernel<float><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(tokens_bf16), static_cast<float*>(out), L, C);
+        tokens_to_nchw_kernel<float><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(tokens_bf16), static_cast<float*>(out), L, C, split);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -149,42 +157,49 @@ extern "C" int wg_ctp_forward(const wg_ctp_weights* w, const void* x, int x_is_b
     return WG_OK;
 }
 
-// neck: 1x1 conv (GEMM) + LayerNorm2d fused in the epilogue; 3x3 conv as im2col GEMM + LayerNorm2d epilogue
-static int neck_impl(const wg_proj_neck_weights* w, const void* pr, int B, int grid_side, void* emb_tokens_bf16, void* n1, void* col,
+// neck, computed at near-fp32 accuracy with split-bf16 operands (see wg_gemm_args): 1x1 conv (GEMM) + LayerNorm2d fused in
+// the epilogue; 3x3 conv as im2col GEMM + LayerNorm2d epilogue.  pr: split-bf16 [rows, 2H]; emb: split-bf16 [rows, 512].
+static int neck_impl(const wg_proj_neck_weights* w, const void* pr, int B, int grid_side, void* emb_tokens_split, void* n1, void* col,
                      cudaStream_t s) {
     const int rows = B * grid_side * grid_side;
     const int H = w->hidden;
+    const int T = w->split_terms;  // 2: W' = [W|W] (weights exactly bf16), 3: W' = [W_hi|W_hi|W_lo]
     {
         wg_gemm_args a = {};
-        a.A = pr; a.lda = H; a.W = w->w_conv1; a.ldw = H; a.M = rows; a.N = 256; a.K = H;
-        a.out_mode = WG_OUT_BF16_LN; a.out = n1; a.ldo = 256; a.ln_gamma = w->ln1_g; a.ln_beta = w->ln1_b; a.ln_eps = 1e-6f;
+        a.A = pr; a.lda = 2 * H; a.W = w->w_conv1; a.ldw = (long long)T * H; a.M = rows; a.N = 256; a.K = T * H;
+        a.a_k_wrap = T == 3 ? 2 * H : 0;
+        a.out_mode = WG_OUT_BF16_LN; a.split_out = 1; a.out = n1; a.ldo = 512; a.ln_gamma = w->ln1_g; a.ln_beta = w->ln1_b; a.ln_eps = 1e-6f;
         WG_TRY(wg_gemm(&a, s));
     }
     {
         const long long total = (long long)rows * (9 * 256 / 8);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        Prof prof("im2col3x3", s, 0.0, (double)rows * 256 * 2 * 10.0);
-        im2col3x3_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(n1), static_cast<__nv_bfloat16*>(col), B, grid_side, 256);
+        Prof prof("im2col3x3", s, 0.0, (double)rows * 256 * 2 * 20.0, 2);
+        const __nv_bfloat16* nin = static_cast<const __nv_bfloat16*>(n1);
+        __nv_bfloat16* cout_ = static_cast<__nv_bfloat16*>(col);
+        im2col3x3_kernel<<<(unsigned)blocks, 256, 0, s>>>(nin, 512, cout_, 2 * 2304, B, grid_side, 256);              // hi
+        im2col3x3_kernel<<<(unsigned)blocks, 256, 0, s>>>(nin + 256, 512, cout_ + 2304, 2 * 2304, B, grid_side, 256);  // lo
         WG_CHECK_CUDA(cudaGetLastError());
     }
     {
         wg_gemm_args a = {};
-        a.A = col; a.lda = 9 * 256; a.W = w->w_conv3; a.ldw = 9 * 256; a.M = rows; a.N = 256; a.K = 9 * 256;
-        a.out_mode = WG_OUT_BF16_LN; a.out = emb_tokens_bf16; a.ldo = 256; a.ln_gamma = w->ln2_g; a.ln_beta = w->ln2_b; a.ln_eps = 1e-6f;
+        a.A = col; a.lda = 2 * 2304; a.W = w->w_conv3; a.ldw = (long long)T * 2304; a.M = rows; a.N = 256; a.K = T * 2304;
+        a.a_k_wrap = T == 3 ? 2 * 2304 : 0;
+        a.out_mode = WG_OUT_BF16_LN; a.split_out = 1; a.out = emb_tokens_split; a.ldo = 512; a.ln_gamma = w->ln2_g; a.ln_beta = w->ln2_b;
+        a.ln_eps = 1e-6f;
         WG_TRY(wg_gemm(&a, s));
     }
     return WG_OK;
 }
 
-
 extern "C" size_t wg_proj_neck_workspace_bytes(const wg_proj_neck_weights* w, int rows) {
     if (!w) return 0;
     Workspace ws(nullptr, 0);
     ws.take((size_t)rows * 2 * w->hidden * 2);
-    ws.take((size_t)rows * w->hidden * 2);
-    ws.take((size_t)rows * 256 * 2);
-    ws.take((size_t)rows * 9 * 256 * 2);
+    ws.take((size_t)rows * 2 * w->hidden * 2);
+    ws.take((size_t)rows * 512 * 2);
+    ws.take((size_t)rows * 2 * 2304 * 2);
     return ws.used();
 }
 
@@ -195,6 +210,8 @@ extern "C" int wg_proj_neck_forward(const wg_proj_neck_weights* w, const void* f
     WG_REQUIRE(w && feats_bf16 && workspace, "wg_proj_neck_forward: null pointer");
     WG_REQUIRE(B > 0 && grid_side > 0, "wg_proj_neck_forward: bad sizes");
     WG_REQUIRE(w->out_chans == 256, "wg_proj_neck_forward: out_chans must be 256");
+    WG_REQUIRE(w->split_terms == 2 || w->split_terms == 3, "wg_proj_neck_forward: split_terms must be 2 or 3");
+    WG_REQUIRE(w->hidden % 64 == 0, "wg_proj_neck_forward: hidden must be a multiple of 64");
     if (!device_is_sm100()) {
         set_error("wg_proj_neck_forward: this library only runs on sm_100 (B200) devices; there is no fallback");
         return WG_ERR_UNSUPPORTED;
@@ -203,22 +220,27 @@ extern "C" int wg_proj_neck_forward(const wg_proj_neck_weights* w, const void* f
     const int H = w->hidden;
     Workspace ws(workspace, workspace_bytes);
     void* h1 = ws.take((size_t)rows * 2 * H * 2);
-    void* pr = ws.take((size_t)rows * H * 2);
-    void* n1 = ws.take((size_t)rows * 256 * 2);
-    void* col = ws.take((size_t)rows * 9 * 256 * 2);
+    void* pr = ws.take((size_t)rows * 2 * H * 2);   // split-bf16 projector output [rows, 2H]
+    void* n1 = ws.take((size_t)rows * 512 * 2);
+    void* col = ws.take((size_t)rows * 2 * 2304 * 2);
     WG_REQUIRE(h1 && pr && n1 && col, "wg_proj_neck_forward: workspace too small");
     if (proj_out_bf16) pr = proj_out_bf16;
     // out_mm_projector: Linear(mm_hidden -> 2H) + GELU(erf) + Linear(2H -> H)
     WG_TRY(gemm_bf16_out(feats_bf16, w->mm_hidden, w->w_fc1, rows, 2 * H, w->mm_hidden, w->b_fc1, WG_ACT_GELU_ERF, h1, 2 * H, s));
-    WG_TRY(gemm_bf16_out(h1, 2 * H, w->w_fc2, rows, H, 2 * H, w->b_fc2, WG_ACT_NONE, pr, H, s));
+    {
+        wg_gemm_args a = {};
+        a.A = h1; a.lda = 2 * H; a.W = w->w_fc2; a.ldw = 2 * H; a.M = rows; a.N = H; a.K = 2 * H;
+        a.bias = w->b_fc2; a.bias_period = 1; a.out_mode = WG_OUT_BF16; a.split_out = 1; a.out = pr; a.ldo = 2 * H;
+        WG_TRY(wg_gemm(&a, s));
+    }
     if (!emb_tokens_bf16) return WG_OK;
     return neck_impl(w, pr, B, grid_side, emb_tokens_bf16, n1, col, s);
 }
 
 extern "C" size_t wg_neck_workspace_bytes(int rows) {
     Workspace ws(nullptr, 0);
-    ws.take((size_t)rows * 256 * 2);
-    ws.take((size_t)rows * 9 * 256 * 2);
+    ws.take((size_t)rows * 512 * 2);
+    ws.take((size_t)rows * 2 * 2304 * 2);
     return ws.used();
 }
 
@@ -234,17 +256,17 @@ extern "C" int wg_neck_forward(const wg_proj_neck_weights* w, const void* proj_t
     }
     const int rows = B * grid_side * grid_side;
     Workspace ws(workspace, workspace_bytes);
-    void* n1 = ws.take((size_t)rows * 256 * 2);
-    void* col = ws.take((size_t)rows * 9 * 256 * 2);
+    void* n1 = ws.take((size_t)rows * 512 * 2);
+    void* col = ws.take((size_t)rows * 2 * 2304 * 2);
     WG_REQUIRE(n1 && col, "wg_neck_forward: workspace too small");
     return neck_impl(w, proj_tokens_bf16, B, grid_side, emb_tokens_bf16, n1, col, s);
 }
 
-extern "C" int wg_tokens_to_nchw(const void* tokens_bf16, void* out, int out_is_bf16, int B, int L, int C, void* stream_) {
+extern "C" int wg_tokens_to_nchw(const void* tokens_bf16, int split, void* out, int out_is_bf16, int B, int L, int C, void* stream_) {
     WG_REQUIRE(tokens_bf16 && out && B > 0 && L > 0 && C > 0, "wg_tokens_to_nchw: bad arguments");
     if (!device_is_sm100()) {
         set_error("wg_tokens_to_nchw: this library only runs on sm_100 (B200) devices; there is no fallback");
         return WG_ERR_UNSUPPORTED;
     }
-    return launch_tokens_to_nchw(tokens_bf16, out, out_is_bf16, B, L, C, static_cast<cudaStream_t>(stream_));
+    return launch_tokens_to_nchw(tokens_bf16, split, out, out_is_bf16, B, L, C, static_cast<cudaStream_t>(stream_));
 }

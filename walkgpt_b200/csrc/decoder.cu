@@ -1,3 +1,7 @@
+// Numerics: this stage is ~1 % of the path's FLOPs but dominates the mask-logit error when run in plain bf16, so it runs at
+// near-fp32 accuracy: image-side activations are kept as split-bf16 (hi | lo) and multiplied against [W_hi | W_hi | W_lo]
+// on the tensor cores (3 bf16 products ~ 16-bit mantissas), projections consumed by CUDA cores are stored in fp32, and the
+// token-side weights are fp32.
 // A6 + A7: prompt encoder (text-embedding path) and the SAM-style two-way mask decoder, batched over ALL prompts of a
 // batch of images (the reference loops per image and per prompt: model/walkgpt.py:511-535, mask_decoder*.py).
 //
@@ -24,21 +28,14 @@ constexpr int NT = 6;    // tokens per prompt: iou, 4 mask tokens, 1 text embedd
 constexpr int CI = 128;  // cross-attention internal dim (downsample 2)
 constexpr int TK_THREADS = 256;
 
-__device__ __forceinline__ float2 ldbf2(const __nv_bfloat16* p) {
-    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-}
 
-// out[t][n] = act( base + sum_k in[t][k] * Wt[k][n] ), t < NT.   in/out in shared memory, Wt bf16 [K][N] in global.
-// base = bias[n] (+ out[t][n] when `accumulate`).  Split-K over thread groups with shared-memory atomics.
-__device__ void tok_linear(const float* in, int ldi, int K, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias, float* out,
-                           int ldo, int N, bool accumulate, bool relu) {
+// out[t][n] = act( base + sum_k in[t][k] * Wt[k][n] ), t < NT.   in/out in shared memory, Wt fp32 [K][N] in global.
+// base = bias[n] (+ out[t][n] when `accumulate`).  Split-K over thread groups; the partial sums go through `part`
+// (>= TK_THREADS * 2 * NT floats of shared memory) and are added in a fixed order, so results are run-to-run deterministic.
+constexpr int TOK_PART_FLOATS = TK_THREADS * 2 * NT;
+__device__ void tok_linear(const float* in, int ldi, int K, const float* __restrict__ Wt, const float* __restrict__ bias, float* out,
+                           int ldo, int N, bool accumulate, bool relu, float* part) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < NT * N; i += TK_THREADS) {
-        const int t = i / N, n = i - t * N;
-        float b = bias ? bias[n] : 0.f;
-        out[t * ldo + n] = accumulate ? out[t * ldo + n] + b : b;
-    }
-    __syncthreads();
     const int pairs = N >> 1;
     int ks = TK_THREADS / pairs;
     if (ks < 1) ks = 1;
@@ -51,10 +48,10 @@ __device__ void tok_linear(const float* in, int ldi, int K, const __nv_bfloat16*
         float a0[NT], a1[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t) a0[t] = a1[t] = 0.f;
-        const __nv_bfloat16* wp = Wt + (size_t)k0 * N + pr * 2;
+        const float* wp = Wt + (size_t)k0 * N + pr * 2;
 #pragma unroll 4
         for (int k = k0; k < k1; ++k, wp += N) {
-            const float2 w = ldbf2(wp);
+            const float2 w = __ldg(reinterpret_cast<const float2*>(wp));
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const float x = in[t * ldi + k];
@@ -62,17 +59,30 @@ __device__ void tok_linear(const float* in, int ldi, int K, const __nv_bfloat16*
                 a1[t] = fmaf(x, w.y, a1[t]);
             }
         }
+        if (ks == 1) {  // this thread owns the whole dot product
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            atomicAdd(&out[t * ldo + pr * 2], a0[t]);
-            atomicAdd(&out[t * ldo + pr * 2 + 1], a1[t]);
+            for (int t = 0; t < NT; ++t) {
+                float b0v = bias ? bias[pr * 2] : 0.f, b1v = bias ? bias[pr * 2 + 1] : 0.f;
+                float v0 = a0[t] + b0v + (accumulate ? out[t * ldo + pr * 2] : 0.f);
+                float v1 = a1[t] + b1v + (accumulate ? out[t * ldo + pr * 2 + 1] : 0.f);
+                out[t * ldo + pr * 2] = relu ? fmaxf(v0, 0.f) : v0;
+                out[t * ldo + pr * 2 + 1] = relu ? fmaxf(v1, 0.f) : v1;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                part[(kpart * NT + t) * N + pr * 2] = a0[t];
+                part[(kpart * NT + t) * N + pr * 2 + 1] = a1[t];
+            }
         }
     }
     __syncthreads();
-    if (relu) {
+    if (ks > 1) {
         for (int i = tid; i < NT * N; i += TK_THREADS) {
             const int t = i / N, n = i - t * N;
-            out[t * ldo + n] = fmaxf(out[t * ldo + n], 0.f);
+            float v = (bias ? bias[n] : 0.f) + (accumulate ? out[t * ldo + n] : 0.f);
+            for (int kp = 0; kp < ks; ++kp) v += part[(kp * NT + t) * N + n];
+            out[t * ldo + n] = relu ? fmaxf(v, 0.f) : v;
         }
         __syncthreads();
     }
@@ -144,11 +154,10 @@ __device__ void tok_self_attn_core(const float* Q, const float* K, const float* 
     __syncthreads();
 }
 
-// token -> image attention: Qt [NT][128] (smem), K/V rows in global (bf16, row pitch ldkv), 8 heads x 16.  A [NT][128] out (smem)
-__device__ void tok_t2i_attention(const float* Qt, const __nv_bfloat16* __restrict__ kv, int ldkv, int k_off, int v_off, int hw, float* A,
-                                  float* sc /* [NT][hw] */) {
+// token -> image attention: Qt [NT][128] (smem), K/V rows in global (fp32, row pitch ldkv), 8 heads x 16.  A [NT][128] out (smem)
+__device__ void tok_t2i_attention(const float* Qt, const float* __restrict__ kv, int ldkv, int k_off, int v_off, int hw, float* A,
+                                  float* sc /* [NT][hw] */, float* part) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < NT * CI; i += TK_THREADS) A[i] = 0.f;
     for (int h = 0; h < 8; ++h) {
         float qh[NT][16];
 #pragma unroll
@@ -156,18 +165,12 @@ __device__ void tok_t2i_attention(const float* Qt, const __nv_bfloat16* __restri
 #pragma unroll
             for (int e = 0; e < 16; ++e) qh[t][e] = Qt[t * CI + h * 16 + e];
         for (int key = tid; key < hw; key += TK_THREADS) {
-            const uint4* kr = reinterpret_cast<const uint4*>(kv + (size_t)key * ldkv + k_off + h * 16);
+            const float4* kr = reinterpret_cast<const float4*>(kv + (size_t)key * ldkv + k_off + h * 16);
             float kf[16];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint4 u = kr[c];
-                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float2 f = __bfloat1622float2(hh[e]);
-                    kf[c * 8 + e * 2] = f.x;
-                    kf[c * 8 + e * 2 + 1] = f.y;
-                }
+            for (int c = 0; c < 4; ++c) {
+                float4 u = __ldg(kr + c);
+                kf[c * 4] = u.x; kf[c * 4 + 1] = u.y; kf[c * 4 + 2] = u.z; kf[c * 4 + 3] = u.w;
             }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -200,12 +203,19 @@ __device__ void tok_t2i_attention(const float* Qt, const __nv_bfloat16* __restri
 #pragma unroll
             for (int t = 0; t < NT; ++t) o[t] = 0.f;
             for (int key = grp; key < hw; key += 16) {
-                const float v = __bfloat162float(kv[(size_t)key * ldkv + v_off + h * 16 + d]);
+                const float v = __ldg(kv + (size_t)key * ldkv + v_off + h * 16 + d);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) o[t] = fmaf(sc[t * hw + key], v, o[t]);
             }
 #pragma unroll
-            for (int t = 0; t < NT; ++t) atomicAdd(&A[t * CI + h * 16 + d], o[t]);
+            for (int t = 0; t < NT; ++t) part[(grp * NT + t) * 16 + d] = o[t];
+        }
+        __syncthreads();
+        if (tid < NT * 16) {  // fixed-order reduction over the 16 key groups
+            const int t = tid >> 4, d = tid & 15;
+            float v = 0.f;
+            for (int gI = 0; gI < 16; ++gI) v += part[(gI * NT + t) * 16 + d];
+            A[t * CI + h * 16 + d] = v;
         }
         __syncthreads();
     }
@@ -221,7 +231,7 @@ struct TokArgs {
     const float* out_tokens;   // [1+n_mask][256]
     const float* sparse_add;   // [256] or null
     const float* txt;          // [P][256]
-    const __nv_bfloat16* kv;   // image-side projections of this phase, [P*hw][ldkv]
+    const float* kv;           // image-side projections of this phase, fp32 [P*hw][ldkv]
     int ldkv;
     float* Tq;                 // [P][NT][256] running queries
     float* Tpe;                // [P][NT][256] token positional term (= initial tokens)
@@ -239,11 +249,12 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
     float* b2 = b1 + NT * C;
     float* b3 = b2 + NT * C;
     float* big = b3 + NT * C;      // [NT][2048]
-    float* sc = big + NT * 2048;   // [NT][hw]
+    float* part = big + NT * 2048;       // [TOK_PART_FLOATS] split-K partial sums
+    float* sc = part + TOK_PART_FLOATS;  // [NT][max(hw, 48)]
     const int p = blockIdx.x;
     const int tid = threadIdx.x;
-    const __nv_bfloat16* kv = a.kv + (size_t)p * a.hw * a.ldkv;
-    const __nv_bfloat16* W;
+    const float* kv = a.kv + (size_t)p * a.hw * a.ldkv;
+    const float* W;
 
     if (a.phase == 0) {
         for (int i = tid; i < NT * C; i += TK_THREADS) {
@@ -270,30 +281,30 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
         } else {
             tok_add(b3, q, qpe, NT * C);
         }
-        tok_linear(b3, C, C, (const __nv_bfloat16*)L.sa_wq_t, L.sa_bq, b0, C, C, false, false);
-        tok_linear(b3, C, C, (const __nv_bfloat16*)L.sa_wk_t, L.sa_bk, b1, C, C, false, false);
-        tok_linear(q, C, C, (const __nv_bfloat16*)L.sa_wv_t, L.sa_bv, b2, C, C, false, false);
+        tok_linear(b3, C, C, (const float*)L.sa_wq_t, L.sa_bq, b0, C, C, false, false, part);
+        tok_linear(b3, C, C, (const float*)L.sa_wk_t, L.sa_bk, b1, C, C, false, false, part);
+        tok_linear(q, C, C, (const float*)L.sa_wv_t, L.sa_bv, b2, C, C, false, false, part);
         tok_self_attn_core(b0, b1, b2, b3, sc);
         if (a.phase == 0) {
-            tok_linear(b3, C, C, (const __nv_bfloat16*)L.sa_wo_t, L.sa_bo, q, C, C, false, false);  // replaces the queries
+            tok_linear(b3, C, C, (const float*)L.sa_wo_t, L.sa_bo, q, C, C, false, false, part);  // replaces the queries
         } else {
-            tok_linear(b3, C, C, (const __nv_bfloat16*)L.sa_wo_t, L.sa_bo, q, C, C, true, false);   // residual
+            tok_linear(b3, C, C, (const float*)L.sa_wo_t, L.sa_bo, q, C, C, true, false, part);   // residual
         }
         tok_layernorm(q, L.n1_g, L.n1_b, 1e-5f);
         // ---- (2) tokens attend to the image
         tok_add(b3, q, qpe, NT * C);
-        tok_linear(b3, C, C, (const __nv_bfloat16*)L.t2i_wq_t, L.t2i_bq, b0, CI, CI, false, false);
-        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc);
-        tok_linear(b1, CI, CI, (const __nv_bfloat16*)L.t2i_wo_t, L.t2i_bo, q, C, C, true, false);
+        tok_linear(b3, C, C, (const float*)L.t2i_wq_t, L.t2i_bq, b0, CI, CI, false, false, part);
+        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part);
+        tok_linear(b1, CI, CI, (const float*)L.t2i_wo_t, L.t2i_bo, q, C, C, true, false, part);
         tok_layernorm(q, L.n2_g, L.n2_b, 1e-5f);
         // ---- (3) MLP
-        tok_linear(q, C, C, (const __nv_bfloat16*)L.mlp_w1_t, L.mlp_b1, big, 2048, 2048, false, true);
-        tok_linear(big, 2048, 2048, (const __nv_bfloat16*)L.mlp_w2_t, L.mlp_b2, q, C, C, true, false);
+        tok_linear(q, C, C, (const float*)L.mlp_w1_t, L.mlp_b1, big, 2048, 2048, false, true, part);
+        tok_linear(big, 2048, 2048, (const float*)L.mlp_w2_t, L.mlp_b2, q, C, C, true, false, part);
         tok_layernorm(q, L.n3_g, L.n3_b, 1e-5f);
         // ---- (4) token-side K/V for the image->token attention
         tok_add(b3, q, qpe, NT * C);
-        tok_linear(b3, C, C, (const __nv_bfloat16*)L.i2t_wk_t, L.i2t_bk, b0, CI, CI, false, false);
-        tok_linear(q, C, C, (const __nv_bfloat16*)L.i2t_wv_t, L.i2t_bv, b1, CI, CI, false, false);
+        tok_linear(b3, C, C, (const float*)L.i2t_wk_t, L.i2t_bk, b0, CI, CI, false, false, part);
+        tok_linear(q, C, C, (const float*)L.i2t_wv_t, L.i2t_bv, b1, CI, CI, false, false, part);
         for (int i = tid; i < NT * CI; i += TK_THREADS) {
             a.KT[(size_t)p * NT * CI + i] = b0[i];
             a.VT[(size_t)p * NT * CI + i] = b1[i];
@@ -302,9 +313,9 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
     } else {
         // ---- final token->image attention, LayerNorm, hypernetworks, IoU head
         tok_add(b3, q, qpe, NT * C);
-        tok_linear(b3, C, C, (const __nv_bfloat16*)a.fin_wq_t, a.fin_bq, b0, CI, CI, false, false);
-        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc);
-        tok_linear(b1, CI, CI, (const __nv_bfloat16*)a.fin_wo_t, a.fin_bo, q, C, C, true, false);
+        tok_linear(b3, C, C, (const float*)a.fin_wq_t, a.fin_bq, b0, CI, CI, false, false, part);
+        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part);
+        tok_linear(b1, CI, CI, (const float*)a.fin_wo_t, a.fin_bo, q, C, C, true, false, part);
         tok_layernorm(q, a.nf_g, a.nf_b, 1e-5f);
         for (int i = tid; i < NT * C; i += TK_THREADS) a.Tq[(size_t)p * NT * C + i] = q[i];
         // hypernetwork MLP m acts on mask token (1+m).  tok_linear works on NT rows; we feed row-replicated inputs
@@ -312,25 +323,49 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
         for (int m = 0; m < a.n_mask_tokens; ++m) {
             for (int i = tid; i < NT * C; i += TK_THREADS) b3[i] = q[(1 + m) * C + (i % C)];
             __syncthreads();
-            W = (const __nv_bfloat16*)a.hyp_w0_t + (size_t)m * C * C;
-            tok_linear(b3, C, C, W, a.hyp_b0 + m * C, b0, C, C, false, true);
-            W = (const __nv_bfloat16*)a.hyp_w1_t + (size_t)m * C * C;
-            tok_linear(b0, C, C, W, a.hyp_b1 + m * C, b1, C, C, false, true);
-            W = (const __nv_bfloat16*)a.hyp_w2_t + (size_t)m * C * 32;
-            tok_linear(b1, C, C, W, a.hyp_b2 + m * 32, b2, 32, 32, false, false);
+            W = (const float*)a.hyp_w0_t + (size_t)m * C * C;
+            tok_linear(b3, C, C, W, a.hyp_b0 + m * C, b0, C, C, false, true, part);
+            W = (const float*)a.hyp_w1_t + (size_t)m * C * C;
+            tok_linear(b0, C, C, W, a.hyp_b1 + m * C, b1, C, C, false, true, part);
+            W = (const float*)a.hyp_w2_t + (size_t)m * C * 32;
+            tok_linear(b1, C, C, W, a.hyp_b2 + m * 32, b2, 32, 32, false, false, part);
             for (int i = tid; i < 32; i += TK_THREADS) a.hyper[((size_t)p * a.n_mask_tokens + m) * 32 + i] = b2[i];
             __syncthreads();
         }
         for (int i = tid; i < NT * C; i += TK_THREADS) b3[i] = q[i % C];  // iou token = row 0
         __syncthreads();
-        tok_linear(b3, C, C, (const __nv_bfloat16*)a.iou_w0_t, a.iou_b0, b0, C, C, false, true);
-        tok_linear(b0, C, C, (const __nv_bfloat16*)a.iou_w1_t, a.iou_b1, b1, C, C, false, true);
-        tok_linear(b1, C, C, (const __nv_bfloat16*)a.iou_w2_t, a.iou_b2, b2, 8, a.n_mask_tokens, false, false);
+        tok_linear(b3, C, C, (const float*)a.iou_w0_t, a.iou_b0, b0, C, C, false, true, part);
+        tok_linear(b0, C, C, (const float*)a.iou_w1_t, a.iou_b1, b1, C, C, false, true, part);
+        tok_linear(b1, C, C, (const float*)a.iou_w2_t, a.iou_b2, b2, 8, a.n_mask_tokens, false, false, part);
         for (int i = tid; i < a.n_mask_tokens; i += TK_THREADS) a.iou[(size_t)p * a.n_mask_tokens + i] = b2[i];
     }
 }
 
-// keys0[p, pos, :] = img_emb[img(p), pos, :] + no_mask_embed      (bf16, channels-last)
+__device__ __forceinline__ void split_store8(__nv_bfloat16* hi_ptr, __nv_bfloat16* lo_ptr, const float (&v)[8]) {
+    uint4 h, l;
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat16 h0 = __float2bfloat16(v[2 * e]), h1 = __float2bfloat16(v[2 * e + 1]);
+        hp[e] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+        lp[e] = pack_bf16x2(v[2 * e] - __bfloat162float(h0), v[2 * e + 1] - __bfloat162float(h1));
+    }
+    *reinterpret_cast<uint4*>(hi_ptr) = h;
+    *reinterpret_cast<uint4*>(lo_ptr) = l;
+}
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float2 t = __bfloat1622float2(h[e]);
+        v[2 * e] = t.x;
+        v[2 * e + 1] = t.y;
+    }
+}
+
+// keys0[p, pos, :] = img_emb[img(p), pos, :] + no_mask_embed      (split-bf16 in [B*hw, 512], split-bf16 out [P*hw, 512])
 __global__ void __launch_bounds__(256) expand_keys_kernel(const __nv_bfloat16* __restrict__ emb, const int* __restrict__ prompt_img,
                                                           const float* __restrict__ no_mask, __nv_bfloat16* __restrict__ keys, int P, int hw) {
     const long long total = (long long)P * hw * (C / 8);
@@ -339,22 +374,18 @@ __global__ void __launch_bounds__(256) expand_keys_kernel(const __nv_bfloat16* _
         const long long row = i / (C / 8);
         const int p = (int)(row / hw), pos = (int)(row % hw);
         const int img = prompt_img[p];
-        uint4 u = *reinterpret_cast<const uint4*>(emb + ((size_t)img * hw + pos) * C + c8 * 8);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-        float4 n0 = *reinterpret_cast<const float4*>(no_mask + c8 * 8);
-        float4 n1 = *reinterpret_cast<const float4*>(no_mask + c8 * 8 + 4);
-        float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
-        uint4 o;
-        o.x = pack_bf16x2(a.x + n0.x, a.y + n0.y);
-        o.y = pack_bf16x2(b.x + n0.z, b.y + n0.w);
-        o.z = pack_bf16x2(c.x + n1.x, c.y + n1.y);
-        o.w = pack_bf16x2(d.x + n1.z, d.y + n1.w);
-        *reinterpret_cast<uint4*>(keys + row * C + c8 * 8) = o;
+        const __nv_bfloat16* src = emb + ((size_t)img * hw + pos) * (2 * C) + c8 * 8;
+        float hi[8], lo[8], v[8];
+        load8_bf16(src, hi);
+        load8_bf16(src + C, lo);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = hi[e] + lo[e] + no_mask[c8 * 8 + e];
+        split_store8(keys + row * (2 * C) + c8 * 8, keys + row * (2 * C) + C + c8 * 8, v);
     }
 }
 
-// image -> token attention, one thread per image position (6 keys, 8 heads x 16): out bf16 [P*hw][128]
-__global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16* __restrict__ kvq, int ldkv, int q_off, const float* __restrict__ KT,
+// image -> token attention, one thread per image position (6 keys, 8 heads x 16): q fp32 in, out split-bf16 [P*hw][2*128]
+__global__ void __launch_bounds__(256) i2t_attention_kernel(const float* __restrict__ kvq, int ldkv, int q_off, const float* __restrict__ KT,
                                                             const float* __restrict__ VT, __nv_bfloat16* __restrict__ out, int hw) {
     __shared__ float kt[NT * CI], vt[NT * CI];
     const int p = blockIdx.y;
@@ -366,21 +397,15 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16*
     const int pos = blockIdx.x * 256 + threadIdx.x;
     if (pos >= hw) return;
     const size_t row = (size_t)p * hw + pos;
-    const uint4* qr = reinterpret_cast<const uint4*>(kvq + row * ldkv + q_off);
-    uint4* orow = reinterpret_cast<uint4*>(out + row * CI);
+    const float4* qr = reinterpret_cast<const float4*>(kvq + row * ldkv + q_off);
+    __nv_bfloat16* orow = out + row * (2 * CI);
 #pragma unroll 1
     for (int h = 0; h < 8; ++h) {
         float qf[16];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint4 u = qr[h * 2 + c];
-            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(hh[e]);
-                qf[c * 8 + e * 2] = f.x;
-                qf[c * 8 + e * 2 + 1] = f.y;
-            }
+        for (int c = 0; c < 4; ++c) {
+            float4 u = __ldg(qr + h * 4 + c);
+            qf[c * 4] = u.x; qf[c * 4 + 1] = u.y; qf[c * 4 + 2] = u.z; qf[c * 4 + 3] = u.w;
         }
         float s[NT], mx = -INFINITY;
 #pragma unroll
@@ -407,11 +432,14 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16*
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] = fmaf(pt, vt[t * CI + h * 16 + e], o[e]);
         }
-        uint4 u0, u1;
-        u0.x = pack_bf16x2(o[0], o[1]); u0.y = pack_bf16x2(o[2], o[3]); u0.z = pack_bf16x2(o[4], o[5]); u0.w = pack_bf16x2(o[6], o[7]);
-        u1.x = pack_bf16x2(o[8], o[9]); u1.y = pack_bf16x2(o[10], o[11]); u1.z = pack_bf16x2(o[12], o[13]); u1.w = pack_bf16x2(o[14], o[15]);
-        orow[h * 2] = u0;
-        orow[h * 2 + 1] = u1;
+        float o0[8], o1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            o0[e] = o[e];
+            o1[e] = o[8 + e];
+        }
+        split_store8(orow + h * 16, orow + CI + h * 16, o0);
+        split_store8(orow + h * 16 + 8, orow + CI + h * 16 + 8, o1);
     }
 }
 
@@ -476,8 +504,8 @@ __global__ void __launch_bounds__(256) upscale_mask_kernel(const float* __restri
 }
 
 struct DecBuffers {
-    __nv_bfloat16 *keysA, *keysB, *kvq, *a2;
-    float *U, *Tq, *Tpe, *KT, *VT, *hyper, *iou_all;
+    __nv_bfloat16 *keysA, *keysB, *a2;   // split-bf16: [rows, 512], [rows, 512], [rows, 256]
+    float *kvq, *U, *Tq, *Tpe, *KT, *VT, *hyper, *iou_all;
 };
 
 bool carve(Workspace& ws, int P, int hw, DecBuffers& d) {
@@ -488,10 +516,10 @@ bool carve(Workspace& ws, int P, int hw, DecBuffers& d) {
         return p;
     };
     const size_t rows = (size_t)P * hw;
-    d.keysA = (__nv_bfloat16*)take(rows * C * 2);
-    d.keysB = (__nv_bfloat16*)take(rows * C * 2);
-    d.kvq = (__nv_bfloat16*)take(rows * 384 * 2);
-    d.a2 = (__nv_bfloat16*)take(rows * CI * 2);
+    d.keysA = (__nv_bfloat16*)take(rows * 2 * C * 2);
+    d.keysB = (__nv_bfloat16*)take(rows * 2 * C * 2);
+    d.kvq = (float*)take(rows * 384 * 4);
+    d.a2 = (__nv_bfloat16*)take(rows * 2 * CI * 2);
     d.U = (float*)take(rows * 128 * 4);
     d.Tq = (float*)take((size_t)P * NT * C * 4);
     d.Tpe = (float*)take((size_t)P * NT * C * 4);
@@ -523,6 +551,7 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     if (P == 0) return WG_OK;
     WG_REQUIRE(img_emb_tokens_bf16 && txt_emb && prompt_img && low_res_out && iou_out && workspace, "wg_mask_decoder_forward: null pointer");
     WG_REQUIRE(P > 0, "wg_mask_decoder_forward: P=%d", P);
+    WG_REQUIRE(w->split_terms == 2 || w->split_terms == 3, "wg_mask_decoder_forward: split_terms must be 2 or 3");
     WG_REQUIRE(w->n_mask_tokens == 4 && w->up_stages == 1, "wg_mask_decoder_forward: only the multi-scale decoder head (4 mask tokens, one ConvTranspose) is built");
     const int hw = w->grid_h * w->grid_w;
     WG_REQUIRE(hw > 0 && hw <= 4096, "wg_mask_decoder_forward: grid %dx%d unsupported", w->grid_h, w->grid_w);
@@ -538,17 +567,18 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     const long long rows = (long long)P * hw;
     WG_REQUIRE(rows < (1ll << 31), "wg_mask_decoder_forward: too many prompt tokens");
     const int n_out = multimask_output ? w->n_mask_tokens : 1;
+    const int T = w->split_terms;
     const int mask_start = 0;  // MaskDecoderMultiScale keeps index 0 in both modes (mask_decoder_multi_scale.py:126-132)
 
     long long blocks = (rows * (C / 8) + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     {
-        Prof prof("dec_expand_keys", s, 0.0, (double)rows * C * 4.0);
+        Prof prof("dec_expand_keys", s, 0.0, (double)rows * C * 8.0);
     expand_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(img_emb_tokens_bf16), prompt_img, w->no_mask, d.keysA, P, hw);
     }
     WG_CHECK_CUDA(cudaGetLastError());
 
-    const size_t tk_smem = (size_t)(6 * NT * C + NT * 2048 + NT * hw) * sizeof(float);
+    const size_t tk_smem = (size_t)(6 * NT * C + NT * 2048 + TOK_PART_FLOATS + NT * (hw > 48 ? hw : 48)) * sizeof(float);
     WG_CHECK_CUDA(cudaFuncSetAttribute(decoder_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     WG_REQUIRE(tk_smem <= 227 * 1024, "wg_mask_decoder_forward: token kernel shared memory %zu too large", tk_smem);
 
@@ -578,8 +608,9 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
         const wg_twoway_layer& L = w->layers[l];
         {   // [K_t2i | V_t2i | Q_i2t] with the positional term as a per-position bias table
             wg_gemm_args a = {};
-            a.A = keys; a.lda = C; a.W = L.w_img; a.ldw = C; a.M = (int)rows; a.N = 384; a.K = C;
-            a.bias = L.b_img; a.bias_period = hw; a.out_mode = WG_OUT_BF16; a.out = d.kvq; a.ldo = 384;
+            a.A = keys; a.lda = 2 * C; a.W = L.w_img; a.ldw = T * C; a.M = (int)rows; a.N = 384; a.K = T * C;
+            a.a_k_wrap = T == 3 ? 2 * C : 0;
+            a.bias = L.b_img; a.bias_period = hw; a.out_mode = WG_OUT_F32; a.out = d.kvq; a.ldo = 384;
             WG_TRY(wg_gemm(&a, s));
         }
         WG_DBG_STEP();
@@ -598,8 +629,9 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
         WG_DBG_STEP();
         {   // keys' = LayerNorm4(keys + attn W_o^T + b)
             wg_gemm_args a = {};
-            a.A = d.a2; a.lda = CI; a.W = L.i2t_wo; a.ldw = CI; a.M = (int)rows; a.N = C; a.K = CI;
-            a.bias = L.i2t_bo; a.bias_period = 1; a.out_mode = WG_OUT_BF16_LN; a.out = keys_next; a.ldo = C; a.resid = keys;
+            a.A = d.a2; a.lda = 2 * CI; a.W = L.i2t_wo; a.ldw = T * CI; a.M = (int)rows; a.N = C; a.K = T * CI;
+            a.a_k_wrap = T == 3 ? 2 * CI : 0;
+            a.bias = L.i2t_bo; a.bias_period = 1; a.out_mode = WG_OUT_BF16_LN; a.split_out = 1; a.out = keys_next; a.ldo = 2 * C; a.resid = keys;
             a.ln_gamma = L.n4_g; a.ln_beta = L.n4_b; a.ln_eps = 1e-5f;
             WG_TRY(wg_gemm(&a, s));
         }
@@ -608,8 +640,9 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     }
     {   // final token->image attention: [K | V]
         wg_gemm_args a = {};
-        a.A = keys; a.lda = C; a.W = w->w_img_fin; a.ldw = C; a.M = (int)rows; a.N = 256; a.K = C;
-        a.bias = w->b_img_fin; a.bias_period = hw; a.out_mode = WG_OUT_BF16; a.out = d.kvq; a.ldo = 256;
+        a.A = keys; a.lda = 2 * C; a.W = w->w_img_fin; a.ldw = T * C; a.M = (int)rows; a.N = 256; a.K = T * C;
+        a.a_k_wrap = T == 3 ? 2 * C : 0;
+        a.bias = w->b_img_fin; a.bias_period = hw; a.out_mode = WG_OUT_F32; a.out = d.kvq; a.ldo = 256;
         WG_TRY(wg_gemm(&a, s));
     }
     ta.phase = 2; ta.kv = d.kvq; ta.ldkv = 256;
@@ -619,7 +652,13 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     }
     WG_CHECK_CUDA(cudaGetLastError());
     // ConvTranspose2d(256 -> 32, k=2, s=2) as a GEMM over positions (N = 4 sub-pixels x 32 channels), fp32 out
-    WG_TRY(gemm_f32_out(keys, C, w->w_up, (int)rows, 128, C, w->b_up, WG_ACT_NONE, d.U, 128, nullptr, s));
+    {
+        wg_gemm_args a = {};
+        a.A = keys; a.lda = 2 * C; a.W = w->w_up; a.ldw = T * C; a.M = (int)rows; a.N = 128; a.K = T * C;
+        a.a_k_wrap = T == 3 ? 2 * C : 0;
+        a.bias = w->b_up; a.bias_period = 1; a.out_mode = WG_OUT_F32; a.out = d.U; a.ldo = 128;
+        WG_TRY(wg_gemm(&a, s));
+    }
     if (depth_pool_out) WG_CHECK_CUDA(cudaMemsetAsync(depth_pool_out, 0, (size_t)P * 33 * sizeof(float), s));
     {
         Prof prof("dec_upscale_mask", s, (double)rows * 128 * 12.0, (double)rows * (512.0 + 16.0 * n_out));

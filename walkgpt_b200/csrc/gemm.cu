@@ -34,6 +34,8 @@ struct GemmParams {
     const float* ln_gamma;
     const float* ln_beta;
     float ln_eps;
+    int a_k_wrap;   // A's k coordinate wraps at this many columns (0 = off): A' = [hi | lo | hi] of a split-bf16 operand
+    int split_out;  // bf16 outputs are written as split-bf16: hi at column c, lo = bf16(x - hi) at column N + c
 };
 
 template <int BN, int STAGES>
@@ -93,6 +95,12 @@ __device__ __forceinline__ void add_resid_bf16_32(float (&f)[32], const __nv_bfl
             }
         }
     }
+}
+
+// resid stored as split-bf16 [.., 2N]: value = hi + lo
+__device__ __forceinline__ void add_resid_split_32(float (&f)[32], const __nv_bfloat16* r_hi, int N, bool row_ok, int ncols_left) {
+    add_resid_bf16_32(f, r_hi, row_ok, 0, ncols_left);
+    add_resid_bf16_32(f, r_hi + N, row_ok, 0, ncols_left);
 }
 
 // write 32 fp32 values as bf16 into a 128B-swizzled [128 x 64] staging tile (row r, column half `half`)
@@ -163,7 +171,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                tma_load_2d(smem + L::OFF_A + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
+                int ka = kb * BK;
+                if (p.a_k_wrap > 0 && ka >= p.a_k_wrap) ka -= p.a_k_wrap;  // K' <= 2 * wrap by construction
+                tma_load_2d(smem + L::OFF_A + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], ka, m0);
                 tma_load_2d(smem + L::OFF_B + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
                 if (++stage == STAGES) {
                     stage = 0;
@@ -266,7 +276,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tmem_ld_32x32b_x32(taddr + c * 32, v);
                         tmem_ld_wait();
                         add_bias32(v, f, p, row, n0 + c * 32);
-                        if (rrow) add_resid_bf16_32(f, rrow + n0 + c * 32, row_ok, 0, BN - c * 32);
+                        if (rrow) {
+                            if (p.split_out) add_resid_split_32(f, rrow + n0 + c * 32, p.N, row_ok, BN - c * 32);
+                            else add_resid_bf16_32(f, rrow + n0 + c * 32, row_ok, 0, BN - c * 32);
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             s1 += f[j];
@@ -277,8 +290,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float var = fmaxf(s2 * (1.0f / BN) - mean * mean, 0.f);
                     rstd = rsqrtf(var + p.ln_eps);
                 }
+                const int nparts = p.split_out ? 2 : 1;
 #pragma unroll 1
-                for (int c = 0; c < BN / 64; ++c) {
+                for (int cp = 0; cp < (BN / 64) * nparts; ++cp) {
+                    const int c = cp / nparts, part = cp - c * nparts;
                     const int colc = n0 + c * 64;
                     if (colc >= p.N) break;  // uniform across the CTA
                     uint8_t* cbuf = cbufs + cbuf_idx * C_BUF_BYTES;
@@ -293,7 +308,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int col0 = colc + half * 32;
                         add_bias32(v, f, p, row, col0);
                         if constexpr (EPI == WG_OUT_BF16_LN) {
-                            if (rrow) add_resid_bf16_32(f, rrow + col0, row_ok, 0, p.N - col0);
+                            if (rrow) {
+                                if (p.split_out) add_resid_split_32(f, rrow + col0, p.N, row_ok, p.N - col0);
+                                else add_resid_bf16_32(f, rrow + col0, row_ok, 0, p.N - col0);
+                            }
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
                                 float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + g * 4));
@@ -315,12 +333,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                             }
                         }
+                        if (part == 1) {  // low half of the split representation
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16(f[j]));
+                        }
                         stage_bf16_32(cbuf, r, half, f);
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(1, EPI_THREADS);
                     if (epi_tid == 0) {
-                        tma_store_2d(&tmC, cbuf, colc, m0);
+                        tma_store_2d(&tmC, cbuf, part * p.N + colc, m0);
                         tma_store_commit();
                     }
                     cbuf_idx ^= 1;
@@ -345,10 +367,10 @@ template <int BN, int STAGES, int EPI>
 int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     using L = SmemLayout<BN, STAGES>;
     CUtensorMap tmA, tmB, tmC;
-    WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->K, a->lda, BM, BK));
+    WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->a_k_wrap > 0 ? a->a_k_wrap : a->K, a->lda, BM, BK));
     WG_TRY(make_tmap_2d_bf16(&tmB, a->W, a->N, a->K, a->ldw, BN, BK));
     if (EPI != WG_OUT_F32) {
-        WG_TRY(make_tmap_2d_bf16(&tmC, a->out, a->M, a->N, a->ldo, BM, 64));
+        WG_TRY(make_tmap_2d_bf16(&tmC, a->out, a->M, a->split_out ? 2 * a->N : a->N, a->ldo, BM, 64));
     } else {
         tmC = tmA;
     }
@@ -369,6 +391,8 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     p.ln_gamma = a->ln_gamma;
     p.ln_beta = a->ln_beta;
     p.ln_eps = a->ln_eps;
+    p.a_k_wrap = a->a_k_wrap;
+    p.split_out = (EPI != WG_OUT_F32) ? a->split_out : 0;
 
     auto kern = gemm_bf16_kernel<BN, STAGES, EPI>;
     static bool attr_set = false;  // per instantiation
@@ -402,6 +426,10 @@ extern "C" int wg_gemm(const wg_gemm_args* a, void* stream_) {
                "wg_gemm: A/W/out must be 16-byte aligned");
     WG_REQUIRE(a->N % 8 == 0, "wg_gemm: N must be a multiple of 8 (N=%d)", a->N);
     WG_REQUIRE(a->ldo % 4 == 0, "wg_gemm: ldo must be a multiple of 4");
+    WG_REQUIRE(a->a_k_wrap == 0 || (a->a_k_wrap % 64 == 0 && a->K <= 2 * a->a_k_wrap && a->K > a->a_k_wrap),
+               "wg_gemm: a_k_wrap=%d must be a multiple of 64 with a_k_wrap < K <= 2*a_k_wrap (K=%d)", a->a_k_wrap, a->K);
+    WG_REQUIRE(!a->split_out || (a->out_mode != WG_OUT_F32 && a->N % 64 == 0 && a->ldo >= 2 * (long long)a->N),
+               "wg_gemm: split_out needs a bf16 output mode, N %% 64 == 0 and ldo >= 2N");
     if (!device_is_sm100()) {
         set_error("wg_gemm: this library only runs on sm_100 (B200) devices; there is no fallback");
         return WG_ERR_UNSUPPORTED;

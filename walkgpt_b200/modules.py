@@ -291,6 +291,39 @@ def pack_conv_transpose2x2(weight: torch.Tensor, bias: torch.Tensor):
     return weight.permute(2, 3, 1, 0).reshape(-1, weight.shape[0]), bias.float().repeat(4)
 
 
+def split_terms_needed(weights: Iterable[torch.Tensor]) -> int:
+    """2 if every weight is exactly representable in bf16 (the usual case: WalkGPT checkpoints are bf16), else 3."""
+    for w in weights:
+        wf = w.detach().float()
+        if (wf - wf.to(torch.bfloat16).float()).abs().max().item() > 0.0:
+            return 3
+    return 2
+
+
+def split_weight(w: torch.Tensor, terms: int) -> torch.Tensor:
+    """nn.Linear weight [N, K] -> bf16 [N, terms*K] = [W_hi | W_hi | W_lo] (terms=3) or [W | W] (terms=2): the B operand that
+    pairs with a split-bf16 activation [hi | lo | hi] (see wg_gemm_args.a_k_wrap)."""
+    wf = w.detach().float()
+    hi = wf.to(torch.bfloat16)
+    parts = [hi, hi]
+    if terms == 3:
+        parts.append((wf - hi.float()).to(torch.bfloat16))
+    return torch.cat(parts, dim=1).contiguous()
+
+
+def to_split(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., C] -> split-bf16 [..., 2C] (hi | lo): a storage-format conversion, like .to(bfloat16) but ~16 mantissa bits."""
+    xf = x.float()
+    hi = xf.to(torch.bfloat16)
+    return torch.cat([hi, (xf - hi.float()).to(torch.bfloat16)], dim=-1).contiguous()
+
+
+def merge_split(x: torch.Tensor) -> torch.Tensor:
+    """split-bf16 [..., 2C] -> fp32 [..., C]."""
+    c = x.shape[-1] // 2
+    return x[..., :c].float() + x[..., c:].float()
+
+
 class _Holder:
     """Keeps repacked device tensors alive for as long as a ctypes weight struct points at them."""
 
@@ -486,22 +519,25 @@ class ProjectorNeck(_SpecModule):
         w.mm_hidden, w.hidden, w.out_chans = self.mm_hidden, self.hidden, self.out_chans
         w.w_fc1, w.b_fc1 = hold.bf16(sd["out_mm_projector.0.weight"]), hold.f32(sd["out_mm_projector.0.bias"])
         w.w_fc2, w.b_fc2 = hold.bf16(sd["out_mm_projector.2.weight"]), hold.f32(sd["out_mm_projector.2.bias"])
-        w.w_conv1 = hold.bf16(sd["image_feature_neck.0.weight"].reshape(self.out_chans, self.hidden))
+        w1 = sd["image_feature_neck.0.weight"].reshape(self.out_chans, self.hidden)
+        w3 = pack_conv3x3(sd["image_feature_neck.2.weight"])  # [co, ci, ky, kx] -> [co, (ky, kx, ci)]: channels-last im2col column order
+        terms = split_terms_needed([w1, w3])
+        w.split_terms = terms
+        w.w_conv1 = hold(split_weight(w1, terms))
         w.ln1_g, w.ln1_b = hold.f32(sd["image_feature_neck.1.weight"]), hold.f32(sd["image_feature_neck.1.bias"])
-        # [co, ci, ky, kx] -> [co, (ky, kx, ci)]: matches the channels-last im2col column order
-        w.w_conv3 = hold.bf16(pack_conv3x3(sd["image_feature_neck.2.weight"]))
+        w.w_conv3 = hold(split_weight(w3, terms))
         w.ln2_g, w.ln2_b = hold.f32(sd["image_feature_neck.3.weight"]), hold.f32(sd["image_feature_neck.3.bias"])
         self._packed = (w, hold)
         return self._packed
 
     def run(self, feats_bf16: torch.Tensor, want_proj: bool = False, want_emb: bool = True):
-        """feats bf16 [B, L, mm_hidden] -> (proj bf16 [B,L,H] | None, emb tokens bf16 [B,L,256] | None)."""
+        """feats bf16 [B, L, mm_hidden] -> (proj split-bf16 [B,L,2H] | None, emb tokens split-bf16 [B,L,512] | None)."""
         B, L, _ = feats_bf16.shape
         g = int(math.isqrt(L))
         assert g * g == L
         w, _ = self._packed or self._pack()
-        proj = torch.empty(B, L, self.hidden, device=feats_bf16.device, dtype=torch.bfloat16) if want_proj else None
-        emb = torch.empty(B, L, self.out_chans, device=feats_bf16.device, dtype=torch.bfloat16) if want_emb else None
+        proj = torch.empty(B, L, 2 * self.hidden, device=feats_bf16.device, dtype=torch.bfloat16) if want_proj else None
+        emb = torch.empty(B, L, 2 * self.out_chans, device=feats_bf16.device, dtype=torch.bfloat16) if want_emb else None
         ws = self._ws.get(_lib.lib().wg_proj_neck_workspace_bytes(C.byref(w), B * L), feats_bf16.device)
         _lib.check(_lib.lib().wg_proj_neck_forward(C.byref(w), feats_bf16.data_ptr(), B, g, None if proj is None else proj.data_ptr(),
                                                    None if emb is None else emb.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
@@ -514,7 +550,7 @@ class ProjectorNeck(_SpecModule):
         _need_cuda(feats, "ProjectorNeck.project")
         with torch.cuda.device(feats.device):
             proj, _ = self.run(feats.to(torch.bfloat16).contiguous(), want_proj=True, want_emb=False)
-        return proj.to(feats.dtype)
+        return merge_split(proj).to(feats.dtype)
 
     @torch.no_grad()
     def neck(self, x_nchw):
@@ -522,14 +558,14 @@ class ProjectorNeck(_SpecModule):
         _need_cuda(x_nchw, "ProjectorNeck.neck")
         B, Hd, gh, gw = x_nchw.shape
         assert gh == gw and Hd == self.hidden
-        tokens = x_nchw.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()  # layout change only
+        tokens = to_split(x_nchw.permute(0, 2, 3, 1))  # layout / storage-format change only
         w, _ = self._packed or self._pack()
-        emb = torch.empty(B, gh * gw, self.out_chans, device=x_nchw.device, dtype=torch.bfloat16)
+        emb = torch.empty(B, gh * gw, 2 * self.out_chans, device=x_nchw.device, dtype=torch.bfloat16)
         with torch.cuda.device(x_nchw.device):
             ws = self._ws.get(_lib.lib().wg_neck_workspace_bytes(B * gh * gw), x_nchw.device)
             _lib.check(_lib.lib().wg_neck_forward(C.byref(w), tokens.data_ptr(), B, gh, emb.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                        "wg_neck_forward")
-            return tokens_to_nchw(emb, gh, gw, x_nchw.dtype)
+            return tokens_to_nchw(emb, gh, gw, x_nchw.dtype, split=True)
 
     @torch.no_grad()
     def forward(self, feats):
@@ -538,15 +574,17 @@ class ProjectorNeck(_SpecModule):
         g = int(math.isqrt(feats.shape[1]))
         with torch.cuda.device(feats.device):
             _, emb = self.run(feats.to(torch.bfloat16).contiguous())
-            return tokens_to_nchw(emb, g, g, feats.dtype)
+            return tokens_to_nchw(emb, g, g, feats.dtype, split=True)
 
 
-def tokens_to_nchw(tokens_bf16: torch.Tensor, h: int, w: int, dtype=torch.float32) -> torch.Tensor:
-    """[B, h*w, C] bf16 -> [B, C, h, w]."""
+def tokens_to_nchw(tokens_bf16: torch.Tensor, h: int, w: int, dtype=torch.float32, split: bool = False) -> torch.Tensor:
+    """[B, h*w, C] bf16 (or split-bf16 [B, h*w, 2C]) -> [B, C, h, w]."""
     B, L, Cc = tokens_bf16.shape
+    if split:
+        Cc //= 2
     kd = torch.bfloat16 if dtype == torch.bfloat16 else torch.float32
     out = torch.empty(B, Cc, h, w, device=tokens_bf16.device, dtype=kd)
-    _lib.check(_lib.lib().wg_tokens_to_nchw(tokens_bf16.data_ptr(), out.data_ptr(), int(kd == torch.bfloat16), B, L, Cc, _stream()),
+    _lib.check(_lib.lib().wg_tokens_to_nchw(tokens_bf16.data_ptr(), int(split), out.data_ptr(), int(kd == torch.bfloat16), B, L, Cc, _stream()),
                "wg_tokens_to_nchw")
     return out.to(dtype)
 
@@ -638,8 +676,15 @@ class MaskDecoderMultiScale(_SpecModule):
         w.sparse_add = hold.f32(lvl)
         T = "transformer.0."
 
-        def lin_t(name):  # transposed bf16 weight + fp32 bias
-            return hold.bf16(sd[name + ".weight"].t()), hold.f32(sd[name + ".bias"])
+        def lin_t(name):  # transposed fp32 weight + fp32 bias (token side, CUDA cores)
+            return hold.f32(sd[name + ".weight"].t()), hold.f32(sd[name + ".bias"])
+
+        img_w = [sd[T + f"layers.{l}.{n}.weight"] for l in range(2) for n in
+                 ("cross_attn_token_to_image.k_proj", "cross_attn_token_to_image.v_proj", "cross_attn_image_to_token.q_proj",
+                  "cross_attn_image_to_token.out_proj")]
+        img_w += [sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.v_proj.weight"], sd["output_upscaling.0.weight"]]
+        terms = split_terms_needed(img_w)
+        w.split_terms = terms
 
         for l in range(2):
             L, lp = w.layers[l], T + f"layers.{l}."
@@ -656,24 +701,25 @@ class MaskDecoderMultiScale(_SpecModule):
             L.n3_g, L.n3_b = hold.f32(sd[lp + "norm3.weight"]), hold.f32(sd[lp + "norm3.bias"])
             L.i2t_wk_t, L.i2t_bk = lin_t(lp + "cross_attn_image_to_token.k_proj")
             L.i2t_wv_t, L.i2t_bv = lin_t(lp + "cross_attn_image_to_token.v_proj")
-            L.w_img = hold.bf16(torch.cat([sd[lp + "cross_attn_token_to_image.k_proj.weight"], sd[lp + "cross_attn_token_to_image.v_proj.weight"],
-                                           sd[lp + "cross_attn_image_to_token.q_proj.weight"]], 0))
-            L.i2t_wo, L.i2t_bo = hold.bf16(sd[lp + "cross_attn_image_to_token.out_proj.weight"]), hold.f32(sd[lp + "cross_attn_image_to_token.out_proj.bias"])
+            L.w_img = hold(split_weight(torch.cat([sd[lp + "cross_attn_token_to_image.k_proj.weight"], sd[lp + "cross_attn_token_to_image.v_proj.weight"],
+                                                   sd[lp + "cross_attn_image_to_token.q_proj.weight"]], 0), terms))
+            L.i2t_wo = hold(split_weight(sd[lp + "cross_attn_image_to_token.out_proj.weight"], terms))
+            L.i2t_bo = hold.f32(sd[lp + "cross_attn_image_to_token.out_proj.bias"])
             L.n4_g, L.n4_b = hold.f32(sd[lp + "norm4.weight"]), hold.f32(sd[lp + "norm4.bias"])
         w.fin_wq_t, w.fin_bq = lin_t(T + "final_attn_token_to_image.q_proj")
         w.fin_wo_t, w.fin_bo = lin_t(T + "final_attn_token_to_image.out_proj")
         w.nf_g, w.nf_b = hold.f32(sd[T + "norm_final_attn.weight"]), hold.f32(sd[T + "norm_final_attn.bias"])
-        w.w_img_fin = hold.bf16(torch.cat([sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.v_proj.weight"]], 0))
+        w.w_img_fin = hold(split_weight(torch.cat([sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.v_proj.weight"]], 0), terms))
         w_up, b_up = pack_conv_transpose2x2(sd["output_upscaling.0.weight"], sd["output_upscaling.0.bias"])
-        w.w_up, w.b_up = hold.bf16(w_up), hold.f32(b_up)
+        w.w_up, w.b_up = hold(split_weight(w_up, terms)), hold.f32(b_up)
         w.up_ln_g, w.up_ln_b = hold.f32(sd["output_upscaling.1.weight"]), hold.f32(sd["output_upscaling.1.bias"])
         for j, (wn, bn) in enumerate((("hyp_w0_t", "hyp_b0"), ("hyp_w1_t", "hyp_b1"), ("hyp_w2_t", "hyp_b2"))):
             ws_ = torch.stack([sd[f"output_hypernetworks_mlps.{i}.layers.{j}.weight"].t() for i in range(self.num_mask_tokens)], 0)
             bs_ = torch.stack([sd[f"output_hypernetworks_mlps.{i}.layers.{j}.bias"] for i in range(self.num_mask_tokens)], 0)
-            setattr(w, wn, hold.bf16(ws_))
+            setattr(w, wn, hold.f32(ws_))
             setattr(w, bn, hold.f32(bs_))
         for j, (wn, bn) in enumerate((("iou_w0_t", "iou_b0"), ("iou_w1_t", "iou_b1"), ("iou_w2_t", "iou_b2"))):
-            setattr(w, wn, hold.bf16(sd[f"iou_prediction_head.layers.{j}.weight"].t()))
+            setattr(w, wn, hold.f32(sd[f"iou_prediction_head.layers.{j}.weight"].t()))
             setattr(w, bn, hold.f32(sd[f"iou_prediction_head.layers.{j}.bias"]))
         self._packed = (w, hold)
         self._pe_key = None
@@ -682,23 +728,22 @@ class MaskDecoderMultiScale(_SpecModule):
     _pack = _pack_static
 
     def bind_prompt_constants(self, pe_tokens: torch.Tensor, no_mask: torch.Tensor, grid: Tuple[int, int]) -> None:
-        """Fold the dense positional encoding into per-position bias tables (pe W^T + b) with the library's own GEMM,
-        and record the dense (no-mask) prompt embedding.  Cached until the inputs or the weights change."""
+        """Fold the dense positional encoding into per-position bias tables (pe W^T + b; one-time fp32 constant folding, like
+        the LayerNorm-affine folding in MSQP) and record the dense (no-mask) prompt embedding.  Cached until inputs/weights change."""
         w, hold = self._packed or self._pack()
         key = (pe_tokens.data_ptr(), pe_tokens._version, no_mask.data_ptr(), no_mask._version, tuple(grid))
         if self._pe_key == key:
             return
-        from . import ops
         sd = self._sd()
-        pe_bf16 = pe_tokens.to(torch.bfloat16).contiguous()
+        pe32 = pe_tokens.float()
         hw = pe_tokens.shape[0]
         T = "transformer.0."
         self._pe_keep = []
 
         def table(wk, bk, bv, wq=None, bq=None):
-            parts = [ops.gemm(pe_bf16, _bf16(wk), _f32(bk), out_mode=ops.OUT_F32), _f32(bv)[None].expand(hw, -1)]
+            parts = [pe32 @ wk.float().t() + bk.float(), bv.float()[None].expand(hw, -1)]
             if wq is not None:
-                parts.append(ops.gemm(pe_bf16, _bf16(wq), _f32(bq), out_mode=ops.OUT_F32))
+                parts.append(pe32 @ wq.float().t() + bq.float())
             t = torch.cat(parts, dim=1).contiguous()
             self._pe_keep.append(t)
             return t.data_ptr()
@@ -718,7 +763,7 @@ class MaskDecoderMultiScale(_SpecModule):
 
     def run(self, emb_tokens_bf16: torch.Tensor, txt_emb_f32: torch.Tensor, prompt_img_i32: torch.Tensor, multimask_output: bool = False,
             want_depth_pool: bool = False):
-        """emb tokens bf16 [B, hw, 256], txt fp32 [P, 256], prompt_img int32 [P] ->
+        """emb tokens split-bf16 [B, hw, 512], txt fp32 [P, 256], prompt_img int32 [P] ->
         (low_res fp32 [P, n, 2h, 2w], iou fp32 [P, n], depth_pool fp32 [P, 33] | None).  bind_prompt_constants first."""
         w, _ = self._packed
         P = txt_emb_f32.shape[0]
@@ -756,7 +801,7 @@ class MaskDecoderMultiScale(_SpecModule):
             # dense prompt embedding: the reference always passes no_mask_embed broadcast over (h, w)
             dense_vec = dense_prompt_embeddings[0, :, 0, 0].float().contiguous()
             self.bind_prompt_constants(pe_tok, dense_vec, (h, wd))
-            emb_tok = image_embeddings.reshape(1, Cc, h * wd).permute(0, 2, 1).to(torch.bfloat16).contiguous()
+            emb_tok = to_split(image_embeddings.reshape(1, Cc, h * wd).permute(0, 2, 1))
             txt = sparse_prompt_embeddings.reshape(S, Cc).float().contiguous()
             pimg = torch.zeros(S, dtype=torch.int32, device=image_embeddings.device)
             low, iou, _ = self.run(emb_tok, txt, pimg, multimask_output)
@@ -884,7 +929,7 @@ class GroundingPath(nn.Module):
             if want_vis_tokens:
                 out["vis_tokens"] = self.msqp.run(feats, torch.bfloat16)
             _, emb = self.proj_neck.run(feats)
-            out["img_emb_tokens"] = emb
+            out["img_emb_split"] = emb  # split-bf16 [B, hw, 512]; merge_split() gives the fp32 [B, hw, 256] embedding
             txt = self.text_hidden_fcs[0].run(_as_kernel_input(seg_hidden), torch.float32)
             out["txt_emb"] = txt
             prompt_img = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), counts, output_size=P)
