@@ -20,16 +20,18 @@ namespace {
 constexpr int ATT_BQ = 128;      // queries per CTA
 constexpr int ATT_BKV = 128;     // keys per block
 constexpr int ATT_D = 64;        // head dim
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: softmax (one thread per query row)
+constexpr int ATT_SOFTMAX_THREADS = 128;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: a [128 x 64] bf16 tile
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + TILE_BYTES;          // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;      // 2 stages
 constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;      // [128 x 128] bf16 = two K-atoms of 64 keys
 constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
-constexpr int ATT_NUM_BARS = 10;
+constexpr int ATT_NUM_BARS = 12;
 constexpr int ATT_SMEM_BYTES = OFF_BAR + ATT_NUM_BARS * 8 + 16;
-constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O_j: [128,192)
+constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: the running scale is refreshed only when the row max grew by > 2^8
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -37,12 +39,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = j + f, f in [-0.5, 0.5], degree-3 minimax polynomial for
+// 2^f (max rel. error 1.0e-4, far below the bf16 rounding of P), exponent add for 2^j.  The B200 SFU evaluates ex2 at
+// 2 lanes/clk/SMSP, which makes d=64 attention SFU-bound; a fixed fraction of the exponentials is routed here instead.
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;            // 1.5 * 2^23: the low mantissa bits now hold round(x)
+    const float f = x - (t - 12582912.0f);
+    float pz = fmaf(0.05500893f, f, 0.24221096f);
+    pz = fmaf(pz, f, 0.69328293f);
+    pz = fmaf(pz, f, 1.0f);
+    return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+}
+#ifndef ATT_POLY_EXP
+#define ATT_POLY_EXP 0  // measured on B200: with one softmax warp per scheduler the kernel is latency- not SFU-bound; kept for tuning
+#endif
+// which of the 32 columns of a chunk use the polynomial (3 of 8)
+__device__ __forceinline__ constexpr bool use_poly(int i) { return (i & 7) == 1 || (i & 7) == 4 || (i & 7) == 6; }
+
 struct AttnParams {
     int T, heads, num_kv_blocks;
     float scale_log2;
     const uint8_t* key_valid;  // [B, T] or null
 };
 
+// Pipeline (per CTA = one 128-query tile of one head of one image; two CTAs share an SM):
+//   S_j = Q K_j^T (TMEM)  ->  softmax threads pull their S row into registers and immediately hand the S buffer back
+//   (s_free) so the tensor core computes S_{j+1} while the exponentials of block j are evaluated  ->  P_j (bf16, smem)
+//   ->  O += P_j V_j accumulated IN TMEM across all key blocks.  The softmax uses a lazily refreshed scale: the reference
+//   maximum is only moved (and O / l rescaled through tcgen05.ld/st) when a row's maximum grew by more than 2^8, which is
+//   exact arithmetic (any common scale cancels in O / l) and takes the O round trip off the per-block critical path.
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -54,8 +80,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     uint64_t* v_full = bars + 3;    // [2]
     uint64_t* kv_empty = bars + 5;  // [2]
     uint64_t* s_full = bars + 7;
-    uint64_t* p_ready = bars + 8;
-    uint64_t* o_full = bars + 9;
+    uint64_t* s_free = bars + 8;
+    uint64_t* p_ready = bars + 9;
+    uint64_t* p_free = bars + 10;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + ATT_NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
@@ -76,8 +103,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             mbar_init(&kv_empty[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(p_ready, 128);
-        mbar_init(o_full, 1);
+        mbar_init(s_free, ATT_SOFTMAX_THREADS);
+        mbar_init(p_ready, ATT_SOFTMAX_THREADS);
+        mbar_init(p_free, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_ptr_smem);
@@ -95,7 +123,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tma_load_3d(smem + OFF_Q, &tmQKV, q_full, head * ATT_D, qt * ATT_BQ, img);
             for (int j = 0; j < nkb; ++j) {
                 const int s = j & 1;
-                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_wait_relaxed(&kv_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
                 tma_load_3d(smem + OFF_K + s * TILE_BYTES, &tmQKV, &k_full[s], HD + head * ATT_D, j * ATT_BKV, img);
                 mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
@@ -121,20 +149,10 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
             for (int j = 0; j < nkb; ++j) {
                 const int s = j & 1;
-                mbar_wait(p_ready, j & 1);
-                mbar_wait(&v_full[s], (j >> 1) & 1);
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + OFF_V + s * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    // A: P atom (k/4) of 64 keys, 16-key step inside the atom = +32 B;  B: V rows (keys) step 16 rows = +2048 B
-                    umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                                umma_desc_sw128(v_addr + k * 2048), IDESC_O, k != 0);
-                }
-                umma_commit(&kv_empty[s]);
-                umma_commit(o_full);
                 if (j + 1 < nkb) {
+                    // S_{j+1} as soon as the softmax threads have pulled S_j out of TMEM: overlaps their exponentials
                     const int s1 = (j + 1) & 1;
+                    mbar_wait(s_free, j & 1);
                     mbar_wait(&k_full[s1], ((j + 1) >> 1) & 1);
                     tc_fence_after();
                     const uint32_t k_addr = smem_u32(smem + OFF_K + s1 * TILE_BYTES);
@@ -143,18 +161,29 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                         umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), IDESC_S, k != 0);
                     umma_commit(s_full);
                 }
+                mbar_wait(p_ready, j & 1);
+                mbar_wait(&v_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(smem + OFF_V + s * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    // A: P atom (k/4) of 64 keys, 16-key step inside the atom = +32 B;  B: V rows (keys) step 16 rows = +2048 B
+                    umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+                                umma_desc_sw128(v_addr + k * 2048), IDESC_O, (j | k) != 0);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(p_free);  // P buffer reusable, O consistent
             }
         }
     } else {
         // ===================== softmax warpgroup: one thread per query row =====================
+        // (A variant with two threads per row -- 8 softmax warps per CTA -- was measured slower on B200: 1.06 ms vs 0.80 ms
+        //  for B=64, T=1025, 16 heads; the extra named barriers / smem exchange cost more than the added warp parallelism.)
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
         const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)img * p.T : nullptr;
-        float m_run = -INFINITY, l_run = 0.f;
-        float o_acc[ATT_D];
-#pragma unroll
-        for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+        float m_ref = 0.f, l_run = 0.f;  // m_ref: the maximum the current scale refers to
         uint8_t* p_row = smem + OFF_P + r * 128;
 
         for (int j = 0; j < nkb; ++j) {
@@ -162,92 +191,106 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             const bool need_mask = (key0 + ATT_BKV > p.T) || (kvalid != nullptr);
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            // pass 1: row maximum
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
-                tmem_ld_wait();
-                if (need_mask) {
+            uint32_t sv[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);  // S_j is in registers: the tensor core may overwrite it with S_{j+1}
+            if (need_mask) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        int key = key0 + c * 32 + i;
-                        bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
-                        if (ok) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        const int key = key0 + c * 32 + i;
+                        const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
+                        if (!ok) sv[c][i] = 0xff800000u;  // -inf
                     }
-                } else {
+            }
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            // lazily refreshed scale
+            float alpha = 1.0f;
+            bool refresh = false;
+            if (j == 0) {
+                m_ref = (mx == -INFINITY) ? 0.f : mx;
+            } else if ((mx - m_ref) * p.scale_log2 > RESCALE_THRESHOLD) {
+                alpha = ex2_approx((m_ref - mx) * p.scale_log2);
+                m_ref = mx;
+                refresh = true;
+            }
+            const float neg_m = -m_ref * p.scale_log2;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = fmaf(__uint_as_float(sv[c][i]), p.scale_log2, neg_m);  // -inf for masked keys -> 0
+                    const float e = (ATT_POLY_EXP && use_poly(i)) ? exp2_poly(x) : ex2_approx(x);
+                    rs4[i & 3] += e;
+                    sv[c][i] = __float_as_uint(e);
+                }
+            l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+            if (j > 0) {
+                mbar_wait(p_free, (j - 1) & 1);  // PV_{j-1} finished: P buffer free, O quiescent
+                if (__any_sync(0xffffffffu, refresh)) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t ov[32];
+                        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                        tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                    }
+                    tmem_st_wait();
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // whole row masked so far
-            const float alpha = ex2_approx((m_run - m_use) * p.scale_log2);
-            const float neg_m = -m_use * p.scale_log2;
-            // pass 2: probabilities -> bf16 P tile (A operand of the PV MMA), row sum
-            float rowsum = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                float f[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-                if (need_mask) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        int key = key0 + c * 32 + i;
-                        bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
-                        if (!ok) f[i] = 0.f;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) rowsum += f[i];
                 uint8_t* atom_row = p_row + (c >> 1) * TILE_BYTES;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 u;
-                    u.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-                    u.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-                    u.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-                    u.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-                    int chunk = ((c & 1) * 4 + g) ^ (r & 7);
+                    u.x = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 0]), __uint_as_float(sv[c][g * 8 + 1]));
+                    u.y = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 2]), __uint_as_float(sv[c][g * 8 + 3]));
+                    u.z = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 4]), __uint_as_float(sv[c][g * 8 + 5]));
+                    u.w = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 6]), __uint_as_float(sv[c][g * 8 + 7]));
+                    const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
                     *reinterpret_cast<uint4*>(atom_row + chunk * 16) = u;
                 }
             }
-            l_run = l_run * alpha + rowsum;
-            m_run = m_new;
             fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
             tc_fence_before();
             mbar_arrive(p_ready);
-            // O_j from TMEM, rescale-and-accumulate in registers
-            mbar_wait(o_full, j & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(v[i]));
-            }
         }
-        // ---- epilogue: normalise, bf16, stage into the (now idle) Q tile, TMA store
+        // ---- epilogue: O / l, bf16, stage into the (now idle) Q tile, TMA store
+        mbar_wait(p_free, (nkb - 1) & 1);
+        tc_fence_after();
         const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
         uint8_t* o_row = smem + OFF_Q + r * 128;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(o_acc[g * 8 + 0] * inv_l, o_acc[g * 8 + 1] * inv_l);
-            u.y = pack_bf16x2(o_acc[g * 8 + 2] * inv_l, o_acc[g * 8 + 3] * inv_l);
-            u.z = pack_bf16x2(o_acc[g * 8 + 4] * inv_l, o_acc[g * 8 + 5] * inv_l);
-            u.w = pack_bf16x2(o_acc[g * 8 + 6] * inv_l, o_acc[g * 8 + 7] * inv_l);
-            *reinterpret_cast<uint4*>(o_row + ((g ^ (r & 7)) * 16)) = u;
+        for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv_l, __uint_as_float(ov[g * 8 + 1]) * inv_l);
+                u.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv_l, __uint_as_float(ov[g * 8 + 3]) * inv_l);
+                u.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv_l, __uint_as_float(ov[g * 8 + 5]) * inv_l);
+                u.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv_l, __uint_as_float(ov[g * 8 + 7]) * inv_l);
+                *reinterpret_cast<uint4*>(o_row + (((c * 4 + g) ^ (r & 7)) * 16)) = u;
+            }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, ATT_SOFTMAX_THREADS);
         if (threadIdx.x == 64) {
             tma_store_3d(&tmO, smem + OFF_Q, head * ATT_D, qt * ATT_BQ, img);
             tma_store_commit();

@@ -169,7 +169,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m0 = (tile / p.num_n_tiles) * BM;
             const int n0 = (tile % p.num_n_tiles) * BN;
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                 int ka = kb * BK;
                 if (p.a_k_wrap > 0 && ka >= p.a_k_wrap) ka -= p.a_k_wrap;  // K' <= 2 * wrap by construction
@@ -189,11 +189,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait_relaxed(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + L::OFF_A + stage * A_STAGE_BYTES);
                 const uint32_t b_addr = smem_u32(smem + L::OFF_B + stage * B_STAGE_BYTES);
@@ -225,13 +225,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int n0 = (tile % p.num_n_tiles) * BN;
             const int row = m0 + r;
             const bool row_ok = row < p.M;
-            mbar_wait(&tmem_full[acc], acc_phase);
+            mbar_wait_relaxed(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
             if constexpr (EPI == WG_OUT_F32) {
-                float* orow = p.out_f32 + (size_t)row * p.ldo;
-                const float* rrow = p.resid_f32 ? p.resid_f32 + (size_t)row * p.ldo : nullptr;
+                // fp32 output (+ fp32 residual, in place on the ViT residual stream).  Each thread owns one accumulator row, which
+                // would make global accesses 16 B per thread at a 4 KB stride; instead every warp transposes its 32x32 chunk
+                // through a padded smem tile so that each quarter-warp touches one full 128-byte line (coalesced LDG/STG.128).
+                float* stg = reinterpret_cast<float*>(cbufs) + q * (32 * 36);
+                const int rr0 = lane >> 3, cc = (lane & 7) * 4;
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t v[32];
@@ -245,23 +248,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
                     }
-                    if (row_ok) {
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            int col = col0 + g * 4;
-                            if (col < p.N) {
-                                float4 o = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-                                if (rrow) {
-                                    float4 rr = *reinterpret_cast<const float4*>(rrow + col);
-                                    o.x += rr.x;
-                                    o.y += rr.y;
-                                    o.z += rr.z;
-                                    o.w += rr.w;
-                                }
-                                *reinterpret_cast<float4*>(orow + col) = o;
-                            }
+                    for (int g = 0; g < 8; ++g)
+                        *reinterpret_cast<float4*>(stg + lane * 36 + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                    __syncwarp();
+                    const int gcol = col0 + cc;
+                    float4 o[8], rsd[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int grow = m0 + q * 32 + it * 4 + rr0;
+                        o[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rr0) * 36 + cc);
+                        rsd[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.resid_f32 && grow < p.M && gcol < p.N)
+                            rsd[it] = *reinterpret_cast<const float4*>(p.resid_f32 + (size_t)grow * p.ldo + gcol);
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int grow = m0 + q * 32 + it * 4 + rr0;
+                        if (grow < p.M && gcol < p.N) {
+                            o[it].x += rsd[it].x; o[it].y += rsd[it].y; o[it].z += rsd[it].z; o[it].w += rsd[it].w;
+                            *reinterpret_cast<float4*>(p.out_f32 + (size_t)grow * p.ldo + gcol) = o[it];
                         }
                     }
+                    __syncwarp();
                 }
             } else {
                 float mean = 0.f, rstd = 1.f;
