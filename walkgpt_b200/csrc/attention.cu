@@ -59,9 +59,101 @@ __device__ __forceinline__ constexpr bool use_poly(int i) { return (i & 7) == 1 
 
 struct AttnParams {
     int T, heads, num_kv_blocks;
+    int n_last;  // keys covered by the last key block, rounded up to 16 (T = 1025: 16 -- the block holds only the 1025th token)
     float scale_log2;
     const uint8_t* key_valid;  // [B, T] or null
 };
+
+struct SoftmaxState {
+    float m_ref;  // the maximum the current scale refers to
+    float l_run;  // running row sum in that scale
+};
+
+// One key block for one query row (= one thread): S row (NCH x 32 columns) from TMEM -> registers, hand S back, online softmax
+// with the lazily refreshed scale, P row (bf16) -> smem.
+template <int NCH>
+__device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const AttnParams& p, const uint8_t* kvalid, uint32_t tmem_S, uint32_t tmem_O,
+                                              uint32_t lane_off, int r, uint8_t* p_row, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready) {
+    const int key0 = j * ATT_BKV;
+    const bool need_mask = (key0 + NCH * 32 > p.T) || (kvalid != nullptr);
+    uint32_t sv[NCH][32];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(s_free);  // S_j is in registers: the tensor core may overwrite it with S_{j+1}
+    if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int key = key0 + c * 32 + i;
+                const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
+                if (!ok) sv[c][i] = 0xff800000u;  // -inf
+            }
+    }
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    // lazily refreshed scale
+    float alpha = 1.0f;
+    bool refresh = false;
+    if (j == 0) {
+        st.m_ref = (mx == -INFINITY) ? 0.f : mx;
+    } else if ((mx - st.m_ref) * p.scale_log2 > RESCALE_THRESHOLD) {
+        alpha = ex2_approx((st.m_ref - mx) * p.scale_log2);
+        st.m_ref = mx;
+        refresh = true;
+    }
+    const float neg_m = -st.m_ref * p.scale_log2;
+    float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float x = fmaf(__uint_as_float(sv[c][i]), p.scale_log2, neg_m);  // -inf for masked keys -> 0
+            const float e = (ATT_POLY_EXP && use_poly(i)) ? exp2_poly(x) : ex2_approx(x);
+            rs4[i & 3] += e;
+            sv[c][i] = __float_as_uint(e);
+        }
+    st.l_run = st.l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+    if (j > 0) {
+        mbar_wait(p_free, (j - 1) & 1);  // PV_{j-1} finished: P buffer free, O quiescent
+        if (__any_sync(0xffffffffu, refresh)) {
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+            }
+            tmem_st_wait();
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint8_t* atom_row = p_row + (c >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 0]), __uint_as_float(sv[c][g * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 2]), __uint_as_float(sv[c][g * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 4]), __uint_as_float(sv[c][g * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 6]), __uint_as_float(sv[c][g * 8 + 7]));
+            const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
+            *reinterpret_cast<uint4*>(atom_row + chunk * 16) = u;
+        }
+    }
+    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    mbar_arrive(p_ready);
+}
 
 // Pipeline (per CTA = one 128-query tile of one head of one image; two CTAs share an SM):
 //   S_j = Q K_j^T (TMEM)  ->  softmax threads pull their S row into registers and immediately hand the S buffer back
@@ -135,6 +227,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             // ===================== MMA issuer =====================
             constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, false, false);  // Q (K-major) x K (K-major)
             constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 64, false, true);    // P (K-major) x V (MN-major)
+            // the last key block only spans n_last (multiple of 16) keys: narrower S MMA, fewer PV k-steps
+            const uint32_t idesc_s_last = umma_idesc_bf16(128, p.n_last, false, false);
+            const int pv_steps_last = p.n_last / 16;
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
             const uint32_t p_addr = smem_u32(smem + OFF_P);
             mbar_wait(q_full, 0);
@@ -142,9 +237,10 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tc_fence_after();
             {
                 const uint32_t k_addr = smem_u32(smem + OFF_K);
+                const uint32_t idesc = nkb == 1 ? idesc_s_last : IDESC_S;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), IDESC_S, k != 0);
+                    umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
                 umma_commit(s_full);
             }
             for (int j = 0; j < nkb; ++j) {
@@ -156,20 +252,23 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     mbar_wait(&k_full[s1], ((j + 1) >> 1) & 1);
                     tc_fence_after();
                     const uint32_t k_addr = smem_u32(smem + OFF_K + s1 * TILE_BYTES);
+                    const uint32_t idesc = (j + 2 == nkb) ? idesc_s_last : IDESC_S;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), IDESC_S, k != 0);
+                        umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
                     umma_commit(s_full);
                 }
                 mbar_wait(p_ready, j & 1);
                 mbar_wait(&v_full[s], (j >> 1) & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(smem + OFF_V + s * TILE_BYTES);
+                const int pv_steps = (j + 1 == nkb) ? pv_steps_last : 8;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     // A: P atom (k/4) of 64 keys, 16-key step inside the atom = +32 B;  B: V rows (keys) step 16 rows = +2048 B
-                    umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                                umma_desc_sw128(v_addr + k * 2048), IDESC_O, (j | k) != 0);
+                    if (k < pv_steps)
+                        umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+                                    umma_desc_sw128(v_addr + k * 2048), IDESC_O, (j | k) != 0);
                 }
                 umma_commit(&kv_empty[s]);
                 umma_commit(p_free);  // P buffer reusable, O consistent
@@ -183,92 +282,29 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const int r = quarter * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
         const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)img * p.T : nullptr;
-        float m_ref = 0.f, l_run = 0.f;  // m_ref: the maximum the current scale refers to
         uint8_t* p_row = smem + OFF_P + r * 128;
 
+        // warps whose 32 query rows all lie past T (last query tile: only the 1025th token is real) skip the arithmetic and only
+        // keep the barrier protocol alive; their P / O rows are never stored (the TMA store clips at T).
+        const bool warp_active = qt * ATT_BQ + quarter * 32 < p.T;
+        SoftmaxState st{0.f, 0.f};
         for (int j = 0; j < nkb; ++j) {
-            const int key0 = j * ATT_BKV;
-            const bool need_mask = (key0 + ATT_BKV > p.T) || (kvalid != nullptr);
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            uint32_t sv[4][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(s_free);  // S_j is in registers: the tensor core may overwrite it with S_{j+1}
-            if (need_mask) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int key = key0 + c * 32 + i;
-                        const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
-                        if (!ok) sv[c][i] = 0xff800000u;  // -inf
-                    }
+            if (!warp_active) {
+                tc_fence_before();
+                mbar_arrive(s_free);
+                if (j > 0) mbar_wait(p_free, (j - 1) & 1);
+                mbar_arrive(p_ready);
+                continue;
             }
-            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            // lazily refreshed scale
-            float alpha = 1.0f;
-            bool refresh = false;
-            if (j == 0) {
-                m_ref = (mx == -INFINITY) ? 0.f : mx;
-            } else if ((mx - m_ref) * p.scale_log2 > RESCALE_THRESHOLD) {
-                alpha = ex2_approx((m_ref - mx) * p.scale_log2);
-                m_ref = mx;
-                refresh = true;
-            }
-            const float neg_m = -m_ref * p.scale_log2;
-            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = fmaf(__uint_as_float(sv[c][i]), p.scale_log2, neg_m);  // -inf for masked keys -> 0
-                    const float e = (ATT_POLY_EXP && use_poly(i)) ? exp2_poly(x) : ex2_approx(x);
-                    rs4[i & 3] += e;
-                    sv[c][i] = __float_as_uint(e);
-                }
-            l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-            if (j > 0) {
-                mbar_wait(p_free, (j - 1) & 1);  // PV_{j-1} finished: P buffer free, O quiescent
-                if (__any_sync(0xffffffffu, refresh)) {
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t ov[32];
-                        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                        tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ov);
-                    }
-                    tmem_st_wait();
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint8_t* atom_row = p_row + (c >> 1) * TILE_BYTES;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 0]), __uint_as_float(sv[c][g * 8 + 1]));
-                    u.y = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 2]), __uint_as_float(sv[c][g * 8 + 3]));
-                    u.z = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 4]), __uint_as_float(sv[c][g * 8 + 5]));
-                    u.w = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 6]), __uint_as_float(sv[c][g * 8 + 7]));
-                    const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(atom_row + chunk * 16) = u;
-                }
-            }
-            fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            mbar_arrive(p_ready);
+            const int ncols = (j + 1 == nkb) ? p.n_last : ATT_BKV;
+            if (ncols > 96) softmax_block<4>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
+            else if (ncols > 64) softmax_block<3>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
+            else if (ncols > 32) softmax_block<2>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
+            else softmax_block<1>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
         }
+        const float l_run = st.l_run;
         // ---- epilogue: O / l, bf16, stage into the (now idle) Q tile, TMA store
         mbar_wait(p_free, (nkb - 1) & 1);
         tc_fence_after();
@@ -276,6 +312,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         uint8_t* o_row = smem + OFF_Q + r * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+            if (!warp_active) break;
             uint32_t ov[32];
             tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
             tmem_ld_wait();
@@ -338,6 +375,7 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     p.T = T;
     p.heads = heads;
     p.num_kv_blocks = (T + ATT_BKV - 1) / ATT_BKV;
+    p.n_last = ((T - (p.num_kv_blocks - 1) * ATT_BKV) + 15) / 16 * 16;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.key_valid = key_valid;
     static bool attr_set = false;
