@@ -324,6 +324,19 @@ def test_full_batch_properties(path_model):
     assert torch.equal(out2["logits"][S:], logits[S:]) and not torch.equal(out2["logits"][:S], logits[:S])
 
 
+def test_torch_custom_ops_call_the_c_abi():
+    from walkgpt_b200 import torch_ops
+
+    g = load("ctp_256")
+    m = load_into(M.CalibratedTextProjector(256, 256), specs.make_state_dict(specs.ctp_spec(256, 256), seed=g["seed"]))
+    h = torch_ops.register(m)
+    before = _lib.lib().wg_launch_count(0)
+    y = torch.ops.walkgpt_b200.ctp_forward(g["x3"].to(DEV), h)
+    assert _lib.lib().wg_launch_count(0) > before and rel_err(y, g["y3"]) < 1e-2
+    lg, mk, sc = torch.ops.walkgpt_b200.postprocess_masks(torch.randn(2, 64, 64, device=DEV), 448, 448, 448, 448)
+    assert torch.equal(mk.bool(), lg > 0)
+
+
 def test_native_library_is_what_ran():
     assert os.path.exists(_lib.LIB_PATH)
     assert _lib.lib().wg_launch_count(0) > 0  # kernels of libwalkgpt_b200.so were launched by the tests above

@@ -110,3 +110,20 @@ def test_shard_helpers():
     got = [parallel.shard_batch(imgs, seg, offs, r, 2) for r in range(2)]
     assert got[0][0].flatten().tolist() == [0, 1, 2] and got[0][1].flatten().tolist() == [0, 1, 2, 3, 4] and got[0][2] == [0, 2, 2, 5]
     assert got[1][0].flatten().tolist() == [3, 4] and got[1][1].flatten().tolist() == [5, 6, 7, 8] and got[1][2] == [0, 3, 4]
+
+
+def test_torch_custom_ops_have_shape_inference():
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from walkgpt_b200 import torch_ops
+
+    h_ctp = torch_ops.register(M.CalibratedTextProjector(256, 256))
+    h_msqp = torch_ops.register(M.MultiScaleQFormerProjector(256, 64, target_square_side=6))
+    h_clip = torch_ops.register(M.CLIPVisionTower(layers=1))
+    with FakeTensorMode():
+        assert torch.ops.walkgpt_b200.ctp_forward(torch.empty(2, 5, 256), h_ctp).shape == (2, 5, 256)
+        assert torch.ops.walkgpt_b200.msqp_forward(torch.empty(3, 64, 256), h_msqp).shape == (3, 36, 64)
+        last, mid = torch.ops.walkgpt_b200.clip_forward(torch.empty(2, 3, 448, 448), h_clip)
+        assert last.shape == mid.shape == (2, 1024, 1024)
+        lg, mk, sc = torch.ops.walkgpt_b200.postprocess_masks(torch.empty(4, 64, 64), 448, 448, 360, 640)
+        assert lg.shape == (4, 360, 640) and mk.dtype == torch.uint8 and sc.shape == (4,)

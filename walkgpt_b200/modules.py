@@ -2,7 +2,7 @@
 
 Each class keeps the reference's constructor arguments, parameter names/shapes (so the reference's
 ``load_state_dict(strict=True)`` checkpoints load unchanged) and ``forward`` signature, but its forward is a
-single call into the C ABI (through the ``walkgpt_b200::*`` torch custom ops in :mod:`walkgpt_b200.torch_ops`).
+single call into the C ABI (ctypes, :mod:`walkgpt_b200._lib`; :mod:`walkgpt_b200.torch_ops` exposes the same calls as ``torch.library`` custom ops).
 Inference only; there is no PyTorch/CPU fallback.
 
 Reference seams: ``model/walkgpt.py:59-146`` (initialize_walkgpt_modules) and
