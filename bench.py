@@ -278,8 +278,14 @@ def main():
     g_n = sum(k["launches"] for k in gemm)
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     peak = peaks["bf16_sustained"]
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    if os.path.exists(tpath):  # dram__bytes_read+write of the dominant launch (ViT fc1), one `ncu --set full` capture
+        tj = json.load(open(tpath))["gemm_fc1"]
+        traffic = tj["dram_bytes"]
+        traffic_note = f"ncu dram bytes of the fc1 launch ({tj['shape']}); algorithmic bytes of that launch {tj['algorithmic_bytes']}"
     roofline = {"kernel": "gemm_bf16_kernel (tcgen05/TMEM + TMA, all epilogue variants)", "bound": "tensor", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_ms": g_ms / max(g_n, 1), "launches_per_step": g_n,
                 "share_of_step": g_ms / tot_ms,
                 "step_tflops": FLOPS_PER_IMAGE * B / (ms_total / K * 1e-3) / 1e12, "step_frac_of_peak": FLOPS_PER_IMAGE * B / (ms_total / K * 1e-3) / 1e12 / peak}
