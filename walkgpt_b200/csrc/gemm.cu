@@ -18,8 +18,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int C_BUF_BYTES = BM * 64 * 2;  // one TMA-store box: 128 rows x 64 bf16
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-11 epilogue
+constexpr int EPI_GROUP_THREADS = 128;  // two epilogue groups of 4 warps (one warp per TMEM lane quarter) take alternate column chunks
 
 struct GemmParams {
     int M, N, K;
@@ -151,7 +151,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -211,12 +211,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        // ===================== epilogue: 2 groups x 4 warps (a warp may only touch TMEM lanes 32*(warp%4)..+31) ===============
+        // The groups take alternate column chunks of every tile, so two warps per scheduler overlap each other's
+        // TMEM-load / SFU / shared-store latencies: with K = 1024 a 128x256 tile leaves only ~8k cycles for its epilogue.
         const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
         const int r = q * 32 + lane;  // row inside the tile == TMEM lane
-        const int epi_tid = threadIdx.x - 4 * 32;
+        const int epi_tid = threadIdx.x - (4 + 4 * grp) * 32;  // index inside the group
         uint8_t* cbufs = smem + L::OFF_C;
-        int cbuf_idx = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
             const int acc = iter & 1;
@@ -233,10 +235,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // fp32 output (+ fp32 residual, in place on the ViT residual stream).  Each thread owns one accumulator row, which
                 // would make global accesses 16 B per thread at a 4 KB stride; instead every warp transposes its 32x32 chunk
                 // through a padded smem tile so that each quarter-warp touches one full 128-byte line (coalesced LDG/STG.128).
-                float* stg = reinterpret_cast<float*>(cbufs) + q * (32 * 36);
-                const int rr0 = lane >> 3, cc = (lane & 7) * 4;
+                // per-warp 32x32 fp32 tile, 16-byte chunks XOR-swizzled by row (conflict-free float4 writes by row and reads by line)
+                float* stg = reinterpret_cast<float*>(cbufs) + (grp * 4 + q) * (32 * 32);
+                const int rr0 = lane >> 3, cj = lane & 7, cc = cj * 4;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = grp; c < BN / 32; c += 2) {
                     uint32_t v[32];
                     float f[32];
                     tmem_ld_32x32b_x32(taddr + c * 32, v);
@@ -250,14 +253,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
 #pragma unroll
                     for (int g = 0; g < 8; ++g)
-                        *reinterpret_cast<float4*>(stg + lane * 36 + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((g ^ (lane & 7)) * 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
                     __syncwarp();
                     const int gcol = col0 + cc;
                     float4 o[8], rsd[8];
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int grow = m0 + q * 32 + it * 4 + rr0;
-                        o[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rr0) * 36 + cc);
+                        o[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rr0) * 32 + ((cj ^ ((it * 4 + rr0) & 7)) * 4));
                         rsd[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.resid_f32 && grow < p.M && gcol < p.N)
                             rsd[it] = *reinterpret_cast<const float4*>(p.resid_f32 + (size_t)grow * p.ldo + gcol);
@@ -301,13 +304,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 const int nparts = p.split_out ? 2 : 1;
 #pragma unroll 1
-                for (int cp = 0; cp < (BN / 64) * nparts; ++cp) {
+                for (int cp = grp; cp < (BN / 64) * nparts; cp += 2) {
                     const int c = cp / nparts, part = cp - c * nparts;
                     const int colc = n0 + c * 64;
-                    if (colc >= p.N) break;  // uniform across the CTA
-                    uint8_t* cbuf = cbufs + cbuf_idx * C_BUF_BYTES;
-                    if (epi_tid == 0) tma_store_wait_read<1>();  // the store that last used this buffer is done reading
-                    named_bar_sync(1, EPI_THREADS);
+                    if (colc >= p.N) break;  // uniform across the group
+                    uint8_t* cbuf = cbufs + grp * C_BUF_BYTES;  // one staging buffer per group
+                    if (epi_tid == 0) tma_store_wait_read<0>();  // this group's previous store is done reading the buffer
+                    named_bar_sync(1 + grp, EPI_GROUP_THREADS);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint32_t v[32];
@@ -349,12 +352,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         stage_bf16_32(cbuf, r, half, f);
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1, EPI_THREADS);
+                    named_bar_sync(1 + grp, EPI_GROUP_THREADS);
                     if (epi_tid == 0) {
                         tma_store_2d(&tmC, cbuf, part * p.N + colc, m0);
                         tma_store_commit();
                     }
-                    cbuf_idx ^= 1;
                 }
             }
             tc_fence_before();
