@@ -7,116 +7,13 @@
 // This one kernel serves the ViT QKV/out/MLP GEMMs (SURVEY K2,K4,K5), patch embedding (K1), MSQP
 // projections (K6,K9,K10), the out_mm_projector MLP (K11), the neck convolutions (K12), CTP (K13) and
 // the mask decoder's image-side projections and ConvTranspose (K14,K15).
-#include "host.h"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace wg {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int C_BUF_BYTES = BM * 64 * 2;  // one TMA-store box: 128 rows x 64 bf16
-constexpr int NUM_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-11 epilogue
-constexpr int EPI_GROUP_THREADS = 128;  // two epilogue groups of 4 warps (one warp per TMEM lane quarter) take alternate column chunks
-
-struct GemmParams {
-    int M, N, K;
-    int num_n_tiles, num_tiles, num_k_blocks;
-    const float* bias;
-    int bias_period;
-    int act;
-    float* out_f32;
-    const float* resid_f32;
-    const __nv_bfloat16* resid_bf16;
-    long long ldo;
-    const float* ln_gamma;
-    const float* ln_beta;
-    float ln_eps;
-    int a_k_wrap;   // A's k coordinate wraps at this many columns (0 = off): A' = [hi | lo | hi] of a split-bf16 operand
-    int split_out;  // bf16 outputs are written as split-bf16: hi at column c, lo = bf16(x - hi) at column N + c
-};
-
-template <int BN, int STAGES>
-struct SmemLayout {
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
-    static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
-    static constexpr int OFF_C = OFF_B + STAGES * B_STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_C + 2 * C_BUF_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 4;
-    static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
-    static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
-};
-
-__device__ __forceinline__ float apply_act(float x, int act) {
-    switch (act) {
-        case WG_ACT_QUICK_GELU: return quick_gelu(x);
-        case WG_ACT_GELU_ERF: return gelu_erf(x);
-        case WG_ACT_RELU: return fmaxf(x, 0.0f);
-        default: return x;
-    }
-}
-
-// v[0..31] (raw accumulator bits) -> f[0..31] = acc + bias, for row `row`, columns col0..col0+31
-__device__ __forceinline__ void add_bias32(const uint32_t (&v)[32], float (&f)[32], const GemmParams& p, int row, int col0) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (p.bias != nullptr) {
-        const float* b = p.bias + (p.bias_period > 1 ? (size_t)(row % p.bias_period) * p.N : 0);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            int col = col0 + g * 4;
-            if (col < p.N) {
-                float4 bb = __ldg(reinterpret_cast<const float4*>(b + col));
-                f[g * 4 + 0] += bb.x;
-                f[g * 4 + 1] += bb.y;
-                f[g * 4 + 2] += bb.z;
-                f[g * 4 + 3] += bb.w;
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void add_resid_bf16_32(float (&f)[32], const __nv_bfloat16* r, bool row_ok, int col0, int N) {
-    if (!row_ok) return;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        int col = col0 + g * 8;
-        if (col < N) {
-            uint4 u = __ldg(reinterpret_cast<const uint4*>(r + col));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 t = __bfloat1622float2(h[e]);
-                f[g * 8 + e * 2] += t.x;
-                f[g * 8 + e * 2 + 1] += t.y;
-            }
-        }
-    }
-}
-
-// resid stored as split-bf16 [.., 2N]: value = hi + lo
-__device__ __forceinline__ void add_resid_split_32(float (&f)[32], const __nv_bfloat16* r_hi, int N, bool row_ok, int ncols_left) {
-    add_resid_bf16_32(f, r_hi, row_ok, 0, ncols_left);
-    add_resid_bf16_32(f, r_hi + N, row_ok, 0, ncols_left);
-}
-
-// write 32 fp32 values as bf16 into a 128B-swizzled [128 x 64] staging tile (row r, column half `half`)
-__device__ __forceinline__ void stage_bf16_32(uint8_t* cbuf, int r, int half, const float (&f)[32]) {
-    uint8_t* rowp = cbuf + r * 128;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 u;
-        u.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-        u.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-        u.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-        u.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-        int chunk = (half * 4 + j) ^ (r & 7);
-        *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
-    }
-}
+using namespace gemm_detail;
 
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -216,7 +113,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // TMEM-load / SFU / shared-store latencies: with K = 1024 a 128x256 tile leaves only ~8k cycles for its epilogue.
         const int q = warp & 3;
         const int grp = (warp - 4) >> 2;
-        const int r = q * 32 + lane;  // row inside the tile == TMEM lane
         const int epi_tid = threadIdx.x - (4 + 4 * grp) * 32;  // index inside the group
         uint8_t* cbufs = smem + L::OFF_C;
         int iter = 0;
@@ -225,140 +121,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int m0 = (tile / p.num_n_tiles) * BM;
             const int n0 = (tile % p.num_n_tiles) * BN;
-            const int row = m0 + r;
-            const bool row_ok = row < p.M;
             mbar_wait_relaxed(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-            if constexpr (EPI == WG_OUT_F32) {
-                // fp32 output (+ fp32 residual, in place on the ViT residual stream).  Each thread owns one accumulator row, which
-                // would make global accesses 16 B per thread at a 4 KB stride; instead every warp transposes its 32x32 chunk
-                // through a padded smem tile so that each quarter-warp touches one full 128-byte line (coalesced LDG/STG.128).
-                // per-warp 32x32 fp32 tile, 16-byte chunks XOR-swizzled by row (conflict-free float4 writes by row and reads by line)
-                float* stg = reinterpret_cast<float*>(cbufs) + (grp * 4 + q) * (32 * 32);
-                const int rr0 = lane >> 3, cj = lane & 7, cc = cj * 4;
-#pragma unroll 1
-                for (int c = grp; c < BN / 32; c += 2) {
-                    uint32_t v[32];
-                    float f[32];
-                    tmem_ld_32x32b_x32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    const int col0 = n0 + c * 32;
-                    if (col0 >= p.N) continue;
-                    add_bias32(v, f, p, row, col0);
-                    if (p.act != WG_ACT_NONE) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        *reinterpret_cast<float4*>(stg + lane * 32 + ((g ^ (lane & 7)) * 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-                    __syncwarp();
-                    const int gcol = col0 + cc;
-                    float4 o[8], rsd[8];
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int grow = m0 + q * 32 + it * 4 + rr0;
-                        o[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rr0) * 32 + ((cj ^ ((it * 4 + rr0) & 7)) * 4));
-                        rsd[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.resid_f32 && grow < p.M && gcol < p.N)
-                            rsd[it] = *reinterpret_cast<const float4*>(p.resid_f32 + (size_t)grow * p.ldo + gcol);
-                    }
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int grow = m0 + q * 32 + it * 4 + rr0;
-                        if (grow < p.M && gcol < p.N) {
-                            o[it].x += rsd[it].x; o[it].y += rsd[it].y; o[it].z += rsd[it].z; o[it].w += rsd[it].w;
-                            *reinterpret_cast<float4*>(p.out_f32 + (size_t)grow * p.ldo + gcol) = o[it];
-                        }
-                    }
-                    __syncwarp();
-                }
-            } else {
-                float mean = 0.f, rstd = 1.f;
-                const __nv_bfloat16* rrow = p.resid_bf16 ? p.resid_bf16 + (size_t)row * p.ldo : nullptr;
-                if constexpr (EPI == WG_OUT_BF16_LN) {
-                    // pass 1: row statistics over the full N == BN columns (this thread owns the row)
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
-                        uint32_t v[32];
-                        float f[32];
-                        tmem_ld_32x32b_x32(taddr + c * 32, v);
-                        tmem_ld_wait();
-                        add_bias32(v, f, p, row, n0 + c * 32);
-                        if (rrow) {
-                            if (p.split_out) add_resid_split_32(f, rrow + n0 + c * 32, p.N, row_ok, BN - c * 32);
-                            else add_resid_bf16_32(f, rrow + n0 + c * 32, row_ok, 0, BN - c * 32);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            s1 += f[j];
-                            s2 = fmaf(f[j], f[j], s2);
-                        }
-                    }
-                    mean = s1 * (1.0f / BN);
-                    float var = fmaxf(s2 * (1.0f / BN) - mean * mean, 0.f);
-                    rstd = rsqrtf(var + p.ln_eps);
-                }
-                const int nparts = p.split_out ? 2 : 1;
-#pragma unroll 1
-                for (int cp = grp; cp < (BN / 64) * nparts; cp += 2) {
-                    const int c = cp / nparts, part = cp - c * nparts;
-                    const int colc = n0 + c * 64;
-                    if (colc >= p.N) break;  // uniform across the group
-                    uint8_t* cbuf = cbufs + grp * C_BUF_BYTES;  // one staging buffer per group
-                    if (epi_tid == 0) tma_store_wait_read<0>();  // this group's previous store is done reading the buffer
-                    named_bar_sync(1 + grp, EPI_GROUP_THREADS);
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t v[32];
-                        float f[32];
-                        tmem_ld_32x32b_x32(taddr + c * 64 + half * 32, v);
-                        tmem_ld_wait();
-                        const int col0 = colc + half * 32;
-                        add_bias32(v, f, p, row, col0);
-                        if constexpr (EPI == WG_OUT_BF16_LN) {
-                            if (rrow) {
-                                if (p.split_out) add_resid_split_32(f, rrow + col0, p.N, row_ok, p.N - col0);
-                                else add_resid_bf16_32(f, rrow + col0, row_ok, 0, p.N - col0);
-                            }
-#pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + g * 4));
-                                float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + g * 4));
-                                f[g * 4 + 0] = (f[g * 4 + 0] - mean) * rstd * ga.x + be.x;
-                                f[g * 4 + 1] = (f[g * 4 + 1] - mean) * rstd * ga.y + be.y;
-                                f[g * 4 + 2] = (f[g * 4 + 2] - mean) * rstd * ga.z + be.z;
-                                f[g * 4 + 3] = (f[g * 4 + 3] - mean) * rstd * ga.w + be.w;
-                            }
-                        } else {
-                            if (p.act == WG_ACT_QUICK_GELU) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
-                            } else if (p.act == WG_ACT_GELU_ERF) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                            } else if (p.act == WG_ACT_RELU) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                            }
-                        }
-                        if (part == 1) {  // low half of the split representation
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16(f[j]));
-                        }
-                        stage_bf16_32(cbuf, r, half, f);
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(1 + grp, EPI_GROUP_THREADS);
-                    if (epi_tid == 0) {
-                        tma_store_2d(&tmC, cbuf, part * p.N + colc, m0);
-                        tma_store_commit();
-                    }
-                }
-            }
+            epilogue_tile<BN, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
