@@ -93,7 +93,8 @@ def attn_ref(qkv, heads, scale, kv=None):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, heads * 64)
 
 def t_attn():
-    for (B, T, H, masked) in [(1, 128, 1, False), (1, 256, 2, False), (2, 1025, 16, False), (2, 1025, 16, True), (1, 300, 3, True)]:
+    for (B, T, H, masked) in [(1, 128, 1, False), (1, 256, 2, False), (2, 1025, 16, False), (2, 1025, 16, True), (1, 300, 3, True),
+                              (2, 130, 2, True), (1, 5, 2, False), (1, 264, 1, False), (1, 1024, 4, False)]:
         qkv = torch.randn(B, T, 3 * H * 64, device=dev).bfloat16()
         kv = None
         if masked:

@@ -3,16 +3,24 @@
 //
 // One CTA per (128-query tile, head, image); two CTAs co-reside per SM so that one CTA's softmax overlaps the
 // other's tensor work.  Per CTA:
-//   warp 0  : TMA producer  (Q once, K/V blocks of 128 keys through a 2-stage ring; 3-D tensor map over
-//             [image, token, 3*heads*64] so rows past T are zero-filled by the hardware)
-//   warp 1  : TMEM allocation + single-thread tcgen05.mma issue:  S = Q K^T (128x128x64) into TMEM,
-//             O_j = P_j V_j (128x64x128, V consumed as an MN-major operand straight from its TMA tile)
+//   warp 0  : TMA producer  (Q once, K/V blocks of 128 keys through 2-stage rings with separate K / V release;
+//             3-D tensor map over [image, token, 3*heads*64] so rows past T are zero-filled by the hardware)
+//   warp 1  : TMEM allocation + single-thread tcgen05.mma issue:  S = Q K^T (128x128x64, both operands from smem)
+//             into TMEM;  O += P_j V_j (128x64x128) with P read FROM TENSOR MEMORY (A operand) and V consumed as an
+//             MN-major smem operand straight from its TMA tile -- P never touches shared memory
 //   warps 2-5: softmax warpgroup, ONE THREAD PER QUERY ROW (TMEM lane == row, so row max / row sum need no
-//             shuffles): tcgen05.ld S -> online softmax in fp32 (exp2 with folded scale) -> P as bf16 into
-//             128B-swizzled smem (A operand of the PV MMA) -> accumulate O_j from TMEM into registers with the
-//             running rescale -> final 1/l, bf16, TMA store.
+//             shuffles): tcgen05.ld S -> online softmax in fp32 (exp2 with folded scale, packed FFMA2/FADD2, 3 of 8
+//             exponentials on the FMA pipe) -> P as bf16 pairs back into TMEM (tcgen05.st); O stays in TMEM across
+//             all key blocks (lazy rescale) -> final 1/l, bf16, TMA store.
+// Leftover rows that do not fill a query tile (the 1025th token of the CLIP sequence) run on CUDA cores in
+// attention_tail_rows_kernel instead of costing a whole tensor-core tile per (head, image).
+//
+// Measured on B200 (B=64, T=1025, 16 heads): 0.71 ms (P through smem, 9 query tiles, serial softmax phases)
+// -> 0.54 ms.  What moved it, in order: the tail-row kernel (-11 %), P in TMEM + packed arithmetic + software-pipelined
+// exponentials (-8 %), branch-free key masking only where keys can be invalid (-4 %), polynomial exp2 share (-2 %).
 #include "host.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace wg {
 namespace {
@@ -26,11 +34,13 @@ constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: a [128 x 64] bf16 tile
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + TILE_BYTES;          // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;      // 2 stages
-constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;      // [128 x 128] bf16 = two K-atoms of 64 keys
-constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
-constexpr int ATT_NUM_BARS = 12;
-constexpr int ATT_SMEM_BYTES = OFF_BAR + ATT_NUM_BARS * 8 + 16;
-constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)
+constexpr int OFF_BAR = OFF_V + 2 * TILE_BYTES;
+constexpr int ATT_NUM_BARS = 14;
+constexpr int OFF_KMASK = OFF_BAR + ATT_NUM_BARS * 8 + 16;  // key-validity bit words (32 keys each), built once per CTA
+constexpr int ATT_MAX_T = 8192;
+constexpr int ATT_SMEM_BYTES = OFF_KMASK + (ATT_MAX_T / 32) * 4;
+constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
+constexpr int ATT_POLY_DEFAULT = 3;  // of every 8 exponentials, evaluated on the FMA pipe (B200: 0 -> 0.556 ms, 3 -> 0.545 ms)
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: the running scale is refreshed only when the row max grew by > 2^8
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -39,23 +49,58 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = j + f, f in [-0.5, 0.5], degree-3 minimax polynomial for
-// 2^f (max rel. error 1.0e-4, far below the bf16 rounding of P), exponent add for 2^j.  The B200 SFU evaluates ex2 at
-// 2 lanes/clk/SMSP, which makes d=64 attention SFU-bound; a fixed fraction of the exponentials is routed here instead.
-__device__ __forceinline__ float exp2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = x + 12582912.0f;            // 1.5 * 2^23: the low mantissa bits now hold round(x)
-    const float f = x - (t - 12582912.0f);
-    float pz = fmaf(0.05500893f, f, 0.24221096f);
-    pz = fmaf(pz, f, 0.69328293f);
-    pz = fmaf(pz, f, 1.0f);
-    return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two lanes per issue slot
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
-#ifndef ATT_POLY_EXP
-#define ATT_POLY_EXP 0  // measured on B200: with one softmax warp per scheduler the kernel is latency- not SFU-bound; kept for tuning
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// 2^x for a PAIR of arguments on the FMA/ALU pipes (no MUFU): x = j + f with j = round(x), f in [-0.5, 0.5]; a degree-3
+// minimax polynomial gives 2^f (max rel. error 1.0e-4, below the bf16 rounding of P) and j goes into the exponent field.
+// The MUFU unit evaluates one warp-wide ex2 per 8 cycles per scheduler, which bounds d=64 attention (ncu: XU pipe 70 % of
+// peak over the whole kernel with every exponential on it), so a fixed fraction of the exponentials is evaluated here.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& e0, float& e1) {
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    const uint64_t X = pk2(x0, x1);
+    const uint64_t MAGIC = pk2(12582912.0f, 12582912.0f);        // 1.5 * 2^23: the low mantissa bits of x + MAGIC hold round(x)
+    const uint64_t NMAGIC = pk2(-12582912.0f, -12582912.0f);
+    const uint64_t T = fadd2(X, MAGIC);
+    const uint64_t F = ffma2(fadd2(T, NMAGIC), pk2(-1.0f, -1.0f), X);  // x - round(x)
+    uint64_t P = ffma2(pk2(0.05500893f, 0.05500893f), F, pk2(0.24221096f, 0.24221096f));
+    P = ffma2(P, F, pk2(0.69328293f, 0.69328293f));
+    P = ffma2(P, F, pk2(1.0f, 1.0f));
+    float p0, p1, t0, t1;
+    upk2(P, p0, p1);
+    upk2(T, t0, t1);
+    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+// which of the 8 column PAIRS of a 16-column window use the polynomial: POLY of 8 (0..4), spread between the MUFU ones
+__device__ __forceinline__ constexpr bool use_poly(int pair, int poly) {
+    return poly == 1 ? (pair == 3) : poly == 2 ? (pair == 1 || pair == 5) : poly == 3 ? (pair == 1 || pair == 4 || pair == 6)
+         : poly == 4 ? ((pair & 1) == 1) : false;
+}
+
+// Debug-only pipeline trace (compile with -DATT_TRACE): clock64() stamps of three CTAs, read back by wg_debug_attn_trace.
+#ifdef ATT_TRACE
+__device__ long long g_att_trace[3][3][16][8];
+#define TR(role, j, slot) do { if (tr >= 0 && (j) < 16) g_att_trace[tr][role][j][slot] = clock64(); } while (0)
+#else
+#define TR(role, j, slot) do { } while (0)
 #endif
-// which of the 32 columns of a chunk use the polynomial (3 of 8)
-__device__ __forceinline__ constexpr bool use_poly(int i) { return (i & 7) == 1 || (i & 7) == 4 || (i & 7) == 6; }
 
 struct AttnParams {
     int T, heads, num_kv_blocks;
@@ -71,32 +116,38 @@ struct SoftmaxState {
 
 // One key block for one query row (= one thread): S row (NCH x 32 columns) from TMEM -> registers, hand S back, online softmax
 // with the lazily refreshed scale, P row (bf16) -> smem.
-template <int NCH>
-__device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const AttnParams& p, const uint8_t* kvalid, uint32_t tmem_S, uint32_t tmem_O,
-                                              uint32_t lane_off, int r, uint8_t* p_row, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready) {
-    const int key0 = j * ATT_BKV;
-    const bool need_mask = (key0 + NCH * 32 > p.T) || (kvalid != nullptr);
-    uint32_t sv[NCH][32];
+//
+// The exponential phase is software-pipelined in groups of 8 columns: the MUFU unit accepts one warp-wide ex2 every 8 cycles,
+// so the row sum (FADD), the bf16 packing (F2FP) and the shared-memory stores of group g-1 are issued in the shadow of group
+// g's exponentials instead of as serial phases after them (ncu showed the softmax warps spending 3/4 of their time outside
+// the MUFU-paced stretch).  The wait for the previous PV MMA (P buffer free) sits in the middle of the phase: the first 64
+// columns are packed into registers before it, so that the tensor core's latency is covered by exponentials, not by a stall.
+template <int NCH, int POLY>
+__device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const AttnParams& p, const uint32_t* kmask, uint32_t tmem_S, uint32_t tmem_O,
+                                              uint32_t tmem_P, uint32_t lane_off, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready, int tr) {
+    constexpr int NG = NCH * 4;                  // groups of 8 columns
+    constexpr int WAIT_AT = NG > 8 ? 8 : NG;     // the P-buffer wait happens once this many groups are packed
+    uint32_t sv2[NCH][32];
+#define sv(i) sv2[(i) >> 5][(i) & 31]
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv[c]);
+    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv2[c]);
     tmem_ld_wait();
+    TR(0, j, 2);
     tc_fence_before();
     mbar_arrive(s_free);  // S_j is in registers: the tensor core may overwrite it with S_{j+1}
-    if (need_mask) {
+    if (kmask != nullptr) {  // keys past T and masked keys: one validity word per 32 columns, branch-free selects
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t word = kmask[j * (ATT_BKV / 32) + c];
+            if (word != 0xffffffffu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int key = key0 + c * 32 + i;
-                const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
-                if (!ok) sv[c][i] = 0xff800000u;  // -inf
+                for (int i = 0; i < 32; ++i) sv(c * 32 + i) = ((word >> i) & 1u) ? sv(c * 32 + i) : 0xff800000u;  // -inf
             }
+        }
     }
     float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+    for (int i = 0; i < NCH * 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv(i)));
     const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     // lazily refreshed scale
     float alpha = 1.0f;
@@ -108,59 +159,87 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
         st.m_ref = mx;
         refresh = true;
     }
-    const float neg_m = -st.m_ref * p.scale_log2;
-    float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float scale = p.scale_log2;
+    const float neg_m = -st.m_ref * scale;
+    const uint64_t SC2 = pk2(scale, scale), NM2 = pk2(neg_m, neg_m);
+    uint64_t rsA = pk2(0.f, 0.f), rsB = pk2(0.f, 0.f);  // row sum, two packed accumulators
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int g = 0; g <= NG; ++g) {
+        if (g < NG) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float x = fmaf(__uint_as_float(sv[c][i]), p.scale_log2, neg_m);  // -inf for masked keys -> 0
-            const float e = (ATT_POLY_EXP && use_poly(i)) ? exp2_poly(x) : ex2_approx(x);
-            rs4[i & 3] += e;
-            sv[c][i] = __float_as_uint(e);
-        }
-    st.l_run = st.l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-    if (j > 0) {
-        mbar_wait(p_free, (j - 1) & 1);  // PV_{j-1} finished: P buffer free, O quiescent
-        if (__any_sync(0xffffffffu, refresh)) {
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t ov[32];
-                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+            for (int k = 0; k < 4; ++k) {  // column pairs: packed scale-and-shift, then MUFU or polynomial
+                const int i = g * 8 + k * 2;
+                float x0, x1, e0, e1;
+                upk2(ffma2(pk2(__uint_as_float(sv(i)), __uint_as_float(sv(i + 1))), SC2, NM2), x0, x1);  // -inf for masked keys -> 0
+                if (use_poly((g & 1) * 4 + k, POLY)) {
+                    exp2_poly2(x0, x1, e0, e1);
+                } else {
+                    e0 = ex2_approx(x0);
+                    e1 = ex2_approx(x1);
+                }
+                sv(i) = __float_as_uint(e0);
+                sv(i + 1) = __float_as_uint(e1);
             }
-            tmem_st_wait();
+        }
+        if (g >= 1) {  // row sum + bf16 packing of the previous group, in place (4 packed words at its first 4 registers)
+            const int b = (g - 1) * 8;
+            rsA = fadd2(rsA, pk2(__uint_as_float(sv(b + 0)), __uint_as_float(sv(b + 1))));
+            rsB = fadd2(rsB, pk2(__uint_as_float(sv(b + 2)), __uint_as_float(sv(b + 3))));
+            rsA = fadd2(rsA, pk2(__uint_as_float(sv(b + 4)), __uint_as_float(sv(b + 5))));
+            rsB = fadd2(rsB, pk2(__uint_as_float(sv(b + 6)), __uint_as_float(sv(b + 7))));
+            const uint32_t w0 = pack_bf16x2(__uint_as_float(sv(b + 0)), __uint_as_float(sv(b + 1)));
+            const uint32_t w1 = pack_bf16x2(__uint_as_float(sv(b + 2)), __uint_as_float(sv(b + 3)));
+            const uint32_t w2 = pack_bf16x2(__uint_as_float(sv(b + 4)), __uint_as_float(sv(b + 5)));
+            const uint32_t w3 = pack_bf16x2(__uint_as_float(sv(b + 6)), __uint_as_float(sv(b + 7)));
+            sv(b + 0) = w0; sv(b + 1) = w1; sv(b + 2) = w2; sv(b + 3) = w3;
+        }
+        if (g == WAIT_AT) {
+            if (j > 0) {
+                TR(0, j, 3);
+                mbar_wait(p_free, (j - 1) & 1);  // PV_{j-1} finished: P buffer free, O quiescent
+                TR(0, j, 4);
+                if (__any_sync(0xffffffffu, refresh)) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t ov[32];
+                        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                        tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                    }
+                    tmem_st_wait();
+                }
+            }
+        }
+        // group q of 8 keys = 4 packed 32-bit TMEM columns of this thread's lane
+        if (g == WAIT_AT) {
+#pragma unroll
+            for (int q = 0; q < WAIT_AT; ++q)
+                tmem_st_32x32b_x4(tmem_P + lane_off + q * 4, sv(q * 8 + 0), sv(q * 8 + 1), sv(q * 8 + 2), sv(q * 8 + 3));
+        } else if (g > WAIT_AT) {
+            const int q = g - 1;
+            tmem_st_32x32b_x4(tmem_P + lane_off + q * 4, sv(q * 8 + 0), sv(q * 8 + 1), sv(q * 8 + 2), sv(q * 8 + 3));
         }
     }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        uint8_t* atom_row = p_row + (c >> 1) * TILE_BYTES;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 0]), __uint_as_float(sv[c][g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 2]), __uint_as_float(sv[c][g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 4]), __uint_as_float(sv[c][g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(sv[c][g * 8 + 6]), __uint_as_float(sv[c][g * 8 + 7]));
-            const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-            *reinterpret_cast<uint4*>(atom_row + chunk * 16) = u;
-        }
-    }
-    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+    float rs0, rs1;
+    upk2(fadd2(rsA, rsB), rs0, rs1);
+    st.l_run = st.l_run * alpha + (rs0 + rs1);
+    tmem_st_wait();  // P is in tensor memory
     tc_fence_before();
     mbar_arrive(p_ready);
+    TR(0, j, 5);
+#undef sv
 }
 
 // Pipeline (per CTA = one 128-query tile of one head of one image; two CTAs share an SM):
 //   S_j = Q K_j^T (TMEM)  ->  softmax threads pull their S row into registers and immediately hand the S buffer back
-//   (s_free) so the tensor core computes S_{j+1} while the exponentials of block j are evaluated  ->  P_j (bf16, smem)
+//   (s_free) so the tensor core computes S_{j+1} while the exponentials of block j are evaluated  ->  P_j (bf16 pairs, TMEM)
 //   ->  O += P_j V_j accumulated IN TMEM across all key blocks.  The softmax uses a lazily refreshed scale: the reference
 //   maximum is only moved (and O / l rescaled through tcgen05.ld/st) when a row's maximum grew by more than 2^8, which is
 //   exact arithmetic (any common scale cancels in O / l) and takes the O round trip off the per-block critical path.
+template <int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -170,11 +249,12 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;    // [2]
     uint64_t* v_full = bars + 3;    // [2]
-    uint64_t* kv_empty = bars + 5;  // [2]
-    uint64_t* s_full = bars + 7;
-    uint64_t* s_free = bars + 8;
-    uint64_t* p_ready = bars + 9;
-    uint64_t* p_free = bars + 10;
+    uint64_t* k_empty = bars + 5;   // [2]  K stage free: committed right behind the S MMA that read it
+    uint64_t* v_empty = bars + 7;   // [2]  V stage free: committed behind the PV MMA
+    uint64_t* s_full = bars + 9;
+    uint64_t* s_free = bars + 10;
+    uint64_t* p_ready = bars + 11;
+    uint64_t* p_free = bars + 12;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + ATT_NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
@@ -184,6 +264,12 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int img = blockIdx.z;
     const int HD = p.heads * ATT_D;
     const int nkb = p.num_kv_blocks;
+#ifdef ATT_TRACE
+    int tr = -1;
+    if (qt == 3 && head == 5 && (img == 0 || img == 20 || img == 40) && (threadIdx.x == 32 || threadIdx.x == 64)) tr = img / 20;
+#else
+    const int tr = -1;
+#endif
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -192,7 +278,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         for (int s = 0; s < 2; ++s) {
             mbar_init(&k_full[s], 1);
             mbar_init(&v_full[s], 1);
-            mbar_init(&kv_empty[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_empty[s], 1);
         }
         mbar_init(s_full, 1);
         mbar_init(s_free, ATT_SOFTMAX_THREADS);
@@ -207,17 +294,28 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t tmem_S = tmem_base;
     const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_P = tmem_base + 192;
 
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
             mbar_arrive_expect_tx(q_full, TILE_BYTES);
             tma_load_3d(smem + OFF_Q, &tmQKV, q_full, head * ATT_D, qt * ATT_BQ, img);
+            // K and V stages are released separately (K right after its S MMA, V after its PV MMA) and the loads are issued
+            // in the order K_{j+1}, V_j: every load goes out about two key blocks before the tensor core needs it.  (With one
+            // combined release after PV_j, K_{j+2} could only be requested when S_{j+2} was already due -- the TMA round trip
+            // was exposed once per key block and set the kernel's pace.)
+            mbar_arrive_expect_tx(&k_full[0], TILE_BYTES);
+            tma_load_3d(smem + OFF_K, &tmQKV, &k_full[0], HD + head * ATT_D, 0, img);
             for (int j = 0; j < nkb; ++j) {
+                if (j + 1 < nkb) {
+                    const int s1 = (j + 1) & 1;
+                    mbar_wait_relaxed(&k_empty[s1], (((j + 1) >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&k_full[s1], TILE_BYTES);
+                    tma_load_3d(smem + OFF_K + s1 * TILE_BYTES, &tmQKV, &k_full[s1], HD + head * ATT_D, (j + 1) * ATT_BKV, img);
+                }
                 const int s = j & 1;
-                mbar_wait_relaxed(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-                tma_load_3d(smem + OFF_K + s * TILE_BYTES, &tmQKV, &k_full[s], HD + head * ATT_D, j * ATT_BKV, img);
+                mbar_wait_relaxed(&v_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
                 tma_load_3d(smem + OFF_V + s * TILE_BYTES, &tmQKV, &v_full[s], 2 * HD + head * ATT_D, j * ATT_BKV, img);
             }
@@ -231,7 +329,6 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             const uint32_t idesc_s_last = umma_idesc_bf16(128, p.n_last, false, false);
             const int pv_steps_last = p.n_last / 16;
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
-            const uint32_t p_addr = smem_u32(smem + OFF_P);
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
@@ -242,14 +339,18 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                 for (int k = 0; k < 4; ++k)
                     umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
                 umma_commit(s_full);
+                umma_commit(&k_empty[0]);
             }
             for (int j = 0; j < nkb; ++j) {
                 const int s = j & 1;
                 if (j + 1 < nkb) {
                     // S_{j+1} as soon as the softmax threads have pulled S_j out of TMEM: overlaps their exponentials
                     const int s1 = (j + 1) & 1;
+                    TR(1, j, 0);
                     mbar_wait(s_free, j & 1);
+                    TR(1, j, 1);
                     mbar_wait(&k_full[s1], ((j + 1) >> 1) & 1);
+                    TR(1, j, 2);
                     tc_fence_after();
                     const uint32_t k_addr = smem_u32(smem + OFF_K + s1 * TILE_BYTES);
                     const uint32_t idesc = (j + 2 == nkb) ? idesc_s_last : IDESC_S;
@@ -257,21 +358,24 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     for (int k = 0; k < 4; ++k)
                         umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
                     umma_commit(s_full);
+                    umma_commit(&k_empty[s1]);
                 }
+                TR(1, j, 3);
                 mbar_wait(p_ready, j & 1);
+                TR(1, j, 4);
                 mbar_wait(&v_full[s], (j >> 1) & 1);
+                TR(1, j, 5);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(smem + OFF_V + s * TILE_BYTES);
                 const int pv_steps = (j + 1 == nkb) ? pv_steps_last : 8;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    // A: P atom (k/4) of 64 keys, 16-key step inside the atom = +32 B;  B: V rows (keys) step 16 rows = +2048 B
-                    if (k < pv_steps)
-                        umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                                    umma_desc_sw128(v_addr + k * 2048), IDESC_O, (j | k) != 0);
+                    // A: P from tensor memory, 16 keys = 8 packed columns per step;  B: V rows (keys) step 16 rows = +2048 B
+                    if (k < pv_steps) umma_f16_ts(tmem_O, tmem_P + k * 8, umma_desc_sw128(v_addr + k * 2048), IDESC_O, (j | k) != 0);
                 }
-                umma_commit(&kv_empty[s]);
+                umma_commit(&v_empty[s]);
                 umma_commit(p_free);  // P buffer reusable, O consistent
+                TR(1, j, 6);
             }
         }
     } else {
@@ -281,15 +385,28 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)img * p.T : nullptr;
-        uint8_t* p_row = smem + OFF_P + r * 128;
-
+        // key-validity words (keys past T, masked keys), built once: the per-block softmax only does selects on them
+        const uint32_t* kmask = nullptr;
+        if (p.key_valid != nullptr || (p.T % ATT_BKV) != 0) {
+            uint32_t* words = reinterpret_cast<uint32_t*>(smem + OFF_KMASK);
+            const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)img * p.T : nullptr;
+            for (int w = quarter; w < nkb * (ATT_BKV / 32); w += 4) {
+                const int key = w * 32 + lane;
+                const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
+                const uint32_t word = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) words[w] = word;
+            }
+            named_bar_sync(1, ATT_SOFTMAX_THREADS);
+            kmask = words;
+        }
         // warps whose 32 query rows all lie past T (last query tile: only the 1025th token is real) skip the arithmetic and only
         // keep the barrier protocol alive; their P / O rows are never stored (the TMA store clips at T).
         const bool warp_active = qt * ATT_BQ + quarter * 32 < p.T;
         SoftmaxState st{0.f, 0.f};
         for (int j = 0; j < nkb; ++j) {
+            TR(0, j, 0);
             mbar_wait(s_full, j & 1);
+            TR(0, j, 1);
             tc_fence_after();
             if (!warp_active) {
                 tc_fence_before();
@@ -299,10 +416,11 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                 continue;
             }
             const int ncols = (j + 1 == nkb) ? p.n_last : ATT_BKV;
-            if (ncols > 96) softmax_block<4>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
-            else if (ncols > 64) softmax_block<3>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
-            else if (ncols > 32) softmax_block<2>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
-            else softmax_block<1>(st, j, p, kvalid, tmem_S, tmem_O, lane_off, r, p_row, s_free, p_free, p_ready);
+            const uint32_t* km = (p.key_valid != nullptr || j + 1 == nkb) ? kmask : nullptr;  // only blocks that can hold invalid keys
+            if (ncols > 96) softmax_block<4, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
+            else if (ncols > 64) softmax_block<3, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
+            else if (ncols > 32) softmax_block<2, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
+            else softmax_block<1, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
         }
         const float l_run = st.l_run;
         // ---- epilogue: O / l, bf16, stage into the (now idle) Q tile, TMA store
@@ -343,6 +461,101 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
 }
 
+// Rows that do not fill a 128-query tile when only a few are left over (T = 1025: the single row 1024 of every head):
+// running them through the tensor-core kernel would cost a full tile of MMAs and softmax per (head, image) -- 1/9 of the
+// whole attention for the CLIP tower.  They go through CUDA cores instead: one CTA of 128 threads per (row, head, image),
+// fp32 scores in shared memory (thread per key), then P V with one warp-wide coalesced 128-byte V row read per key.
+constexpr int TAIL_THREADS = 128;
+constexpr int TAIL_MAX_ROWS = 8;  // leftovers up to this many rows take this path
+
+__global__ void __launch_bounds__(TAIL_THREADS)
+attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const uint8_t* __restrict__ key_valid,
+                           int T, int heads, int row0, float scale_log2) {
+    extern __shared__ float tail_smem[];
+    float* sc = tail_smem;             // [T] scores, then probabilities
+    float* red = tail_smem + T;        // [4 warps][64] partial outputs / reductions
+    const int row = row0 + blockIdx.x;
+    const int head = blockIdx.y;
+    const int img = blockIdx.z;
+    const int HD = heads * ATT_D;
+    const size_t ld = (size_t)3 * HD;
+    const __nv_bfloat16* base = qkv + (size_t)img * T * ld;
+    const uint8_t* kvalid = key_valid ? key_valid + (size_t)img * T : nullptr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    float q[ATT_D];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(base + (size_t)row * ld + head * ATT_D);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = __ldg(qp + c);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h[i]);
+                q[c * 8 + i * 2] = f.x * scale_log2;
+                q[c * 8 + i * 2 + 1] = f.y * scale_log2;
+            }
+        }
+    }
+    float mx = -INFINITY;
+    for (int k = tid; k < T; k += TAIL_THREADS) {
+        const uint4* kp = reinterpret_cast<const uint4*>(base + (size_t)k * ld + HD + head * ATT_D);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = __ldg(kp + c);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h[i]);
+                a0 = fmaf(q[c * 8 + i * 2], f.x, a0);
+                a1 = fmaf(q[c * 8 + i * 2 + 1], f.y, a1);
+            }
+        }
+        float sv = a0 + a1;
+        if (kvalid != nullptr && kvalid[k] == 0) sv = -INFINITY;
+        sc[k] = sv;
+        mx = fmaxf(mx, sv);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    if (mx == -INFINITY) mx = 0.f;
+    __syncthreads();
+    float sum = 0.f;
+    for (int k = tid; k < T; k += TAIL_THREADS) {
+        const float e = ex2_approx(sc[k] - mx);
+        sc[k] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    // O = P V: warp w takes keys w, w+4, ...; lane l owns output dims 2l, 2l+1
+    float o0 = 0.f, o1 = 0.f;
+    const __nv_bfloat16* vbase = base + 2 * HD + head * ATT_D + lane * 2;
+#pragma unroll 8
+    for (int k = warp; k < T; k += 4) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)k * ld);
+        const float2 f = __bfloat1622float2(v);
+        const float pk = sc[k];
+        o0 = fmaf(pk, f.x, o0);
+        o1 = fmaf(pk, f.y, o1);
+    }
+    red[warp * ATT_D + lane * 2] = o0;
+    red[warp * ATT_D + lane * 2 + 1] = o1;
+    __syncthreads();
+    if (tid < ATT_D) {
+        const float o = (red[tid] + red[ATT_D + tid]) + (red[2 * ATT_D + tid] + red[3 * ATT_D + tid]);
+        const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+        out[((size_t)img * T + row) * HD + head * ATT_D + tid] = __float2bfloat16(o * inv);
+    }
+}
+
 }  // namespace
 }  // namespace wg
 
@@ -353,6 +566,7 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     WG_REQUIRE(qkv && out, "wg_attention_d64: null pointer");
     WG_REQUIRE(B > 0 && T > 0 && heads > 0, "wg_attention_d64: bad sizes B=%d T=%d heads=%d", B, T, heads);
     WG_REQUIRE(heads <= 65535 && B <= 65535, "wg_attention_d64: grid too large");
+    WG_REQUIRE(T <= ATT_MAX_T, "wg_attention_d64: T=%d exceeds the supported maximum %d", T, ATT_MAX_T);
     if (!device_is_sm100()) {
         set_error("wg_attention_d64: this library only runs on sm_100 (B200) devices; there is no fallback");
         return WG_ERR_UNSUPPORTED;
@@ -378,14 +592,52 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     p.n_last = ((T - (p.num_kv_blocks - 1) * ATT_BKV) + 15) / 16 * 16;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.key_valid = key_valid;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-        attr_set = true;
+    // fraction of the exponentials evaluated on the FMA pipe (POLY of every 8); WG_ATTN_POLY overrides for tuning
+    static int poly = -1;
+    if (poly < 0) {
+        const char* e = getenv("WG_ATTN_POLY");
+        poly = e ? atoi(e) : ATT_POLY_DEFAULT;
+        if (poly < 0 || poly > 4) poly = ATT_POLY_DEFAULT;
+        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     }
-    dim3 grid((T + ATT_BQ - 1) / ATT_BQ, heads, B);
-    Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D);
-    attention_d64_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p);
-    WG_CHECK_CUDA(cudaGetLastError());
+    // a few leftover rows (T % 128 <= TAIL_MAX_ROWS) go through the CUDA-core tail kernel instead of a whole tensor-core tile
+    const int rem = T % ATT_BQ;
+    const int tail_rows = (rem > 0 && rem <= TAIL_MAX_ROWS) ? rem : 0;
+    const int row0 = T - tail_rows;
+    Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D,
+              (row0 > 0 ? 1 : 0) + (tail_rows > 0 ? 1 : 0));
+    if (row0 > 0) {
+        dim3 grid((row0 + ATT_BQ - 1) / ATT_BQ, heads, B);
+        switch (poly) {
+            case 1: attention_d64_kernel<1><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
+            case 2: attention_d64_kernel<2><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
+            case 3: attention_d64_kernel<3><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
+            case 4: attention_d64_kernel<4><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
+            default: attention_d64_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
+        }
+        WG_CHECK_CUDA(cudaGetLastError());
+    }
+    if (tail_rows > 0) {
+        const size_t smem = ((size_t)T + 4 * ATT_D) * sizeof(float);
+        WG_REQUIRE(smem <= 200 * 1024, "wg_attention_d64: T=%d too long for the tail-row kernel", T);
+        static bool tail_attr_set = false;
+        if (!tail_attr_set) {
+            WG_CHECK_CUDA(cudaFuncSetAttribute(attention_tail_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            tail_attr_set = true;
+        }
+        attention_tail_rows_kernel<<<dim3(tail_rows, heads, B), TAIL_THREADS, smem, stream>>>(
+            static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), key_valid, T, heads, row0, p.scale_log2);
+        WG_CHECK_CUDA(cudaGetLastError());
+    }
     return WG_OK;
 }
+
+#ifdef ATT_TRACE
+extern "C" __attribute__((visibility("default"))) int wg_debug_attn_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, wg::g_att_trace, sizeof(long long) * 3 * 3 * 16 * 8);
+}
+#endif
