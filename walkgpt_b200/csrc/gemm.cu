@@ -8,6 +8,7 @@
 // projections (K6,K9,K10), the out_mm_projector MLP (K11), the neck convolutions (K12), CTP (K13) and
 // the mask decoder's image-side projections and ConvTranspose (K14,K15).
 #include "gemm_common.cuh"
+#include <cstdlib>
 
 namespace wg {
 
@@ -213,13 +214,23 @@ extern "C" int wg_gemm(const wg_gemm_args* a, void* stream_) {
         return WG_ERR_UNSUPPORTED;
     }
     const long long tiles256 = (long long)((a->M + 127) / 128) * ((a->N + 255) / 256);
+    // CTA-pair kernel (256 x 256 tiles over two SMs) once there is at least one full wave of pair tiles; WG_GEMM_PAIR=0 disables
+    static int pair_enabled = -1;
+    if (pair_enabled < 0) {
+        const char* e = getenv("WG_GEMM_PAIR");
+        pair_enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    }
+    const long long tiles_pair = (long long)((a->M + 255) / 256) * ((a->N + 255) / 256);
+    const bool use_pair = pair_enabled && (a->N % 256 == 0) && tiles_pair >= device_sm_count() / 2;
     switch (a->out_mode) {
         case WG_OUT_BF16: {
             WG_REQUIRE(a->ldo % 8 == 0, "wg_gemm: bf16 output needs ldo %% 8 == 0");
+            if (use_pair) return launch_gemm_pair(a, stream);
             bool use256 = (a->N % 256 == 0) && tiles256 >= device_sm_count();
             return use256 ? launch_gemm<256, 4, WG_OUT_BF16>(a, stream) : launch_gemm<128, 6, WG_OUT_BF16>(a, stream);
         }
         case WG_OUT_F32: {
+            if (use_pair) return launch_gemm_pair(a, stream);
             bool use256 = (a->N % 256 == 0) && tiles256 >= device_sm_count();
             return use256 ? launch_gemm<256, 4, WG_OUT_F32>(a, stream) : launch_gemm<128, 6, WG_OUT_F32>(a, stream);
         }

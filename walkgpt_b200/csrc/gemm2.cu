@@ -1,0 +1,260 @@
+// CTA-pair (cta_group::2) variant of the persistent tcgen05 GEMM:  C[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//
+// Two CTAs on the two SMs of a TPC (cluster of 2) compute one 256 x 256 tile together.  Each CTA stages only ITS half of
+// both operands -- A rows [m0 + 128*rank, +128) and W rows [n0 + 128*rank, +128) -- and one thread of the leader CTA
+// issues tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16): the tensor cores of both SMs read the two W halves from both
+// CTAs' shared memory.  Against the 1-CTA kernel (128 x 256 tile, 16 KB A + 32 KB W per k-block per SM) a k-block costs each
+// SM 16 KB + 16 KB of TMA fill and tensor-core smem reads: a third less shared-memory traffic, six pipeline stages instead of
+// four, and half the L2 -> smem W traffic.  Accumulators: each CTA's TMEM holds its own 128 rows x 256 columns, double
+// buffered (512 columns), and its own 8 epilogue warps drain them (shared code: epilogue_tile in gemm_common.cuh).
+//
+// Barriers (all mbarriers; "L" = lives in / is waited on by the leader only):
+//   full[s]  (L, count 1)  : the leader's producer arrives with expect_tx(64 KB = both CTAs); both CTAs' TMA loads complete_tx on it
+//   empty[s] (per CTA)     : tcgen05.commit multicast from the leader after the MMAs that read stage s
+//   tmem_full[a] (per CTA) : tcgen05.commit multicast after the last k-block of a tile
+//   tmem_empty[a] (L, 16)  : one arrival per epilogue warp of both CTAs
+#include "gemm_common.cuh"
+
+namespace wg {
+
+namespace {
+
+using namespace gemm_detail;
+
+constexpr int BN2 = 256;                      // pair tile: 256 (M, two CTAs) x 256 (N)
+constexpr int B_HALF_BYTES = 128 * BK * 2;    // this CTA's half of the W tile
+
+#ifdef GEMM2_TRACE
+__device__ long long g_gemm2_trace[3][64][4];  // role (0 MMA, 1 producer rank 0, 2 producer rank 1) x k-block x stamp
+#define TR2(role, i, slot) do { if (trace_on && (i) < 64) g_gemm2_trace[role][i][slot] = clock64(); } while (0)
+#else
+#define TR2(role, i, slot) do { } while (0)
+#endif
+
+template <int STAGES>
+struct SmemLayout2 {
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+    static constexpr int OFF_C = OFF_B + STAGES * B_HALF_BYTES;
+    static constexpr int OFF_BAR = OFF_C + 2 * C_BUF_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 4;
+    static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
+};
+
+template <int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+    using L = SmemLayout2<STAGES>;
+    constexpr int TMEM_COLS = 2 * BN2;
+    constexpr uint32_t IDESC = umma_idesc_bf16(2 * BM, BN2, false, false);
+    constexpr uint32_t STAGE_TX_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+#ifdef GEMM2_TRACE
+    const bool trace_pair = pair == 5;
+#endif
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (EPI != WG_OUT_F32) tma_prefetch_desc(&tmC);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 16);  // one arrival per epilogue warp of both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_cg2<TMEM_COLS>(tmem_ptr_smem);
+    tc_fence_before();
+    cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer (both CTAs: own A rows, own half of the W tile) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int titer = 0;
+        const uint32_t full_leader0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+        for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++titer) {
+            const int m0 = (tile / p.num_n_tiles) * (2 * BM) + rank * BM;
+            const int n0 = (tile % p.num_n_tiles) * BN2 + rank * 128;
+#ifdef GEMM2_TRACE
+            const bool trace_on = trace_pair && (titer == 2 || titer == 3);
+            const int tb = (titer - 2) * p.num_k_blocks;
+#endif
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                TR2(1 + rank, tb + kb, 0);
+                mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                TR2(1 + rank, tb + kb, 1);
+                // only the leader arms the barrier, with the bytes of BOTH CTAs; the peer's loads may complete_tx before
+                // that (the count goes negative transiently -- the phase cannot complete before the leader's arrival)
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_TX_BYTES);
+                int ka = kb * BK;
+                if (p.a_k_wrap > 0 && ka >= p.a_k_wrap) ka -= p.a_k_wrap;  // K' <= 2 * wrap by construction
+                const uint32_t full_leader = full_leader0 + stage * 8;
+                tma_load_2d_cg2(smem + L::OFF_A + stage * A_STAGE_BYTES, &tmA, full_leader, ka, m0);
+                TR2(1 + rank, tb + kb, 3);
+                tma_load_2d_cg2(smem + L::OFF_B + stage * B_HALF_BYTES, &tmB, full_leader, kb * BK, n0);
+                TR2(1 + rank, tb + kb, 2);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN2;
+#ifdef GEMM2_TRACE
+            const bool trace_on = trace_pair && (iter == 2 || iter == 3);
+            const int tb = (iter - 2) * p.num_k_blocks;
+#endif
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                TR2(0, tb + kb, 0);
+                mbar_wait_relaxed(&full_bar[stage], phase);
+                TR2(0, tb + kb, 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + L::OFF_A + stage * A_STAGE_BYTES);
+                const uint32_t b_addr = smem_u32(smem + L::OFF_B + stage * B_HALF_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    umma_f16_ss_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), IDESC,
+                                    (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit_cg2(&empty_bar[stage], 0b11);  // frees the smem slot in both CTAs
+                TR2(0, tb + kb, 2);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit_cg2(&tmem_full[acc], 0b11);  // accumulators of both CTAs complete -> both epilogues
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 2 groups x 4 warps per CTA, on this CTA's 128 rows =====================
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int epi_tid = threadIdx.x - (4 + 4 * grp) * 32;  // index inside the group
+        uint8_t* cbufs = smem + L::OFF_C;
+        int iter = 0;
+        for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int m0 = (tile / p.num_n_tiles) * (2 * BM) + rank * BM;
+            const int n0 = (tile % p.num_n_tiles) * BN2;
+            mbar_wait_relaxed(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
+
+            epilogue_tile<BN2, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        }
+        if (EPI != WG_OUT_F32 && epi_tid == 0) tma_store_wait_all<0>();
+    }
+
+    // neither CTA may leave (or free its TMEM) while the peer can still signal its barriers or read its shared memory
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int STAGES, int EPI>
+int launch2(const wg_gemm_args* a, cudaStream_t stream) {
+    using L = SmemLayout2<STAGES>;
+    CUtensorMap tmA, tmB, tmC;
+    WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->a_k_wrap > 0 ? a->a_k_wrap : a->K, a->lda, BM, BK));
+    WG_TRY(make_tmap_2d_bf16(&tmB, a->W, a->N, a->K, a->ldw, 128, BK));
+    if (EPI != WG_OUT_F32) {
+        WG_TRY(make_tmap_2d_bf16(&tmC, a->out, a->M, a->split_out ? 2 * a->N : a->N, a->ldo, BM, 64));
+    } else {
+        tmC = tmA;
+    }
+    GemmParams p;
+    p.M = a->M;
+    p.N = a->N;
+    p.K = a->K;
+    p.num_n_tiles = (a->N + BN2 - 1) / BN2;
+    p.num_tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
+    p.num_k_blocks = (a->K + BK - 1) / BK;
+    p.bias = a->bias;
+    p.bias_period = a->bias_period;
+    p.act = a->act;
+    p.out_f32 = (EPI == WG_OUT_F32) ? static_cast<float*>(a->out) : nullptr;
+    p.resid_f32 = (EPI == WG_OUT_F32) ? static_cast<const float*>(a->resid) : nullptr;
+    p.resid_bf16 = (EPI == WG_OUT_BF16_LN) ? static_cast<const __nv_bfloat16*>(a->resid) : nullptr;
+    p.ldo = a->ldo;
+    p.ln_gamma = a->ln_gamma;
+    p.ln_beta = a->ln_beta;
+    p.ln_eps = a->ln_eps;
+    p.a_k_wrap = a->a_k_wrap;
+    p.split_out = (EPI != WG_OUT_F32) ? a->split_out : 0;
+
+    auto kern = gemm2_bf16_kernel<STAGES, EPI>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        WG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+        attr_set = true;
+    }
+    const int max_pairs = device_sm_count() / 2;
+    const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+    static const char* kname = EPI == WG_OUT_BF16 ? "gemm2_bf16" : EPI == WG_OUT_F32 ? "gemm2_f32" : "gemm2_bf16ln";
+    const double out_bytes = (double)a->M * a->N * (EPI == WG_OUT_F32 ? (a->resid ? 8.0 : 4.0) : (a->resid ? 4.0 : 2.0));
+    Prof prof(kname, stream, 2.0 * a->M * a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
+    kern<<<2 * pairs, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, p);
+    WG_CHECK_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+}  // namespace
+
+// Used by wg_gemm for N % 256 == 0 problems with at least one full wave of 256 x 256 tiles.
+int launch_gemm_pair(const wg_gemm_args* a, cudaStream_t stream) {
+    switch (a->out_mode) {
+        case WG_OUT_BF16: return launch2<6, WG_OUT_BF16>(a, stream);
+        case WG_OUT_F32: return launch2<6, WG_OUT_F32>(a, stream);
+        default: set_error("launch_gemm_pair: unsupported out_mode %d", a->out_mode); return WG_ERR_INVALID;
+    }
+}
+
+}  // namespace wg
+
+#ifdef GEMM2_TRACE
+extern "C" __attribute__((visibility("default"))) int wg_debug_gemm2_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, wg::g_gemm2_trace, sizeof(long long) * 3 * 64 * 4);
+}
+#endif

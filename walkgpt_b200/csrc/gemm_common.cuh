@@ -5,6 +5,10 @@
 #include "ptx.cuh"
 
 namespace wg {
+
+// gemm2.cu: CTA-pair (cta_group::2) kernel, 256 x 256 tiles; out_mode WG_OUT_BF16 or WG_OUT_F32, N % 256 == 0
+int launch_gemm_pair(const wg_gemm_args* a, cudaStream_t stream);
+
 namespace gemm_detail {
 
 constexpr int BM = 128;
