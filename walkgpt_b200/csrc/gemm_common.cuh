@@ -231,7 +231,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
                         for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
                     } else if (p.act == WG_ACT_GELU_ERF) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
                     } else if (p.act == WG_ACT_RELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
