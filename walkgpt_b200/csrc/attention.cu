@@ -28,8 +28,9 @@ namespace {
 constexpr int ATT_BQ = 128;      // queries per CTA
 constexpr int ATT_BKV = 128;     // keys per block
 constexpr int ATT_D = 64;        // head dim
-constexpr int ATT_THREADS = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: softmax (one thread per query row)
-constexpr int ATT_SOFTMAX_THREADS = 128;
+// threads: warp 0 TMA, warp 1 MMA, then 4 * SPLIT softmax warps (SPLIT = threads per query row: 1, or 2 with the key block's
+// columns divided between them -- four softmax warps per scheduler at two CTAs per SM instead of two)
+__host__ __device__ constexpr int att_threads(int split) { return 64 + 128 * split; }
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: a [128 x 64] bf16 tile
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + TILE_BYTES;          // 2 stages
@@ -38,8 +39,10 @@ constexpr int OFF_BAR = OFF_V + 2 * TILE_BYTES;
 constexpr int ATT_NUM_BARS = 14;
 constexpr int OFF_KMASK = OFF_BAR + ATT_NUM_BARS * 8 + 16;  // key-validity bit words (32 keys each), built once per CTA
 constexpr int ATT_MAX_T = 8192;
-constexpr int ATT_SMEM_BYTES = OFF_KMASK + (ATT_MAX_T / 32) * 4;
+constexpr int OFF_XCH = OFF_KMASK + (ATT_MAX_T / 32) * 4;  // SPLIT = 2: row max [2 parities][2 halves][128] + row sum [2][128] exchange
+constexpr int ATT_SMEM_BYTES = OFF_XCH + (4 + 2) * 128 * 4;
 constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
+constexpr int ATT_SPLIT_DEFAULT = 1;
 constexpr int ATT_POLY_DEFAULT = 3;  // of every 8 exponentials, evaluated on the FMA pipe (B200: 0 -> 0.556 ms, 3 -> 0.545 ms)
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: the running scale is refreshed only when the row max grew by > 2^8
 
@@ -122,23 +125,25 @@ struct SoftmaxState {
 // g's exponentials instead of as serial phases after them (ncu showed the softmax warps spending 3/4 of their time outside
 // the MUFU-paced stretch).  The wait for the previous PV MMA (P buffer free) sits in the middle of the phase: the first 64
 // columns are packed into registers before it, so that the tensor core's latency is covered by exponentials, not by a stall.
-template <int NCH, int POLY>
+template <int NCH, int POLY, int SPLIT>
 __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const AttnParams& p, const uint32_t* kmask, uint32_t tmem_S, uint32_t tmem_O,
-                                              uint32_t tmem_P, uint32_t lane_off, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready, int tr) {
+                                              uint32_t tmem_P, uint32_t lane_off, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready, int tr, int half, int r, float* xch) {
+    // NCH = number of 32-column chunks THIS thread handles (SPLIT = 2: the thread owns columns [64 half, 64 half + 32 NCH))
     constexpr int NG = NCH * 4;                  // groups of 8 columns
-    constexpr int WAIT_AT = NG > 8 ? 8 : NG;     // the P-buffer wait happens once this many groups are packed
-    uint32_t sv2[NCH][32];
+    constexpr int HALF_NG = 4 * (4 / SPLIT) / 2; // the P-buffer wait happens once this many groups are packed (half a full row share)
+    constexpr int WAIT_AT = NG > HALF_NG ? HALF_NG : NG;
+    uint32_t sv2[NCH > 0 ? NCH : 1][32];
 #define sv(i) sv2[(i) >> 5][(i) & 31]
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, sv2[c]);
-    tmem_ld_wait();
+    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + half * 64 + c * 32, sv2[c]);
+    if (NCH > 0) tmem_ld_wait();
     TR(0, j, 2);
     tc_fence_before();
     mbar_arrive(s_free);  // S_j is in registers: the tensor core may overwrite it with S_{j+1}
     if (kmask != nullptr) {  // keys past T and masked keys: one validity word per 32 columns, branch-free selects
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            const uint32_t word = kmask[j * (ATT_BKV / 32) + c];
+            const uint32_t word = kmask[j * (ATT_BKV / 32) + half * 2 + c];
             if (word != 0xffffffffu) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) sv(c * 32 + i) = ((word >> i) & 1u) ? sv(c * 32 + i) : 0xff800000u;  // -inf
@@ -148,7 +153,15 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
     float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
 #pragma unroll
     for (int i = 0; i < NCH * 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv(i)));
-    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    if constexpr (SPLIT == 2) {
+        // the two threads of a row agree on the block maximum through smem (double-buffered by block parity: one 64-thread
+        // named barrier per block is enough); every later decision (reference max, rescale) is then identical in both
+        float* slot = xch + (j & 1) * 256;
+        slot[half * 128 + r] = mx;
+        named_bar_sync(2 + (r >> 5), 64);
+        mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+    }
     // lazily refreshed scale
     float alpha = 1.0f;
     bool refresh = false;
@@ -201,7 +214,8 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
                 if (__any_sync(0xffffffffu, refresh)) {
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    for (int cc = 0; cc < 2 / SPLIT; ++cc) {  // SPLIT = 2: each thread of the row rescales its 32 O columns
+                        const int c = SPLIT == 2 ? half : cc;
                         uint32_t ov[32];
                         tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
                         tmem_ld_wait();
@@ -217,16 +231,16 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
         if (g == WAIT_AT) {
 #pragma unroll
             for (int q = 0; q < WAIT_AT; ++q)
-                tmem_st_32x32b_x4(tmem_P + lane_off + q * 4, sv(q * 8 + 0), sv(q * 8 + 1), sv(q * 8 + 2), sv(q * 8 + 3));
+                tmem_st_32x32b_x4(tmem_P + lane_off + half * 32 + q * 4, sv(q * 8 + 0), sv(q * 8 + 1), sv(q * 8 + 2), sv(q * 8 + 3));
         } else if (g > WAIT_AT) {
             const int q = g - 1;
-            tmem_st_32x32b_x4(tmem_P + lane_off + q * 4, sv(q * 8 + 0), sv(q * 8 + 1), sv(q * 8 + 2), sv(q * 8 + 3));
+            tmem_st_32x32b_x4(tmem_P + lane_off + half * 32 + q * 4, sv(q * 8 + 0), sv(q * 8 + 1), sv(q * 8 + 2), sv(q * 8 + 3));
         }
     }
     float rs0, rs1;
     upk2(fadd2(rsA, rsB), rs0, rs1);
     st.l_run = st.l_run * alpha + (rs0 + rs1);
-    tmem_st_wait();  // P is in tensor memory
+    if (NCH > 0) tmem_st_wait();  // P is in tensor memory
     tc_fence_before();
     mbar_arrive(p_ready);
     TR(0, j, 5);
@@ -239,8 +253,8 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
 //   ->  O += P_j V_j accumulated IN TMEM across all key blocks.  The softmax uses a lazily refreshed scale: the reference
 //   maximum is only moved (and O / l rescaled through tcgen05.ld/st) when a row's maximum grew by more than 2^8, which is
 //   exact arithmetic (any common scale cancels in O / l) and takes the O round trip off the per-block critical path.
-template <int POLY>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+template <int POLY, int SPLIT>
+__global__ void __launch_bounds__(att_threads(SPLIT), 2)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled tiles need 1024B alignment
@@ -282,8 +296,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             mbar_init(&v_empty[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_free, ATT_SOFTMAX_THREADS);
-        mbar_init(p_ready, ATT_SOFTMAX_THREADS);
+        mbar_init(s_free, 128 * SPLIT);
+        mbar_init(p_ready, 128 * SPLIT);
         mbar_init(p_free, 1);
         fence_mbar_init();
     }
@@ -321,82 +335,90 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, false, false);  // Q (K-major) x K (K-major)
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 64, false, true);    // P (K-major) x V (MN-major)
-            // the last key block only spans n_last (multiple of 16) keys: narrower S MMA, fewer PV k-steps
-            const uint32_t idesc_s_last = umma_idesc_bf16(128, p.n_last, false, false);
-            const int pv_steps_last = p.n_last / 16;
-            const uint32_t q_addr = smem_u32(smem + OFF_Q);
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[0], 0);
-            tc_fence_after();
-            {
-                const uint32_t k_addr = smem_u32(smem + OFF_K);
-                const uint32_t idesc = nkb == 1 ? idesc_s_last : IDESC_S;
+        // ===================== MMA issuer: the whole warp runs the protocol, one elected lane issues =====================
+        constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, false, false);  // Q (K-major) x K (K-major)
+        constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 64, false, true);    // P (K-major) x V (MN-major)
+        // the last key block only spans n_last (multiple of 16) keys: narrower S MMA, fewer PV k-steps
+        const uint32_t idesc_s_last = umma_idesc_bf16(128, p.n_last, false, false);
+        const int pv_steps_last = p.n_last / 16;
+        // descriptors differ only in the 14-bit start-address field (bytes >> 4): build each once, then add
+        const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + OFF_Q));
+        const uint64_t k_desc0 = umma_desc_sw128(smem_u32(smem + OFF_K));
+        const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + OFF_V));
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t idesc = nkb == 1 ? idesc_s_last : IDESC_S;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
-                umma_commit(s_full);
-                umma_commit(&k_empty[0]);
-            }
-            for (int j = 0; j < nkb; ++j) {
-                const int s = j & 1;
-                if (j + 1 < nkb) {
-                    // S_{j+1} as soon as the softmax threads have pulled S_j out of TMEM: overlaps their exponentials
-                    const int s1 = (j + 1) & 1;
-                    TR(1, j, 0);
-                    mbar_wait(s_free, j & 1);
-                    TR(1, j, 1);
-                    mbar_wait(&k_full[s1], ((j + 1) >> 1) & 1);
-                    TR(1, j, 2);
-                    tc_fence_after();
-                    const uint32_t k_addr = smem_u32(smem + OFF_K + s1 * TILE_BYTES);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc + k * 2, k_desc0 + k * 2, idesc, k != 0);
+            umma_commit(s_full);
+            umma_commit(&k_empty[0]);
+        }
+        __syncwarp();
+        for (int j = 0; j < nkb; ++j) {
+            const int s = j & 1;
+            if (j + 1 < nkb) {
+                // S_{j+1} as soon as the softmax threads have pulled S_j out of TMEM: overlaps their exponentials
+                const int s1 = (j + 1) & 1;
+                TR(1, j, 0);
+                mbar_wait(s_free, j & 1);
+                TR(1, j, 1);
+                mbar_wait(&k_full[s1], ((j + 1) >> 1) & 1);
+                TR(1, j, 2);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t k_desc = k_desc0 + s1 * (TILE_BYTES >> 4);
                     const uint32_t idesc = (j + 2 == nkb) ? idesc_s_last : IDESC_S;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc, k != 0);
+                    for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc + k * 2, k_desc + k * 2, idesc, k != 0);
                     umma_commit(s_full);
                     umma_commit(&k_empty[s1]);
                 }
-                TR(1, j, 3);
-                mbar_wait(p_ready, j & 1);
-                TR(1, j, 4);
-                mbar_wait(&v_full[s], (j >> 1) & 1);
-                TR(1, j, 5);
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + OFF_V + s * TILE_BYTES);
+                __syncwarp();
+            }
+            TR(1, j, 3);
+            mbar_wait(p_ready, j & 1);
+            TR(1, j, 4);
+            mbar_wait(&v_full[s], (j >> 1) & 1);
+            TR(1, j, 5);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t v_desc = v_desc0 + s * (TILE_BYTES >> 4);
                 const int pv_steps = (j + 1 == nkb) ? pv_steps_last : 8;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     // A: P from tensor memory, 16 keys = 8 packed columns per step;  B: V rows (keys) step 16 rows = +2048 B
-                    if (k < pv_steps) umma_f16_ts(tmem_O, tmem_P + k * 8, umma_desc_sw128(v_addr + k * 2048), IDESC_O, (j | k) != 0);
+                    if (k < pv_steps) umma_f16_ts(tmem_O, tmem_P + k * 8, v_desc + k * (2048 >> 4), IDESC_O, (j | k) != 0);
                 }
                 umma_commit(&v_empty[s]);
                 umma_commit(p_free);  // P buffer reusable, O consistent
-                TR(1, j, 6);
             }
+            __syncwarp();
+            TR(1, j, 6);
         }
     } else {
-        // ===================== softmax warpgroup: one thread per query row =====================
-        // (A variant with two threads per row -- 8 softmax warps per CTA -- was measured slower on B200: 1.06 ms vs 0.80 ms
-        //  for B=64, T=1025, 16 heads; the extra named barriers / smem exchange cost more than the added warp parallelism.)
-        const int quarter = warp & 3;
+        // ===================== softmax warps: SPLIT threads per query row =====================
+        // SPLIT = 2 puts four softmax warps on every scheduler (two CTAs per SM); the two threads of a row exchange only the
+        // block maximum and the final row sum.  Measured on B200 (ncu, B=64 T=1025): issue slots 52 % -> 64 % busy, eligible
+        // warps 0.7 -> 1.4 per cycle, but 23 % more instructions and the same 0.47 ms -- kept as a tuning knob, default 1.
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;        // which 64 columns of a key block this thread owns (always 0 for SPLIT = 1)
         const int r = quarter * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
         // key-validity words (keys past T, masked keys), built once: the per-block softmax only does selects on them
         const uint32_t* kmask = nullptr;
         if (p.key_valid != nullptr || (p.T % ATT_BKV) != 0) {
             uint32_t* words = reinterpret_cast<uint32_t*>(smem + OFF_KMASK);
             const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)img * p.T : nullptr;
-            for (int w = quarter; w < nkb * (ATT_BKV / 32); w += 4) {
+            for (int w = warp - 2; w < nkb * (ATT_BKV / 32); w += 4 * SPLIT) {
                 const int key = w * 32 + lane;
                 const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
                 const uint32_t word = __ballot_sync(0xffffffffu, ok);
                 if (lane == 0) words[w] = word;
             }
-            named_bar_sync(1, ATT_SOFTMAX_THREADS);
+            named_bar_sync(1, 128 * SPLIT);
             kmask = words;
         }
         // warps whose 32 query rows all lie past T (last query tile: only the 1025th token is real) skip the arithmetic and only
@@ -417,20 +439,38 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
             const int ncols = (j + 1 == nkb) ? p.n_last : ATT_BKV;
             const uint32_t* km = (p.key_valid != nullptr || j + 1 == nkb) ? kmask : nullptr;  // only blocks that can hold invalid keys
-            if (ncols > 96) softmax_block<4, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
-            else if (ncols > 64) softmax_block<3, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
-            else if (ncols > 32) softmax_block<2, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
-            else softmax_block<1, POLY>(st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr);
+            const int nch_tot = (ncols + 31) >> 5;                       // 32-column chunks that hold keys in this block
+            int nch = nch_tot - half * 2;                                // ... of which this thread owns
+            nch = nch < 0 ? 0 : (nch > 4 / SPLIT ? 4 / SPLIT : nch);
+#define WG_SM_ARGS st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr, half, r, xch
+            if constexpr (SPLIT == 1) {
+                if (nch == 4) softmax_block<4, POLY, 1>(WG_SM_ARGS);
+                else if (nch == 3) softmax_block<3, POLY, 1>(WG_SM_ARGS);
+                else if (nch == 2) softmax_block<2, POLY, 1>(WG_SM_ARGS);
+                else softmax_block<1, POLY, 1>(WG_SM_ARGS);
+            } else {
+                if (nch == 2) softmax_block<2, POLY, 2>(WG_SM_ARGS);
+                else if (nch == 1) softmax_block<1, POLY, 2>(WG_SM_ARGS);
+                else softmax_block<0, POLY, 2>(WG_SM_ARGS);
+            }
+#undef WG_SM_ARGS
         }
-        const float l_run = st.l_run;
+        float l_run = st.l_run;
+        if constexpr (SPLIT == 2) {  // row sum = the two threads' partial sums (same scale: the reference max is common)
+            float* ls = xch + 512;
+            ls[half * 128 + r] = l_run;
+            named_bar_sync(2 + quarter, 64);
+            l_run += ls[(half ^ 1) * 128 + r];
+        }
         // ---- epilogue: O / l, bf16, stage into the (now idle) Q tile, TMA store
         mbar_wait(p_free, (nkb - 1) & 1);
         tc_fence_after();
         const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
         uint8_t* o_row = smem + OFF_Q + r * 128;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int cc = 0; cc < 2 / SPLIT; ++cc) {
             if (!warp_active) break;
+            const int c = SPLIT == 2 ? half : cc;  // SPLIT = 2: each thread of the row normalises its 32 O columns
             uint32_t ov[32];
             tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
             tmem_ld_wait();
@@ -445,7 +485,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, ATT_SOFTMAX_THREADS);
+        named_bar_sync(1, 128 * SPLIT);
         if (threadIdx.x == 64) {
             tma_store_3d(&tmO, smem + OFF_Q, head * ATT_D, qt * ATT_BQ, img);
             tma_store_commit();
@@ -592,17 +632,18 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     p.n_last = ((T - (p.num_kv_blocks - 1) * ATT_BKV) + 15) / 16 * 16;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.key_valid = key_valid;
-    // fraction of the exponentials evaluated on the FMA pipe (POLY of every 8); WG_ATTN_POLY overrides for tuning
-    static int poly = -1;
+    // tuning knobs (defaults measured on B200): WG_ATTN_POLY = exponentials per 8 evaluated on the FMA pipe,
+    // WG_ATTN_SPLIT = softmax threads per query row
+    static int poly = -1, split = -1, smem_pad = 0;
     if (poly < 0) {
+        const char* pad = getenv("WG_ATTN_SMEM_PAD");  // debug: extra dynamic smem (forces one CTA per SM when large)
+        smem_pad = pad ? atoi(pad) : 0;
         const char* e = getenv("WG_ATTN_POLY");
         poly = e ? atoi(e) : ATT_POLY_DEFAULT;
         if (poly < 0 || poly > 4) poly = ATT_POLY_DEFAULT;
-        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-        WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        e = getenv("WG_ATTN_SPLIT");
+        split = e ? atoi(e) : ATT_SPLIT_DEFAULT;
+        if (split != 1 && split != 2) split = ATT_SPLIT_DEFAULT;
     }
     // a few leftover rows (T % 128 <= TAIL_MAX_ROWS) go through the CUDA-core tail kernel instead of a whole tensor-core tile
     const int rem = T % ATT_BQ;
@@ -612,13 +653,33 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
               (row0 > 0 ? 1 : 0) + (tail_rows > 0 ? 1 : 0));
     if (row0 > 0) {
         dim3 grid((row0 + ATT_BQ - 1) / ATT_BQ, heads, B);
-        switch (poly) {
-            case 1: attention_d64_kernel<1><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
-            case 2: attention_d64_kernel<2><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
-            case 3: attention_d64_kernel<3><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
-            case 4: attention_d64_kernel<4><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
-            default: attention_d64_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQKV, tmO, p); break;
+#define WG_ATT_LAUNCH(P, S)                                                                                                     \
+    do {                                                                                                                        \
+        static bool attr_set = false;                                                                                           \
+        if (!attr_set) {                                                                                                        \
+            WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES + smem_pad)); \
+            attr_set = true;                                                                                                    \
+        }                                                                                                                       \
+        attention_d64_kernel<P, S><<<grid, att_threads(S), ATT_SMEM_BYTES + smem_pad, stream>>>(tmQKV, tmO, p);                            \
+    } while (0)
+        if (split == 2) {
+            switch (poly) {
+                case 1: WG_ATT_LAUNCH(1, 2); break;
+                case 2: WG_ATT_LAUNCH(2, 2); break;
+                case 3: WG_ATT_LAUNCH(3, 2); break;
+                case 4: WG_ATT_LAUNCH(4, 2); break;
+                default: WG_ATT_LAUNCH(0, 2); break;
+            }
+        } else {
+            switch (poly) {
+                case 1: WG_ATT_LAUNCH(1, 1); break;
+                case 2: WG_ATT_LAUNCH(2, 1); break;
+                case 3: WG_ATT_LAUNCH(3, 1); break;
+                case 4: WG_ATT_LAUNCH(4, 1); break;
+                default: WG_ATT_LAUNCH(0, 1); break;
+            }
         }
+#undef WG_ATT_LAUNCH
         WG_CHECK_CUDA(cudaGetLastError());
     }
     if (tail_rows > 0) {

@@ -75,6 +75,20 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     }
 }
 
+// One lane of a fully converged warp (elect.sync).  Code that issues tcgen05 / TMA instructions should be reached with
+// WARP-UNIFORM control flow and then narrowed with this predicate: after `if (lane == 0)` the compiler must assume
+// divergence and wraps every tensor-core instruction in an ELECT / R2UR / BRA.U.ANY loop (~13 instructions and ~90 cycles per
+// MMA, measured in the attention kernel), whereas here operands stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- named barriers / fences
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
