@@ -129,89 +129,144 @@ __global__ void __launch_bounds__(256) broadcast_queries_kernel(const float* __r
 
 // Cross attention of nq (<=12) projected queries against Nkv keys, head_dim 128.  grid (B, heads); 256 threads.
 //   qp  bf16 [B*nq, D]; kv bf16 [B*Nkv, ldkv] with K at column k_off + h*128 and V at v_off + h*128; out bf16 [B*nq, D]
+// fp32 CUDA-core arithmetic (3 GFLOP per launch).  The first version was bound by shared-memory instructions (one scalar
+// LDS per FMA for the broadcast query values, one per probability): 0.50 ms per launch at Nkv = 1024.  Here the queries are
+// read as float4 and shared by two keys per thread, scores / probabilities live as [key][12] rows (three float4 per key),
+// and the softmax statistics are reduced across the block instead of being re-read per query row.
 constexpr int MAXQ = 12;
+constexpr int QPAD = 12;  // score row pitch (floats): three float4 per key, 48-byte pitch (conflict-free for 16-byte accesses)
 __global__ void __launch_bounds__(256) msqp_attention_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ kv, int ldkv,
                                                              int k_off, int v_off, __nv_bfloat16* __restrict__ out, int nq, int Nkv) {
-    extern __shared__ float sm[];
-    float* qs = sm;                 // [nq][128]
-    float* sc = sm + MAXQ * 128;    // [nq][Nkv]
-    float* red = sc + (size_t)nq * Nkv;  // [4][MAXQ][128] partial outputs
+    extern __shared__ __align__(16) float sm[];
+    float* qs = sm;                            // [MAXQ][128], rows >= nq zero
+    float* sc = sm + MAXQ * 128;               // [Nkv][QPAD] scores, then exp(score - max)
+    float* red = sc + (size_t)Nkv * QPAD;      // [4][MAXQ][128] partial outputs; first used as [8 warps][QPAD] reduction scratch
     const int b = blockIdx.x, h = blockIdx.y;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < nq * 128; i += 256) qs[i] = __bfloat162float(qp[((size_t)b * nq + i / 128) * D + h * 128 + (i & 127)]);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < MAXQ * 128; i += 256)
+        qs[i] = (i / 128 < nq) ? __bfloat162float(qp[((size_t)b * nq + i / 128) * D + h * 128 + (i & 127)]) : 0.f;
     __syncthreads();
     const float scale = 0.08838834764831845f;  // 1/sqrt(128)
     const __nv_bfloat16* kbase = kv + (size_t)b * Nkv * ldkv + k_off + h * 128;
     const __nv_bfloat16* vbase = kv + (size_t)b * Nkv * ldkv + v_off + h * 128;
-    for (int key = tid; key < Nkv; key += 256) {
-        float acc[MAXQ];
+    // ---- scores: two keys per thread and pass, so every float4 of a query feeds 8 FMAs
+    float mx[MAXQ];
 #pragma unroll
-        for (int i = 0; i < MAXQ; ++i) acc[i] = 0.f;
-        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)key * ldkv);
-#pragma unroll 4
+    for (int i = 0; i < MAXQ; ++i) mx[i] = -INFINITY;
+    for (int key0 = tid; key0 < Nkv; key0 += 512) {
+        const int key1 = key0 + 256;
+        const bool has1 = key1 < Nkv;
+        float acc0[MAXQ], acc1[MAXQ];
+#pragma unroll
+        for (int i = 0; i < MAXQ; ++i) acc0[i] = acc1[i] = 0.f;
+        const uint4* kr0 = reinterpret_cast<const uint4*>(kbase + (size_t)key0 * ldkv);
+        const uint4* kr1 = reinterpret_cast<const uint4*>(kbase + (size_t)(has1 ? key1 : key0) * ldkv);
+#pragma unroll 2
         for (int c = 0; c < 16; ++c) {
-            uint4 u = kr[c];
-            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-            float kf[8];
+            const uint4 u0 = __ldg(kr0 + c), u1 = __ldg(kr1 + c);
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+            float k0[8], k1[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float2 t = __bfloat1622float2(hh[e]);
-                kf[e * 2] = t.x;
-                kf[e * 2 + 1] = t.y;
+                const float2 t0 = __bfloat1622float2(h0[e]), t1 = __bfloat1622float2(h1[e]);
+                k0[e * 2] = t0.x; k0[e * 2 + 1] = t0.y;
+                k1[e * 2] = t1.x; k1[e * 2 + 1] = t1.y;
             }
 #pragma unroll
             for (int i = 0; i < MAXQ; ++i) {
-                if (i < nq) {
-                    const float* qi = qs + i * 128 + c * 8;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[i] = fmaf(kf[e], qi[e], acc[i]);
-                }
+                const float4 qa = *reinterpret_cast<const float4*>(qs + i * 128 + c * 8);
+                const float4 qb = *reinterpret_cast<const float4*>(qs + i * 128 + c * 8 + 4);
+                acc0[i] = fmaf(k0[0], qa.x, acc0[i]); acc0[i] = fmaf(k0[1], qa.y, acc0[i]);
+                acc0[i] = fmaf(k0[2], qa.z, acc0[i]); acc0[i] = fmaf(k0[3], qa.w, acc0[i]);
+                acc0[i] = fmaf(k0[4], qb.x, acc0[i]); acc0[i] = fmaf(k0[5], qb.y, acc0[i]);
+                acc0[i] = fmaf(k0[6], qb.z, acc0[i]); acc0[i] = fmaf(k0[7], qb.w, acc0[i]);
+                acc1[i] = fmaf(k1[0], qa.x, acc1[i]); acc1[i] = fmaf(k1[1], qa.y, acc1[i]);
+                acc1[i] = fmaf(k1[2], qa.z, acc1[i]); acc1[i] = fmaf(k1[3], qa.w, acc1[i]);
+                acc1[i] = fmaf(k1[4], qb.x, acc1[i]); acc1[i] = fmaf(k1[5], qb.y, acc1[i]);
+                acc1[i] = fmaf(k1[6], qb.z, acc1[i]); acc1[i] = fmaf(k1[7], qb.w, acc1[i]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < MAXQ; ++i)
-            if (i < nq) sc[(size_t)i * Nkv + key] = acc[i] * scale;
-    }
-    __syncthreads();
-    // softmax per query row (warp per row)
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int i = warp; i < nq; i += 8) {
-        float* row = sc + (size_t)i * Nkv;
-        float mx = -INFINITY;
-        for (int k = lane; k < Nkv; k += 32) mx = fmaxf(mx, row[k]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int k = lane; k < Nkv; k += 32) {
-            float e = __expf(row[k] - mx);
-            row[k] = e;
-            sum += e;
+        for (int i = 0; i < MAXQ; ++i) {
+            acc0[i] *= scale;
+            acc1[i] *= scale;
+            mx[i] = fmaxf(mx[i], acc0[i]);
+            if (has1) mx[i] = fmaxf(mx[i], acc1[i]);
         }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        for (int k = lane; k < Nkv; k += 32) row[k] *= inv;
+#pragma unroll
+        for (int g = 0; g < MAXQ / 4; ++g) {
+            *reinterpret_cast<float4*>(sc + (size_t)key0 * QPAD + g * 4) = make_float4(acc0[g * 4], acc0[g * 4 + 1], acc0[g * 4 + 2], acc0[g * 4 + 3]);
+            if (has1) *reinterpret_cast<float4*>(sc + (size_t)key1 * QPAD + g * 4) = make_float4(acc1[g * 4], acc1[g * 4 + 1], acc1[g * 4 + 2], acc1[g * 4 + 3]);
+        }
+    }
+    // ---- block-wide max per query
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) mx[i] = warp_max(mx[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < MAXQ; ++i) red[warp * QPAD + i] = mx[i];
     }
     __syncthreads();
-    // out[i][dim] = sum_k p[i][k] V[k][dim]:  thread = (key group 0..3, dim pair 0..63)
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+        float m = red[i];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w * QPAD + i]);
+        mx[i] = m;
+    }
+    __syncthreads();
+    // ---- exponentials (each thread on the keys it wrote) + block-wide sums; the 1/sum is applied to the output
+    float sum[MAXQ];
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) sum[i] = 0.f;
+    for (int key = tid; key < Nkv; key += 256) {
+#pragma unroll
+        for (int g = 0; g < MAXQ / 4; ++g) {
+            float4 v = *reinterpret_cast<const float4*>(sc + (size_t)key * QPAD + g * 4);
+            v.x = __expf(v.x - mx[g * 4]); v.y = __expf(v.y - mx[g * 4 + 1]); v.z = __expf(v.z - mx[g * 4 + 2]); v.w = __expf(v.w - mx[g * 4 + 3]);
+            sum[g * 4] += v.x; sum[g * 4 + 1] += v.y; sum[g * 4 + 2] += v.z; sum[g * 4 + 3] += v.w;
+            *reinterpret_cast<float4*>(sc + (size_t)key * QPAD + g * 4) = v;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) sum[i] = warp_sum(sum[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < MAXQ; ++i) red[warp * QPAD + i] = sum[i];
+    }
+    __syncthreads();
+    float inv[MAXQ];
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+        float t = red[i];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += red[w * QPAD + i];
+        inv[i] = 1.0f / t;
+    }
+    __syncthreads();
+    // ---- out[i][dim] = sum_k p[i][k] V[k][dim]:  thread = (key group 0..3, dim pair 0..63)
     const int dp = tid & 63, grp = tid >> 6;
     float o0[MAXQ], o1[MAXQ];
 #pragma unroll
     for (int i = 0; i < MAXQ; ++i) o0[i] = o1[i] = 0.f;
+#pragma unroll 4
     for (int key = grp; key < Nkv; key += 4) {
-        float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)key * ldkv + dp * 2));
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)key * ldkv + dp * 2));
 #pragma unroll
-        for (int i = 0; i < MAXQ; ++i) {
-            if (i < nq) {
-                float p = sc[(size_t)i * Nkv + key];
-                o0[i] = fmaf(p, v.x, o0[i]);
-                o1[i] = fmaf(p, v.y, o1[i]);
-            }
+        for (int g = 0; g < MAXQ / 4; ++g) {
+            const float4 pr = *reinterpret_cast<const float4*>(sc + (size_t)key * QPAD + g * 4);
+            o0[g * 4] = fmaf(pr.x, v.x, o0[g * 4]);         o1[g * 4] = fmaf(pr.x, v.y, o1[g * 4]);
+            o0[g * 4 + 1] = fmaf(pr.y, v.x, o0[g * 4 + 1]); o1[g * 4 + 1] = fmaf(pr.y, v.y, o1[g * 4 + 1]);
+            o0[g * 4 + 2] = fmaf(pr.z, v.x, o0[g * 4 + 2]); o1[g * 4 + 2] = fmaf(pr.z, v.y, o1[g * 4 + 2]);
+            o0[g * 4 + 3] = fmaf(pr.w, v.x, o0[g * 4 + 3]); o1[g * 4 + 3] = fmaf(pr.w, v.y, o1[g * 4 + 3]);
         }
     }
 #pragma unroll
     for (int i = 0; i < MAXQ; ++i)
         if (i < nq) {
-            red[(grp * MAXQ + i) * 128 + dp * 2] = o0[i];
-            red[(grp * MAXQ + i) * 128 + dp * 2 + 1] = o1[i];
+            red[(grp * MAXQ + i) * 128 + dp * 2] = o0[i] * inv[i];
+            red[(grp * MAXQ + i) * 128 + dp * 2 + 1] = o1[i] * inv[i];
         }
     __syncthreads();
     for (int i = tid; i < nq * 128; i += 256) {
@@ -361,7 +416,7 @@ extern "C" int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16,
         broadcast_queries_kernel<<<grid_for((long long)Mq * (D / 4)), 256, 0, s>>>(S.queries, m.q[sc], B, S.nq);
         }
         WG_CHECK_CUDA(cudaGetLastError());
-        const size_t smem = (size_t)(MAXQ * 128 + (size_t)S.nq * Nkv + 4 * MAXQ * 128) * sizeof(float);
+        const size_t smem = (size_t)(MAXQ * 128 + (size_t)QPAD * Nkv + 4 * MAXQ * 128) * sizeof(float);
         WG_REQUIRE(smem <= 227 * 1024, "wg_msqp_forward: %d kv tokens x %d queries exceed shared memory", Nkv, S.nq);
         WG_CHECK_CUDA(cudaFuncSetAttribute(msqp_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         for (int l = 0; l < 2; ++l) {
