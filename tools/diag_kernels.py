@@ -243,6 +243,14 @@ def t_post():
     ms = e0.elapsed_time(e1) / 10
     byts = 768 * (64 * 64 * 4 + 448 * 448 * 5)
     print(f"time postprocess 768 masks (incl. torch.empty): {ms:.3f} ms -> {byts/ms/1e6:.1f} GB/s", flush=True)
+    low = torch.randn(64 * 3, 64, 64, device=dev)
+    for _ in range(3): postprocess_masks_fused(low, (448, 448), (448, 448))
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(10): postprocess_masks_fused(low, (448, 448), (448, 448))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    byts = 192 * (64 * 64 * 4 + 448 * 448 * 5)
+    print(f"time postprocess 192 masks (incl. torch.empty): {ms:.3f} ms -> {byts/ms/1e6:.1f} GB/s", flush=True)
 
 def t_path():
     from walkgpt_b200.modules import GroundingPath, merge_split

@@ -21,59 +21,90 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 }
 
 // dst[n, y, x] = bilinear(src[n]) for y < dh, x < dw, where the virtual full output is (full_h, full_w) (crop = top-left).
-// VEC consecutive x per thread.  SCORE: also write the u8 mask and accumulate (sum sigmoid*[>0], count [>0]) per mask.
+// One thread owns VEC consecutive x of a BAND of rows: the column taps / weights are computed once per thread, the source
+// (a few KB per mask) stays in L1, every logit is written exactly once with 16-byte streaming stores, and the score partial
+// sums are reduced once per CTA (2 atomics per band instead of per row).  grid (x groups, bands, masks).
+// SCORE: also write the u8 mask and accumulate (sum sigmoid*[>0], count [>0]) per mask.
+constexpr int BIL_THREADS = 128;
 template <int VEC, bool SCORE>
-__global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__ src, int sh, int sw, float* __restrict__ dst, int dh, int dw,
-                                                       float scale_y, float scale_x, uint8_t* __restrict__ mask, float* __restrict__ accum) {
+__global__ void __launch_bounds__(BIL_THREADS) bilinear_kernel(const float* __restrict__ src, int sh, int sw, float* __restrict__ dst, int dh, int dw,
+                                                                float scale_y, float scale_x, uint8_t* __restrict__ mask, float* __restrict__ accum,
+                                                                int rows_per_band) {
     const int n = blockIdx.z;
-    const int y = blockIdx.y;
+    const int ya = blockIdx.y * rows_per_band;
+    const int yb = min(dh, ya + rows_per_band);
     const int xg = blockIdx.x * blockDim.x + threadIdx.x;  // group of VEC pixels
     const int x0 = xg * VEC;
     float ssum = 0.f, scnt = 0.f;
     if (x0 < dw) {
-        int y0, y1;
-        float ly;
-        src_index(y, scale_y, sh, y0, y1, ly);
-        const float* r0 = src + ((size_t)n * sh + y0) * sw;
-        const float* r1 = src + ((size_t)n * sh + y1) * sw;
-        float o[VEC];
+        int xa[VEC], xb[VEC];
+        float lx[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const int x = x0 + v;
-            int xa, xb;
-            float lx;
-            src_index(x < dw ? x : dw - 1, scale_x, sw, xa, xb, lx);
-            const float top = (1.f - lx) * __ldg(r0 + xa) + lx * __ldg(r0 + xb);
-            const float bot = (1.f - lx) * __ldg(r1 + xa) + lx * __ldg(r1 + xb);
-            o[v] = (1.f - ly) * top + ly * bot;
+            src_index(x < dw ? x : dw - 1, scale_x, sw, xa[v], xb[v], lx[v]);
         }
-        const size_t off = ((size_t)n * dh + y) * dw + x0;
-        if (VEC == 4 && x0 + 3 < dw) {
-            *reinterpret_cast<float4*>(dst + off) = make_float4(o[0], o[1], o[2], o[3]);
-            if (SCORE && mask) {
-                uchar4 m;
-                m.x = o[0] > 0.f; m.y = o[1] > 0.f; m.z = o[2] > 0.f; m.w = o[3] > 0.f;
-                *reinterpret_cast<uchar4*>(mask + off) = m;
+        const float* sbase = src + (size_t)n * sh * sw;
+        const bool full_vec = (VEC == 4) && (x0 + 3 < dw);
+        // horizontally interpolated source rows y0 / y1, recomputed only when the source row pair changes (an up-sampling
+        // band reuses each pair for several output rows): 4 * VEC L1 loads per CHANGE instead of per output row
+        float h0[VEC], h1[VEC];
+        int cur0 = -1, cur1 = -1;
+        for (int y = ya; y < yb; ++y) {
+            int y0, y1;
+            float ly;
+            src_index(y, scale_y, sh, y0, y1, ly);
+            if (y0 != cur0 || y1 != cur1) {
+                if (y0 == cur1) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) h0[v] = h1[v];
+                } else {
+                    const float* r0 = sbase + (size_t)y0 * sw;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) h0[v] = (1.f - lx[v]) * __ldg(r0 + xa[v]) + lx[v] * __ldg(r0 + xb[v]);
+                }
+                if (y1 == y0) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) h1[v] = h0[v];
+                } else {
+                    const float* r1 = sbase + (size_t)y1 * sw;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) h1[v] = (1.f - lx[v]) * __ldg(r1 + xa[v]) + lx[v] * __ldg(r1 + xb[v]);
+                }
+                cur0 = y0;
+                cur1 = y1;
             }
-        } else {
+            float o[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v)
-                if (x0 + v < dw) {
-                    dst[off + v] = o[v];
-                    if (SCORE && mask) mask[off + v] = o[v] > 0.f;
+            for (int v = 0; v < VEC; ++v) o[v] = (1.f - ly) * h0[v] + ly * h1[v];
+            const size_t off = ((size_t)n * dh + y) * dw + x0;
+            if (full_vec) {
+                __stcs(reinterpret_cast<float4*>(dst + off), make_float4(o[0], o[1], o[2], o[3]));
+                if (SCORE && mask) {
+                    uchar4 m;
+                    m.x = o[0] > 0.f; m.y = o[1] > 0.f; m.z = o[2] > 0.f; m.w = o[3] > 0.f;
+                    __stcs(reinterpret_cast<uchar4*>(mask + off), m);
                 }
-        }
-        if (SCORE) {
+            } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v)
-                if (x0 + v < dw && o[v] > 0.f) {
-                    ssum += 1.0f / (1.0f + __expf(-o[v]));
-                    scnt += 1.f;
-                }
+                for (int v = 0; v < VEC; ++v)
+                    if (x0 + v < dw) {
+                        dst[off + v] = o[v];
+                        if (SCORE && mask) mask[off + v] = o[v] > 0.f;
+                    }
+            }
+            if (SCORE) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (x0 + v < dw && o[v] > 0.f) {
+                        ssum += 1.0f / (1.0f + __expf(-o[v]));
+                        scnt += 1.f;
+                    }
+            }
         }
     }
     if (SCORE) {
-        __shared__ float red[2][8];
+        __shared__ float red[2][BIL_THREADS / 32];
         ssum = warp_sum(ssum);
         scnt = warp_sum(scnt);
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,16 +194,20 @@ int launch_bilinear(const float* src, int n, int sh, int sw, float* dst, int dh,
     // algorithmic bytes: read the source once, write fp32 logits (+ u8 mask)
     Prof prof(SCORE ? "postprocess_bilinear_score" : "postprocess_bilinear", s, 0.0,
               (double)n * ((double)sh * sw * 4.0 + (double)dh * dw * (SCORE && mask ? 5.0 : 4.0)));
-    if (dw % 4 == 0) {
-        const int groups = dw / 4;
-        const int threads = groups >= 128 ? 128 : ((groups + 31) / 32) * 32;
-        dim3 grid((groups + threads - 1) / threads, dh, n);
-        bilinear_kernel<4, SCORE><<<grid, threads, 0, s>>>(src, sh, sw, dst, dh, dw, sy, sx, mask, accum);
-    } else {
-        const int threads = dw >= 256 ? 256 : ((dw + 31) / 32) * 32;
-        dim3 grid((dw + threads - 1) / threads, dh, n);
-        bilinear_kernel<1, SCORE><<<grid, threads, 0, s>>>(src, sh, sw, dst, dh, dw, sy, sx, mask, accum);
-    }
+    // bands of rows: enough CTAs for ~8 per SM, at least 8 rows each so the per-thread column set-up is amortised
+    const int vec = (dw % 4 == 0) ? 4 : 1;
+    const int groups = (dw + vec - 1) / vec;
+    const int xblocks = (groups + BIL_THREADS - 1) / BIL_THREADS;
+    int bands = (8 * device_sm_count() + n * xblocks - 1) / (n * xblocks);
+    if (bands < 1) bands = 1;
+    int rows_per_band = (dh + bands - 1) / bands;
+    if (rows_per_band < 8) rows_per_band = 8;
+    bands = (dh + rows_per_band - 1) / rows_per_band;
+    dim3 grid(xblocks, bands, n);
+    if (vec == 4)
+        bilinear_kernel<4, SCORE><<<grid, BIL_THREADS, 0, s>>>(src, sh, sw, dst, dh, dw, sy, sx, mask, accum, rows_per_band);
+    else
+        bilinear_kernel<1, SCORE><<<grid, BIL_THREADS, 0, s>>>(src, sh, sw, dst, dh, dw, sy, sx, mask, accum, rows_per_band);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
 }
