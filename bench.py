@@ -201,38 +201,70 @@ def main():
     value = world * B * K / (ms_total / 1e3)
 
     # ---------------- end-to-end through the public API with HOST buffers ("e2e") ----------------
-    h_masks = torch.empty(B * S, 448, 448, dtype=torch.uint8).pin_memory()
-    h_scores = torch.empty(B * S, dtype=torch.float32).pin_memory()
-    h_iou = torch.empty(B * S, 1, dtype=torch.float32).pin_memory()
-    h_depth = torch.empty(B * S, dtype=torch.float32).pin_memory()
-    h_vis = torch.empty(B, 36, H, dtype=torch.bfloat16).pin_memory()
-    d_px = torch.empty_like(dev_px[0])
-    d_seg = torch.empty_like(dev_seg[0])
+    # Every step copies ITS inputs from pinned host memory and returns ITS results to pinned host memory inside the timed
+    # region.  The loop is the double-buffered serving loop a caller would write around GroundingPath.forward: the H2D copy
+    # of step i+1 and the D2H copy of step i-1 run on their own streams while step i computes; the host consumes (waits
+    # for) the results of step i-1 before it launches step i+1, and the region ends when the last result is on the host.
+    NB2 = 2
+    h_masks = [torch.empty(B * S, 448, 448, dtype=torch.uint8).pin_memory() for _ in range(NB2)]
+    h_scores = [torch.empty(B * S, dtype=torch.float32).pin_memory() for _ in range(NB2)]
+    h_iou = [torch.empty(B * S, 1, dtype=torch.float32).pin_memory() for _ in range(NB2)]
+    h_depth = [torch.empty(B * S, dtype=torch.float32).pin_memory() for _ in range(NB2)]
+    h_vis = [torch.empty(B, 36, H, dtype=torch.bfloat16).pin_memory() for _ in range(NB2)]
+    d_px = [torch.empty_like(dev_px[0]) for _ in range(NB2)]
+    d_seg = [torch.empty_like(dev_seg[0]) for _ in range(NB2)]
+    s_main = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(NB2)]        # inputs of the step using buffer b are on the device
+    ev_used = [torch.cuda.Event() for _ in range(NB2)]      # the step using input buffer b has finished reading it
+    ev_out = [torch.cuda.Event() for _ in range(NB2)]       # results of the step using host buffer b are on the host
 
-    def step_e2e(i):
-        d_px.copy_(host_px[i % NBUF], non_blocking=True)
-        d_seg.copy_(host_seg[i % NBUF], non_blocking=True)
-        out = model(d_px, d_seg, offs)
-        h_masks.copy_(out["masks"], non_blocking=True)
-        h_scores.copy_(out["scores"], non_blocking=True)
-        h_iou.copy_(out["iou"], non_blocking=True)
-        h_depth.copy_(out["depth"], non_blocking=True)
-        h_vis.copy_(out["vis_tokens"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the result of every step
-        return out
+    def issue_h2d(i):
+        b = i % NB2
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_used[b])
+            d_px[b].copy_(host_px[i % NBUF], non_blocking=True)
+            d_seg[b].copy_(host_seg[i % NBUF], non_blocking=True)
+            ev_in[b].record(s_in)
 
-    h2d = d_px.numel() * 2 + d_seg.numel() * 2
-    d2h = h_masks.numel() + 4 * (h_scores.numel() + h_iou.numel() + h_depth.numel()) + 2 * h_vis.numel()
-    for i in range(2):
-        step_e2e(i)
+    def run_e2e(n):
+        for b in range(NB2):
+            ev_used[b].record(s_main)
+        e0.record(s_in)  # device timestamp right before the first H2D copy
+        issue_h2d(0)
+        for i in range(n):
+            b = i % NB2
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            s_main.wait_event(ev_in[b])
+            out = model(d_px[b], d_seg[b], offs)
+            ev_used[b].record(s_main)
+            done = torch.cuda.Event()
+            done.record(s_main)
+            if i >= NB2:
+                ev_out[b].synchronize()  # host buffers b are about to be overwritten: their previous results were consumed
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                for h, key in ((h_masks, "masks"), (h_scores, "scores"), (h_iou, "iou"), (h_depth, "depth"), (h_vis, "vis_tokens")):
+                    out[key].record_stream(s_out)
+                    h[b].copy_(out[key], non_blocking=True)
+                ev_out[b].record(s_out)
+            if i >= 1:
+                ev_out[(i - 1) % NB2].synchronize()  # the caller consumes the result of step i-1 while step i runs
+        e1.record(s_out)  # device timestamp right after the last D2H copy
+        ev_out[(n - 1) % NB2].synchronize()
+
+    h2d = d_px[0].numel() * 2 + d_seg[0].numel() * 2
+    d2h = h_masks[0].numel() + 4 * (h_scores[0].numel() + h_iou[0].numel() + h_depth[0].numel()) + 2 * h_vis[0].numel()
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    e0.record()
-    for i in range(K):
-        step_e2e(i)
-    e1.record()
+    run_e2e(K)
+    torch.cuda.synchronize()
+    e2e_ms_host = (time.perf_counter() - t0) * 1e3   # host clock cross-check: first H2D issued -> last result on the host
+    e2e_ms = e0.elapsed_time(e1)                     # CUDA events: before the first H2D copy -> after the last D2H copy
     barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    ms2 = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (ms2.item() / 1e3)
@@ -319,7 +351,8 @@ def main():
                            "l2": f"{NBUF} input batches rotated; per-step activation traffic (several GB) exceeds the 126 MB L2",
                            "parallelism": f"dp{world} (images sharded, no collective on the hot path)"},
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                          "ms_per_step": ms2.item() / K},
+                                          "ms_per_step": ms2.item() / K, "ms_per_step_host_clock": e2e_ms_host / K,
+                                          "loop": "double-buffered: H2D of step i+1 and D2H of step i-1 on side streams overlap step i; results consumed one step late"},
                 "gpu_launches": int(launches), "roofline": roofline, "kernels": extra}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
