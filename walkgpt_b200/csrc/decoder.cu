@@ -26,7 +26,8 @@ namespace {
 constexpr int C = 256;   // transformer dim
 constexpr int NT = 6;    // tokens per prompt: iou, 4 mask tokens, 1 text embedding
 constexpr int CI = 128;  // cross-attention internal dim (downsample 2)
-constexpr int TK_THREADS = 256;
+constexpr int TK_THREADS = 512;  // one CTA per prompt: the kernel streams fp32 weights from L2, more threads = more loads in flight
+constexpr int TK_KEY_GROUPS = TK_THREADS / 16;  // token->image attention: 16 dims x this many key groups
 
 
 // out[t][n] = act( base + sum_k in[t][k] * Wt[k][n] ), t < NT.   in/out in shared memory, Wt fp32 [K][N] in global.
@@ -198,11 +199,11 @@ __device__ void tok_t2i_attention(const float* Qt, const float* __restrict__ kv,
         }
         __syncthreads();
         {
-            const int d = tid & 15, grp = tid >> 4;  // 16 dims x 16 key groups
+            const int d = tid & 15, grp = tid >> 4;  // 16 dims x TK_KEY_GROUPS key groups
             float o[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) o[t] = 0.f;
-            for (int key = grp; key < hw; key += 16) {
+            for (int key = grp; key < hw; key += TK_KEY_GROUPS) {
                 const float v = __ldg(kv + (size_t)key * ldkv + v_off + h * 16 + d);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) o[t] = fmaf(sc[t * hw + key], v, o[t]);
@@ -214,7 +215,7 @@ __device__ void tok_t2i_attention(const float* Qt, const float* __restrict__ kv,
         if (tid < NT * 16) {  // fixed-order reduction over the 16 key groups
             const int t = tid >> 4, d = tid & 15;
             float v = 0.f;
-            for (int gI = 0; gI < 16; ++gI) v += part[(gI * NT + t) * 16 + d];
+            for (int gI = 0; gI < TK_KEY_GROUPS; ++gI) v += part[(gI * NT + t) * 16 + d];
             A[t * CI + h * 16 + d] = v;
         }
         __syncthreads();
