@@ -50,7 +50,10 @@ def load_into(module, sd):
 
 
 # ------------------------------------------------------------------------------------------------ kernels
-@pytest.mark.parametrize("M_,N,K", [(128, 128, 64), (300, 384, 1024), (2050, 3072, 1024), (777, 512, 200), (65, 1024, 4096), (1, 256, 256)])
+# (2050, 3072, 1024) and (4900, 1024, 512) are large enough for the CTA-pair kernel (cta_group::2, 256 x 256 tiles; the second
+# with a ragged last row tile whose peer CTA lies completely past M); the others run on the 1-CTA kernel (BN = 128 / 256).
+@pytest.mark.parametrize("M_,N,K", [(128, 128, 64), (300, 384, 1024), (2050, 3072, 1024), (4900, 1024, 512), (777, 512, 200), (65, 1024, 4096),
+                                    (1, 256, 256)])
 def test_gemm_bf16_epilogues(M_, N, K):
     torch.manual_seed(0)
     a = (torch.randn(M_, K, device=DEV) * 0.5).bfloat16()
@@ -80,6 +83,29 @@ def test_gemm_layernorm_epilogue_and_periodic_bias():
     assert rel_err(ops.gemm(a2, w2, b2, bias_period=1024), a2.float() @ w2.float().T + b2.repeat(3, 1)) < 6e-3
 
 
+def test_gemm_pair_kernel_matches_single_cta_kernel():
+    """The CTA-pair kernel and the 1-CTA kernel accumulate every output in the same k order: bit-identical results."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import math, sys, torch
+        from walkgpt_b200 import ops
+        torch.manual_seed(0)
+        a = (torch.randn(5000, 1024, device="cuda") * 0.5).bfloat16(); w = (torch.randn(2048, 1024, device="cuda") / 32).bfloat16()
+        b = torch.randn(2048, device="cuda")
+        out = ops.gemm(a, w, b, act=ops.ACT_QUICK_GELU)
+        x = torch.randn(5000, 2048, device="cuda"); y = x.clone()
+        ops.gemm(a, w, b, out_mode=ops.OUT_F32, out=y, resid=y)
+        torch.save({"bf16": out.cpu(), "f32": y.cpu()}, sys.argv[1])
+    """)
+    outs = []
+    for pair in ("1", "0"):  # the switch is read once per process
+        path = f"/tmp/wg_pair_{pair}.pt"
+        env = dict(os.environ, WG_GEMM_PAIR=pair, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+        outs.append(torch.load(path))
+    assert torch.equal(outs[0]["bf16"], outs[1]["bf16"]) and torch.equal(outs[0]["f32"], outs[1]["f32"])
+
+
 def test_gemm_rejects_bad_arguments():
     a, w = torch.zeros(8, 60, device=DEV).bfloat16(), torch.zeros(8, 60, device=DEV).bfloat16()
     with pytest.raises(_lib.WalkGPTB200Error, match="multiples of 8"):
@@ -103,7 +129,10 @@ def _attn_ref(qkv, heads, scale, kv=None):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, heads * 64)
 
 
-@pytest.mark.parametrize("B,T,H,masked", [(1, 128, 1, False), (1, 1, 2, False), (2, 1025, 16, False), (2, 1025, 16, True), (1, 300, 3, True)])
+# T = 1025 / 130 / 5 / 1 leave 1-8 rows past the last full query tile: those rows run in the CUDA-core tail kernel; T = 300 / 264
+# have a partial tensor-core tile; masked cases exercise the key-validity words in every key block.
+@pytest.mark.parametrize("B,T,H,masked", [(1, 128, 1, False), (1, 1, 2, False), (2, 1025, 16, False), (2, 1025, 16, True), (1, 300, 3, True),
+                                          (2, 130, 2, True), (1, 5, 2, False), (1, 264, 1, False), (1, 1024, 4, False), (1, 1032, 2, True)])
 def test_attention(B, T, H, masked):
     torch.manual_seed(3)
     qkv = torch.randn(B, T, 3 * H * 64, device=DEV).bfloat16()

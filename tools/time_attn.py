@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from walkgpt_b200 import ops
 torch.manual_seed(0)
-B, T, H = 2, 1025, 16
+B, T, H = 2, int(os.environ.get("T", "1025")), 16
 qkv = torch.randn(B, T, 3 * H * 64, device="cuda").bfloat16()
 out = ops.attention_d64(qkv, H, 0.125)
 q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
