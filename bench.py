@@ -311,9 +311,9 @@ def main():
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     peak = peaks["bf16_sustained"]
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    tpath = os.path.join(ROOT, "profiles", "r01b_ncu_full_summary.json")
     if os.path.exists(tpath):  # dram__bytes_read+write of the dominant launch (ViT fc1), one `ncu --set full` capture
-        tj = json.load(open(tpath))["gemm_fc1"]
+        tj = json.load(open(tpath))["gemm2_fc1"]
         traffic = tj["dram_bytes"]
         traffic_note = f"ncu dram bytes of the fc1 launch ({tj['shape']}); algorithmic bytes of that launch {tj['algorithmic_bytes']}"
     roofline = {"kernel": "gemm2_bf16_kernel (CTA pair, tcgen05 cta_group::2) + gemm_bf16_kernel (1 CTA): tcgen05/TMEM + TMA, all epilogue variants", "bound": "tensor", "achieved": achieved, "peak": peak,
