@@ -296,6 +296,30 @@ def test_path_a_end_to_end_gates(path_model):
     assert rel_err(out["iou"], ref["iou"]) < 2e-2 or (out["iou"].cpu() - ref["iou"]).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("H,S", [(4096, 12), (5120, 16)])
+def test_path_a_other_baseline_configs(H, S):
+    """BASELINE.json configs[2] (12 [SEG] per image, H=4096) and configs[4] (LLaVA-13B width 5120, 16 [SEG] per image), one image each,
+    against the fp32 oracle at the north-star tolerances."""
+    m = M.GroundingPath(hidden_size=H, clip_layers=24, seed=2)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() >= 2:
+                p.copy_(p.to(torch.bfloat16).float())
+    m = m.to(DEV)
+    px = rnd((1, 3, 448, 448), 21).bfloat16()
+    seg = rnd((S, H), 22)
+    offs = [0, S]
+    out = m(px.to(DEV), seg.to(DEV), offs)
+    ref = path_a.path_a_forward(_oracle_weights(m), px.float(), seg, offs)
+    assert out["logits"].shape == (S, 448, 448) and out["vis_tokens"].shape == (1, 36, H)
+    err = (out["logits"].cpu() - ref["logits"]).abs().max().item()
+    decided = ref["logits"].abs() > LOGIT_TOL
+    iou = _mask_iou(out["masks"].cpu().bool() & decided, (ref["logits"] > 0) & decided)
+    print(f"H={H} S={S}: mask logits max-abs err {err:.4f}; IoU on decided pixels min {iou.min().item():.4f}")
+    assert err <= LOGIT_TOL and iou.min().item() >= IOU_MIN
+    assert rel_err(out["vis_tokens"], ref["vis_tokens"]) < 2e-2 and rel_err(out["txt_emb"], ref["txt_emb"]) < 1e-2
+
+
 def test_depth_extension_against_its_definition(path_model):
     """Depth has no reference implementation (parity unpinned): checked against oracle.path_a.depth_head evaluated on the
     CUDA path's own low-res logits and an fp32 recomputation of the upscaled embedding."""
