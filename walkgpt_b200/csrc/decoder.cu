@@ -458,10 +458,11 @@ __global__ void __launch_bounds__(256) upscale_mask_kernel(const float* __restri
         if (threadIdx.x < 33) pool_sm[threadIdx.x] = 0.f;
         __syncthreads();
     }
+    float v[32];
+    float pool_w = 0.f;
     if (row < rows) {
         const int p = (int)(row / hw), pos = (int)(row % hw);
         const int y = pos / gw, x = pos % gw;
-        float v[32];
         const float4* ur = reinterpret_cast<const float4*>(U + row * 128 + sub * 32);
         float s = 0.f;
 #pragma unroll
@@ -490,12 +491,31 @@ __global__ void __launch_bounds__(256) upscale_mask_kernel(const float* __restri
             low_res[((long long)p * n_out + m) * plane + opix] = d;
             if (m == 0) logit0 = d;
         }
-        if (do_pool) {
-            const float wgt = 1.0f / (1.0f + __expf(-logit0));
+        if (do_pool) pool_w = 1.0f / (1.0f + __expf(-logit0));
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(&pool_sm[i], wgt * v[i]);
-            atomicAdd(&pool_sm[32], wgt);
+        for (int i = 0; i < 32; ++i) v[i] *= pool_w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    if (do_pool) {
+        // sigmoid-weighted channel sums for the depth extension: butterfly transpose-reduction across the warp (31 shuffles:
+        // lane l ends up with the warp's sum of channel l), then one shared atomic per lane.  (33 shared atomics per thread
+        // onto 33 addresses serialised 256-fold and made this kernel 0.8 ms.)
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+                const float send = upper ? v[i] : v[i + off];
+                const float keep = upper ? v[i + off] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
         }
+        atomicAdd(&pool_sm[lane], v[0]);
+        const float wsum = warp_sum(pool_w);
+        if (lane == 0) atomicAdd(&pool_sm[32], wsum);
     }
     if (do_pool) {
         __syncthreads();

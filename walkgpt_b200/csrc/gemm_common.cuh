@@ -171,10 +171,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         float mean = 0.f, rstd = 1.f;
         const __nv_bfloat16* rrow = p.resid_bf16 ? p.resid_bf16 + (size_t)row * p.ldo : nullptr;
         if constexpr (EPI == WG_OUT_BF16_LN) {
-            // pass 1: row statistics over the full N == BN columns (this thread owns the row)
+            // pass 1: acc + bias + residual for the full N == BN columns of this thread's row, split between the two epilogue
+            // groups (alternate 32-column chunks).  The sums are written BACK to tensor memory, so pass 2 neither re-reads the
+            // residual rows (the expensive, uncoalesced part of this epilogue) nor the bias; the two groups exchange their
+            // partial (sum, sum of squares) through the head of the staging area.
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = grp; c < BN / 32; c += 2) {
                 uint32_t v[32];
                 float f[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
@@ -188,8 +191,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
                 for (int j = 0; j < 32; ++j) {
                     s1 += f[j];
                     s2 = fmaf(f[j], f[j], s2);
+                    v[j] = __float_as_uint(f[j]);
                 }
+                tmem_st_32x32b_x32(taddr + c * 32, v);
             }
+            tmem_st_wait();
+            tc_fence_before();
+            float2* xch = reinterpret_cast<float2*>(cbufs);  // [2 groups][128 rows]
+            if (grp == 0 && epi_tid == 0) tma_store_wait_read<0>();  // the previous tile's store no longer reads the staging area
+            named_bar_sync(3, 2 * EPI_GROUP_THREADS);
+            xch[grp * 128 + r] = make_float2(s1, s2);
+            named_bar_sync(3, 2 * EPI_GROUP_THREADS);
+            const float2 other = xch[(grp ^ 1) * 128 + r];
+            named_bar_sync(3, 2 * EPI_GROUP_THREADS);  // both groups have read before pass 2 reuses the staging area
+            tc_fence_after();
+            s1 += other.x;
+            s2 += other.y;
             mean = s1 * (1.0f / BN);
             float var = fmaxf(s2 * (1.0f / BN) - mean * mean, 0.f);
             rstd = rsqrtf(var + p.ln_eps);
@@ -210,12 +227,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
                 tmem_ld_32x32b_x32(taddr + c * 64 + half * 32, v);
                 tmem_ld_wait();
                 const int col0 = colc + half * 32;
-                add_bias32(v, f, p, row, col0);
                 if constexpr (EPI == WG_OUT_BF16_LN) {
-                    if (rrow) {
-                        if (p.split_out) add_resid_split_32(f, rrow + col0, p.N, row_ok, p.N - col0);
-                        else add_resid_bf16_32(f, rrow + col0, row_ok, 0, p.N - col0);
-                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);  // pass 1 left acc + bias + residual in TMEM
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + g * 4));
@@ -226,6 +240,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
                         f[g * 4 + 3] = (f[g * 4 + 3] - mean) * rstd * ga.w + be.w;
                     }
                 } else {
+                    add_bias32(v, f, p, row, col0);
                     if (p.act == WG_ACT_QUICK_GELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
