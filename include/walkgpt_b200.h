@@ -312,6 +312,32 @@ WG_API int wg_postprocess_masks(const float* low_res, int n_masks, int Hm, int W
 WG_API int wg_depth_head(const float* pooled, const int32_t* seg_offsets, int B, int max_S, const float* w1, const float* b1,
                          const float* w2, const float* b2, float* depth_out, void* stream);
 
+/* ---- SURVEY section 8(f), "next" rows: the steps on either side of the grounding path ------------------------------------- */
+
+/* F2a -- visual-token resample handed to the LLM (model/llava_walkgpt/model/llava_arch.py:252-259):
+ *   tokens [n, p*p, C] (channels last) -> [n, t*t, C], F.interpolate(bilinear, align_corners=False) computed in fp32 in
+ *   PyTorch's operation order, stored in the input dtype (bf16 when is_bf16, else fp32).  C % 4 == 0. */
+WG_API int wg_resample_tokens(const void* tokens, int is_bf16, int n, int p, int C, int t, void* out, void* stream);
+
+/* F2b -- [SEG]-row extraction (model/walkgpt.py:287-306 mask, :406-420 gather and per-image offsets):
+ *   input_ids int64 [rows, Lin] (device); hidden [rows, L, H] bf16 or fp32 with L == Lin + shift (shift = 255: the image
+ *   token expands to 256 visual tokens).  Hidden position q of row r is selected iff q >= shift, i = q - shift + 1 < Lin and
+ *   input_ids[r][i] is one of the n_seg_ids (<= 8) token ids in the HOST array seg_ids.  Selected rows are copied to
+ *   out [max_out, H] in (row, position) order (rows past max_out are dropped; the caller compares row_offsets[rows] with
+ *   max_out); counts int32 [rows]; row_offsets int32 [rows+1] = exclusive scan; img_offsets[b] = row_offsets[img_rows[b]]
+ *   for the n_img_p1 entries of the image -> text-row map `offset` (img_rows may be NULL).  No host synchronisation. */
+WG_API int wg_seg_gather(const int64_t* input_ids, int rows, int Lin, const void* hidden, int hidden_is_bf16, int L, int H,
+                         const int64_t* seg_ids, int n_seg_ids, int shift, const int32_t* img_rows, int n_img_p1, void* out,
+                         int max_out, int32_t* counts, int32_t* row_offsets, int32_t* img_offsets, void* stream);
+
+/* F4 -- intersectionAndUnionGPU (utils/utils.py:192-204) for n_masks (output, target) pairs of `pixels` uint8 class ids:
+ *   output[target == ignore_index] = ignore_index; out fp32 [n_masks, 3, K] = per-class histograms (area_intersection,
+ *   area_union = area_output + area_target - area_intersection, area_target), exactly as torch.histc(bins=K, min=0, max=K-1)
+ *   returns them (values outside [0, K-1] are dropped).  1 <= K <= 8. */
+WG_API size_t wg_intersection_and_union_workspace_bytes(int n_masks, int K);
+WG_API int wg_intersection_and_union(const uint8_t* output, const uint8_t* target, int n_masks, int64_t pixels, int K,
+                                     int ignore_index, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -425,6 +425,41 @@ def intersection_and_union(output: torch.Tensor, target: torch.Tensor, K: int = 
     return ai, ao + at - ai, at
 
 
+
+# --------------------------------------------------------------------------------------------------
+# SURVEY section 8(f) "next" rows 2 and 4: the steps on either side of the grounding path.  These live inline in large
+# reference functions that cannot be imported under transformers 5.5, so they are restated from the cited
+# lines; tests/test_oracle_golden.py re-derives them a second time with independent torch code.
+# --------------------------------------------------------------------------------------------------
+def resample_visual_tokens(tokens: torch.Tensor, t: int = 16) -> torch.Tensor:
+    """model/llava_walkgpt/model/llava_arch.py:252-259: [n, p*p, c] -> [n, t*t, c], bilinear on the fp32 grid, cast back."""
+    n, l, c = tokens.shape
+    p = int(l ** 0.5)
+    assert p * p == l, f"Token count {l} is not square."
+    grid = tokens.permute(0, 2, 1).reshape(n, c, p, p).float()
+    grid = F.interpolate(grid, size=(t, t), mode="bilinear", align_corners=False)
+    return grid.flatten(2).permute(0, 2, 1).to(dtype=tokens.dtype)
+
+
+def seg_token_mask(input_ids: torch.Tensor, seg_token_idx, shift: int = 255) -> torch.Tensor:
+    """model/walkgpt.py:287-306: mask over the hidden-state positions [rows, Lin + shift]."""
+    ids = seg_token_idx if isinstance(seg_token_idx, (list, tuple)) else [seg_token_idx]
+    m = torch.zeros_like(input_ids[:, 1:]).bool()
+    for i in ids:
+        m = m | (input_ids[:, 1:] == i)
+    m = torch.cat([m, torch.zeros((m.shape[0], 1)).bool()], dim=1)
+    return torch.cat([torch.zeros((m.shape[0], shift)).bool(), m], dim=1)
+
+
+def gather_seg_rows(hidden: torch.Tensor, input_ids: torch.Tensor, seg_token_idx, offset: Sequence[int], shift: int = 255):
+    """model/walkgpt.py:406-420: hidden [rows, L, H] -> (pred_embeddings [sum S, H], counts [rows], per-image offsets [B+1])."""
+    mask = seg_token_mask(input_ids, seg_token_idx, shift)
+    pred = hidden[mask]
+    counts = mask.int().sum(-1)
+    off = torch.cat([torch.zeros(1).long(), counts.cumsum(-1)], dim=0)
+    return pred, counts, off[torch.as_tensor(list(offset), dtype=torch.long)]
+
+
 # --------------------------------------------------------------------------------------------------
 # A10 relative-depth head.  NOT IN THE REFERENCE (SURVEY §0, §8c): the reference emits depth as LLM text.
 # This is this repo's own extension, defined here so the CUDA tail has something to be checked against:

@@ -377,6 +377,62 @@ def test_full_batch_properties(path_model):
     assert torch.equal(out2["logits"][S:], logits[S:]) and not torch.equal(out2["logits"][:S], logits[:S])
 
 
+# ------------------------------------------------------------------------------------------------ SURVEY 8(f) "next" rows
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_visual_token_resample_is_bit_exact(dt):
+    """F2a (llava_arch.py:252-259): 36 MSQP tokens -> 16 x 16 grid.  bf16 tokens (what the path produces): bit-identical to
+    F.interpolate on the CPU; fp32 tokens: within 2 ulp (the four-tap sum is contracted into FMAs differently by nvcc and by
+    the CPU build of PyTorch)."""
+    def check(x, t):
+        got, ref = ops.resample_tokens(x.to(DEV), t).cpu(), path_a.resample_visual_tokens(x, t)
+        if dt == torch.bfloat16:
+            assert torch.equal(got, ref)
+        else:
+            assert (got - ref).abs().max().item() <= 2.5e-7 * ref.abs().max().item()
+    check(rnd((3, 36, 4096), 31).to(dt), 16)
+    check(rnd((1, 64, 40), 32).to(dt), 5)  # other grid sizes, down-sampling included
+    with pytest.raises(AssertionError, match="not square"):
+        ops.resample_tokens(torch.zeros(1, 35, 8, device=DEV), 16)
+
+
+@pytest.mark.parametrize("dt,ids", [(torch.bfloat16, 32003), (torch.float32, [32003, 32004])])
+def test_seg_row_extraction_is_bit_exact(dt, ids):
+    """F2b (model/walkgpt.py:287-306, 406-420): rows, counts and per-image offsets, including rows without any [SEG], a [SEG]
+    in the last position, one in position 0 (never counted) and a sequence longer than one scan chunk."""
+    g = torch.Generator().manual_seed(33)
+    rows, Lin, H, shift = 7, 300, 256, 255
+    inp = torch.randint(0, 32000, (rows, Lin), generator=g)
+    first = ids if isinstance(ids, int) else ids[0]
+    inp[0, [3, 17, Lin - 1]] = first
+    inp[1, 0] = first
+    inp[3, [1, 2, 290]] = first
+    if not isinstance(ids, int):
+        inp[5, [7, 260]] = ids[1]
+    hidden = torch.randn(rows, Lin + shift, H, generator=g).to(dt)
+    offset = [0, 2, 4, 7]
+    pred, counts, off = path_a.gather_seg_rows(hidden, inp, ids, offset, shift)
+    out, cnt, row_off, img_off = ops.seg_gather(hidden.to(DEV), inp.to(DEV), ids, offset, shift)
+    assert torch.equal(out.cpu(), pred) and cnt.cpu().tolist() == counts.tolist() and img_off.cpu().tolist() == off.tolist()
+    assert row_off.cpu().tolist() == [0] + counts.cumsum(0).tolist()
+    out2, _, row_off2, _ = ops.seg_gather(hidden.to(DEV), inp.to(DEV), ids, None, shift, max_out=4)  # capacity below the row count: truncated
+    assert out2.shape[0] == 4 and torch.equal(out2.cpu(), pred[:4]) and int(row_off2[-1]) == pred.shape[0]
+    with pytest.raises(_lib.WalkGPTB200Error, match="must equal input length"):
+        ops.seg_gather(hidden[:, :-1].contiguous().to(DEV), inp.to(DEV), ids, None, shift)
+
+
+def test_intersection_and_union_is_bit_exact():
+    """F4 (utils/utils.py:192-204): per-mask histograms equal the reference expression, ignore_index included; K = 2 and K = 5."""
+    g = torch.Generator().manual_seed(34)
+    for K, shape in ((2, (6, 448, 448)), (5, (3, 37, 51))):
+        out = torch.randint(0, K, shape, generator=g, dtype=torch.uint8)
+        tgt = torch.randint(0, K, shape, generator=g, dtype=torch.uint8)
+        tgt[torch.rand(shape, generator=g) < 0.1] = 255
+        got = ops.intersection_and_union(out.to(DEV), tgt.to(DEV), K, 255).cpu()
+        for i in range(shape[0]):
+            ai, au, at = path_a.intersection_and_union(out[i], tgt[i], K, 255)
+            assert torch.equal(got[i, 0], ai) and torch.equal(got[i, 1], au) and torch.equal(got[i, 2], at)
+
+
 def test_torch_custom_ops_call_the_c_abi():
     from walkgpt_b200 import torch_ops
 

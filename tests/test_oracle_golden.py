@@ -5,6 +5,7 @@ import os
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import path_a
 from walkgpt_b200 import specs
@@ -151,3 +152,31 @@ def test_depth_extension_is_self_consistent():
     up = rnd((4, 32, 64, 64), 2)
     d = path_a.depth_head(sd, low, up)
     assert d.shape == (4,) and d.min().item() == 0.0 and abs(d.max().item() - 1.0) < 1e-4
+
+
+def test_seg_row_extraction_restatement():
+    """oracle.gather_seg_rows (model/walkgpt.py:287-306, 406-420) against an independent loop over the token ids."""
+    g = torch.Generator().manual_seed(5)
+    rows, Lin, H, seg, shift = 5, 40, 16, 32003, 255
+    ids = torch.randint(0, 32000, (rows, Lin), generator=g)
+    ids[0, [3, 17, 39]] = seg      # the last position counts (it is input_ids[:, 1:][-1])
+    ids[1, 0] = seg                # position 0 never counts: the mask is built from input_ids[:, 1:]
+    ids[3, [1, 2]] = seg
+    hidden = torch.randn(rows, Lin + shift, H, generator=g)
+    pred, counts, off = path_a.gather_seg_rows(hidden, ids, seg, [0, 2, 5], shift)
+    want = [hidden[r, i - 1 + shift] for r in range(rows) for i in range(1, Lin) if ids[r, i] == seg]
+    assert counts.tolist() == [3, 0, 0, 2, 0] and off.tolist() == [0, 3, 5]
+    assert torch.equal(pred, torch.stack(want))
+    pred2, counts2, _ = path_a.gather_seg_rows(hidden, ids, [seg, int(ids[2, 5])], [0, 5], shift)
+    assert counts2[2] >= 1 and pred2.shape[0] == counts2.sum()
+
+
+def test_visual_token_resample_restatement():
+    """oracle.resample_visual_tokens (llava_arch.py:252-259): 36 -> 256 tokens, fp32 interpolation, cast back."""
+    x = rnd((2, 36, 64), 6).bfloat16()
+    y = path_a.resample_visual_tokens(x, 16)
+    assert y.shape == (2, 256, 64) and y.dtype == torch.bfloat16
+    grid = F.interpolate(x.float().transpose(1, 2).reshape(2, 64, 6, 6), (16, 16), mode="bilinear", align_corners=False)
+    assert torch.equal(y, grid.reshape(2, 64, 256).transpose(1, 2).bfloat16())
+    with pytest.raises(AssertionError, match="not square"):
+        path_a.resample_visual_tokens(torch.zeros(1, 35, 8))

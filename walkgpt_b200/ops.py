@@ -90,3 +90,65 @@ def attention_d64(qkv: torch.Tensor, heads: int, scale: float, key_valid: Option
     _lib.check(_lib.lib().wg_attention_d64(qkv.data_ptr(), out.data_ptr(), _ptr(key_valid), B, T, heads, scale, _stream()),
                "wg_attention_d64")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8(f) "next" rows
+def resample_tokens(tokens: torch.Tensor, t: int = 16) -> torch.Tensor:
+    """Visual-token resample handed to the LLM (llava_arch.py:252-259): [n, p*p, C] -> [n, t*t, C] (bf16 or fp32)."""
+    _need_cuda(tokens)
+    assert tokens.dim() == 3 and tokens.is_contiguous() and tokens.dtype in (torch.bfloat16, torch.float32)
+    n, l, c = tokens.shape
+    p = int(l ** 0.5)
+    if p * p != l:
+        raise AssertionError(f"Token count {l} is not square.")  # llava_arch.py:254
+    out = torch.empty(n, t * t, c, device=tokens.device, dtype=tokens.dtype)
+    _lib.check(_lib.lib().wg_resample_tokens(tokens.data_ptr(), int(tokens.dtype == torch.bfloat16), n, p, c, t, out.data_ptr(), _stream()),
+               "wg_resample_tokens")
+    return out
+
+
+def seg_gather(hidden: torch.Tensor, input_ids: torch.Tensor, seg_token_idx, offset=None, shift: int = 255, max_out: Optional[int] = None):
+    """[SEG]-row extraction (model/walkgpt.py:287-306, 406-420).  hidden [rows, Lin + shift, H]; input_ids int64 [rows, Lin].
+    Returns (rows_out [max_out, H], counts int32 [rows], row_offsets int32 [rows+1], img_offsets int32 [len(offset)] or None).
+    Without max_out the number of selected rows is read back from the device (one synchronisation, like the reference's
+    boolean-mask indexing) and rows_out is trimmed to it."""
+    _need_cuda(hidden, input_ids)
+    assert hidden.dim() == 3 and hidden.is_contiguous() and hidden.dtype in (torch.bfloat16, torch.float32)
+    assert input_ids.dim() == 2 and input_ids.dtype == torch.int64 and input_ids.is_contiguous()
+    rows, L, H = hidden.shape
+    Lin = input_ids.shape[1]
+    ids = list(seg_token_idx) if isinstance(seg_token_idx, (list, tuple)) else [int(seg_token_idx)]
+    seg_arr = (C.c_int64 * len(ids))(*ids)
+    dev = hidden.device
+    counts = torch.empty(rows, dtype=torch.int32, device=dev)
+    row_off = torch.empty(rows + 1, dtype=torch.int32, device=dev)
+    img_rows = img_off = None
+    if offset is not None:
+        img_rows = torch.as_tensor(list(offset), dtype=torch.int32).to(dev)
+        img_off = torch.empty(img_rows.numel(), dtype=torch.int32, device=dev)
+    cap = rows * (Lin - 1) if max_out is None else max_out
+    out = torch.empty(max(cap, 1), H, device=dev, dtype=hidden.dtype)
+    _lib.check(_lib.lib().wg_seg_gather(input_ids.data_ptr(), rows, Lin, hidden.data_ptr(), int(hidden.dtype == torch.bfloat16), L, H,
+                                        C.cast(seg_arr, C.c_void_p), len(ids), shift, _ptr(img_rows), 0 if img_rows is None else img_rows.numel(),
+                                        out.data_ptr(), cap, counts.data_ptr(), row_off.data_ptr(), _ptr(img_off), _stream()), "wg_seg_gather")
+    if max_out is None:
+        out = out[: int(row_off[-1].item())]
+    return out, counts, row_off, img_off
+
+
+def intersection_and_union(output: torch.Tensor, target: torch.Tensor, K: int = 2, ignore_index: int = 255) -> torch.Tensor:
+    """intersectionAndUnionGPU (utils/utils.py:192-204) for a batch of mask pairs: uint8 [n, ...] -> fp32 [n, 3, K]
+    (area_intersection, area_union, area_target per class)."""
+    _need_cuda(output, target)
+    assert output.shape == target.shape and output.dtype == torch.uint8 and target.dtype == torch.uint8
+    assert output.is_contiguous() and target.is_contiguous()
+    n = output.shape[0]
+    pixels = output[0].numel() if n else 0
+    out = torch.empty(n, 3, K, device=output.device, dtype=torch.float32)
+    if n == 0:
+        return out
+    need = _lib.lib().wg_intersection_and_union_workspace_bytes(n, K)
+    ws = torch.empty(need, dtype=torch.uint8, device=output.device)
+    _lib.check(_lib.lib().wg_intersection_and_union(output.data_ptr(), target.data_ptr(), n, pixels, K, ignore_index, out.data_ptr(), ws.data_ptr(), need,
+                                                    _stream()), "wg_intersection_and_union")
+    return out
