@@ -258,8 +258,10 @@ typedef struct wg_twoway_layer {
 } wg_twoway_layer;
 
 typedef struct wg_mask_decoder_weights {
-    int32_t grid_h, grid_w, n_mask_tokens, up_stages;   /* 32, 32, 4, 1 */
-    int32_t split_terms, reserved;                      /* T = 2 or 3 (see above) */
+    int32_t grid_h, grid_w, n_mask_tokens, up_stages;   /* 32, 32, 4, 1 (MaskDecoderMultiScale) ; 64, 64, 4, 2 (SAM MaskDecoder, Path B) */
+    int32_t split_terms;                                /* T = 2 or 3 (see above) */
+    int32_t multimask_first;                            /* first mask returned with multimask_output: 0 (multi-scale decoder,
+                                                           mask_decoder_multi_scale.py:126-132) or 1 (SAM, mask_decoder.py:106-111) */
     const float* out_tokens;     /* fp32 [1 + n_mask_tokens][256] = (iou_token ; mask_tokens) + level_embed[0] */
     const float* sparse_add;     /* fp32 [256] added to each text embedding (level_embed[0]); NULL = none */
     const float* no_mask;        /* fp32 [256] PromptEncoder.no_mask_embed (dense prompt embedding) */
@@ -269,9 +271,12 @@ typedef struct wg_mask_decoder_weights {
     const float* nf_g; const float* nf_b;           /* norm_final_attn */
     const void* w_img_fin;                          /* bf16 [256][T*256]: rows = final.k_proj | final.v_proj */
     const float* b_img_fin;                         /* fp32 [hw][256] = (pe Wk^T + bk | bv) */
-    const void* w_up;                               /* bf16 [4*32][T*256]: row (dy*2+dx)*32 + co = ConvT.weight[ci, co, dy, dx] */
-    const float* b_up;                              /* fp32 [128] = ConvT.bias tiled over the 4 sub-pixels */
-    const float* up_ln_g; const float* up_ln_b;     /* output_upscaling.1 (LayerNorm2d over 32 channels) */
+    const void* w_up;                               /* bf16 [4*Cu][T*256]: row (dy*2+dx)*Cu + co = ConvT.weight[ci, co, dy, dx]; Cu = 32
+                                                       (up_stages 1) or 64 (up_stages 2) */
+    const float* b_up;                              /* fp32 [4*Cu] = ConvT.bias tiled over the 4 sub-pixels */
+    const float* up_ln_g; const float* up_ln_b;     /* output_upscaling.1 (LayerNorm2d over Cu channels) */
+    const void* w_up2;                              /* up_stages 2: bf16 [4*32][T*64] second ConvTranspose (64 -> 32), same row order */
+    const float* b_up2;                             /* up_stages 2: fp32 [128] */
     const void* hyp_w0_t; const float* hyp_b0;      /* hypernetwork MLPs: fp32 [4][256][256], fp32 [4][256] */
     const void* hyp_w1_t; const float* hyp_b1;      /* [4][256][256] */
     const void* hyp_w2_t; const float* hyp_b2;      /* [4][256][32], fp32 [4][32] */
@@ -280,10 +285,12 @@ typedef struct wg_mask_decoder_weights {
     const void* iou_w2_t; const float* iou_b2;      /* [256][4] */
 } wg_mask_decoder_weights;
 
-WG_API size_t wg_mask_decoder_workspace_bytes(int P, int hw);
+WG_API size_t wg_mask_decoder_workspace_bytes(int P, int hw);                      /* up_stages = 1 */
+WG_API size_t wg_mask_decoder_workspace_bytes_ex(int P, int hw, int up_stages);
 /* img_emb_tokens split-bf16 [B, hw, 512] (channels-last image embeddings, hi | lo), txt_emb fp32 [P, 256] (CTP outputs = sparse prompt
  * embeddings), prompt_img int32 [P] (image index of each prompt; prompts of one image are contiguous).
- * low_res_out fp32 [P, n_out, 2*grid_h, 2*grid_w], iou_out fp32 [P, n_out]; n_out = 1 (multimask_output = 0) or 4.
+ * low_res_out fp32 [P, n_out, u*grid_h, u*grid_w] with u = 2^up_stages, iou_out fp32 [P, n_out]; n_out = 1 (multimask_output = 0)
+ * or n_mask_tokens - multimask_first (4 for the multi-scale decoder, 3 for the SAM decoder).
  * depth_pool_out (nullable) fp32 [P, 33]: sigmoid(logit)-weighted sums of the 32 upscaled channels + the weight sum
  * (input of this repo's relative-depth extension; not part of the reference). */
 WG_API int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, const float* txt_emb,

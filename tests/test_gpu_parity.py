@@ -224,6 +224,34 @@ def test_prompt_encoder_and_mask_decoder_against_reference_golden(grid):
         dec(emb, pe, sparse, dense, False, 1, previous_masks=m1)
 
 
+def test_sam_mask_decoder_against_reference_golden_and_oracle():
+    """Path B (released SAM-1024 wiring): the standard SAM MaskDecoder (mask_decoder.py:75-164), two ConvTranspose stages, masks 1..3
+    with multimask_output; golden fixture from the reference module at an 8 x 8 grid, oracle at the real 64 x 64 grid."""
+    g = load("decoder_sam_g8")
+    pe_m = load_into(M.PromptEncoder(256, (8, 8), (128, 128), 16), specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"]))
+    sdd = specs.make_state_dict(specs.mask_decoder_sam_spec(), seed=g["seed_dec"])
+    dec = load_into(M.MaskDecoder(), sdd)
+    pe = pe_m.get_dense_pe()
+    sparse, dense = pe_m(None, None, None, g["txt"].to(DEV))
+    m1, i1 = dec(g["emb"].to(DEV), pe, sparse, dense, False)
+    m3, i3 = dec(g["emb"].to(DEV), pe, sparse, dense, True)
+    assert m1.shape == g["masks1"].shape and m3.shape == g["masks3"].shape and m3.shape[1] == 3
+    assert rel_err(m1, g["masks1"]) < 1e-3 and rel_err(i1, g["iou1"]) < 1e-3
+    assert rel_err(m3, g["masks3"]) < 1e-3 and rel_err(i3, g["iou3"]) < 1e-3
+    # the real Path-B geometry: 64 x 64 embedding grid (1024-pixel SAM input), 3 prompts, masks at 256 x 256
+    pe64 = load_into(M.PromptEncoder(256, (64, 64), (1024, 1024), 16), specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"]))
+    emb = rnd((1, 256, 64, 64), 41)
+    txt = rnd((3, 1, 256), 42)
+    sp, de = pe64(None, None, None, txt.to(DEV))
+    got_m, got_i = dec(emb.to(DEV), pe64.get_dense_pe(), sp, de, False)
+    sdp = specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"])
+    pe_ref = path_a.dense_pe(sdp["pe_layer.positional_encoding_gaussian_matrix"], 64, 64)[None]
+    sp_ref, de_ref = path_a.prompt_encoder(sdp, txt, (64, 64))
+    ref_m, ref_i = path_a.mask_decoder_sam(sdd, emb, pe_ref, sp_ref, de_ref, multimask_output=False)
+    assert got_m.shape == (3, 1, 256, 256)
+    assert rel_err(got_m, ref_m) < 1e-3 and rel_err(got_i, ref_i) < 1e-3
+
+
 def test_postprocess_threshold_score_against_reference_golden():
     g = load("postprocess")
     for name, c in g["cases"].items():

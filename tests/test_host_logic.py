@@ -29,13 +29,15 @@ def test_reference_modules_load_our_state_dicts_strictly():
     import sys
     sys.path.insert(0, REF)
     from utils.utils_walkgpt import CalibratedTextProjector, MultiScaleQFormerProjector
-    from model.segment_anything.modeling import MaskDecoderMultiScale, PromptEncoder, TwoWayTransformer
+    from model.segment_anything.modeling import MaskDecoder, MaskDecoderMultiScale, PromptEncoder, TwoWayTransformer
 
     MultiScaleQFormerProjector(256, 64).load_state_dict(M.MultiScaleQFormerProjector(256, 64).state_dict(), strict=True)
     CalibratedTextProjector(512, 256).load_state_dict(M.CalibratedTextProjector(512, 256).state_dict(), strict=True)
     PromptEncoder(256, (32, 32), (448, 448), 16).load_state_dict(M.PromptEncoder(256, (32, 32), (448, 448), 16).state_dict(), strict=True)
     MaskDecoderMultiScale(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
                           transformer_dim=256, image_feature_scale_num=1).load_state_dict(M.MaskDecoderMultiScale().state_dict(), strict=True)
+    MaskDecoder(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                transformer_dim=256).load_state_dict(M.MaskDecoder().state_dict(), strict=True)  # Path B (released SAM-1024 wiring)
 
 
 def test_synthetic_init_is_deterministic_and_order_independent():

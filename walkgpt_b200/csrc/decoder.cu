@@ -524,12 +524,70 @@ __global__ void __launch_bounds__(256) upscale_mask_kernel(const float* __restri
     }
 }
 
+// ---- SAM head (Path B), stage 1: U1 fp32 [rows, 4 sub-pixels x 64] -> LayerNorm2d(64, eps 1e-6) -> GELU -> split-bf16
+// [rows * 4, hi 64 | lo 64]  (row index = position * 4 + sub-pixel)
+__global__ void __launch_bounds__(256) up1_ln_gelu_kernel(const float* __restrict__ U1, const float* __restrict__ g, const float* __restrict__ b,
+                                                          __nv_bfloat16* __restrict__ A2, long long rows4) {
+    const long long r4 = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (r4 >= rows4) return;
+    const float4* src = reinterpret_cast<const float4*>(U1 + r4 * 64);
+    float v[64];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float4 t = src[i];
+        v[i * 4] = t.x; v[i * 4 + 1] = t.y; v[i * 4 + 2] = t.z; v[i * 4 + 3] = t.w;
+        s += (t.x + t.y) + (t.z + t.w);
+    }
+    const float mean = s * (1.0f / 64);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) q = fmaf(v[i] - mean, v[i] - mean, q);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / 64) + 1e-6f);
+    __nv_bfloat16* dst = A2 + r4 * 128;
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = gelu_erf((v[c8 * 8 + e] - mean) * rstd * g[c8 * 8 + e] + b[c8 * 8 + e]);
+        split_store8(dst + c8 * 8, dst + 64 + c8 * 8, o);
+    }
+}
+// ---- SAM head, stage 2: U2 fp32 [rows4, 4 sub-pixels x 32] -> GELU -> hypernetwork dot -> masks [P, n_out, 4h, 4w]
+__global__ void __launch_bounds__(256) upscale_mask2_kernel(const float* __restrict__ U2, const float* __restrict__ hyper, int n_mask_tokens,
+                                                            int mask_start, int n_out, float* __restrict__ low_res, int hw, int gw, long long rows4) {
+    const long long r4 = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
+    const int sub2 = threadIdx.x & 3;
+    if (r4 >= rows4) return;
+    const long long row = r4 >> 2;
+    const int sub1 = (int)(r4 & 3);
+    const int p = (int)(row / hw), pos = (int)(row % hw);
+    const int y = pos / gw, x = pos % gw;
+    float v[32];
+    const float4* ur = reinterpret_cast<const float4*>(U2 + r4 * 128 + sub2 * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = ur[i];
+        v[i * 4] = gelu_erf(t.x); v[i * 4 + 1] = gelu_erf(t.y); v[i * 4 + 2] = gelu_erf(t.z); v[i * 4 + 3] = gelu_erf(t.w);
+    }
+    const int OW = 4 * gw;
+    const long long oy = 4 * y + 2 * (sub1 >> 1) + (sub2 >> 1), ox = 4 * x + 2 * (sub1 & 1) + (sub2 & 1);
+    const long long plane = (long long)16 * hw;
+    for (int m = 0; m < n_out; ++m) {
+        const float* hv = hyper + ((size_t)p * n_mask_tokens + mask_start + m) * 32;
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d = fmaf(hv[i], v[i], d);
+        low_res[((long long)p * n_out + m) * plane + oy * OW + ox] = d;
+    }
+}
+
 struct DecBuffers {
     __nv_bfloat16 *keysA, *keysB, *a2;   // split-bf16: [rows, 512], [rows, 512], [rows, 256]
     float *kvq, *U, *Tq, *Tpe, *KT, *VT, *hyper, *iou_all;
 };
 
-bool carve(Workspace& ws, int P, int hw, DecBuffers& d) {
+bool carve(Workspace& ws, int P, int hw, int up_stages, DecBuffers& d) {
     bool ok = true;
     auto take = [&](size_t bytes) {
         void* p = ws.take(bytes);
@@ -541,7 +599,7 @@ bool carve(Workspace& ws, int P, int hw, DecBuffers& d) {
     d.keysB = (__nv_bfloat16*)take(rows * 2 * C * 2);
     d.kvq = (float*)take(rows * 384 * 4);
     d.a2 = (__nv_bfloat16*)take(rows * 2 * CI * 2);
-    d.U = (float*)take(rows * 128 * 4);
+    d.U = (float*)take(rows * 128 * 4 * (up_stages == 2 ? 4 : 1));  // up_stages 2: second ConvT output [rows*4, 128]
     d.Tq = (float*)take((size_t)P * NT * C * 4);
     d.Tpe = (float*)take((size_t)P * NT * C * 4);
     d.KT = (float*)take((size_t)P * NT * CI * 4);
@@ -556,13 +614,14 @@ bool carve(Workspace& ws, int P, int hw, DecBuffers& d) {
 
 using namespace wg;
 
-extern "C" size_t wg_mask_decoder_workspace_bytes(int P, int hw) {
+extern "C" size_t wg_mask_decoder_workspace_bytes_ex(int P, int hw, int up_stages) {
     if (P <= 0 || hw <= 0) return 0;
     Workspace ws(nullptr, 0);
     DecBuffers d;
-    carve(ws, P, hw, d);
+    carve(ws, P, hw, up_stages, d);
     return ws.used();
 }
+extern "C" size_t wg_mask_decoder_workspace_bytes(int P, int hw) { return wg_mask_decoder_workspace_bytes_ex(P, hw, 1); }
 
 extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, const float* txt_emb,
                                        const int32_t* prompt_img, int P, int multimask_output, float* low_res_out, float* iou_out,
@@ -573,7 +632,9 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     WG_REQUIRE(img_emb_tokens_bf16 && txt_emb && prompt_img && low_res_out && iou_out && workspace, "wg_mask_decoder_forward: null pointer");
     WG_REQUIRE(P > 0, "wg_mask_decoder_forward: P=%d", P);
     WG_REQUIRE(w->split_terms == 2 || w->split_terms == 3, "wg_mask_decoder_forward: split_terms must be 2 or 3");
-    WG_REQUIRE(w->n_mask_tokens == 4 && w->up_stages == 1, "wg_mask_decoder_forward: only the multi-scale decoder head (4 mask tokens, one ConvTranspose) is built");
+    WG_REQUIRE(w->n_mask_tokens == 4 && (w->up_stages == 1 || w->up_stages == 2), "wg_mask_decoder_forward: 4 mask tokens and 1 or 2 ConvTranspose stages are built");
+    WG_REQUIRE(w->up_stages == 1 || (w->w_up2 && w->b_up2 && depth_pool_out == nullptr), "wg_mask_decoder_forward: the SAM head needs w_up2 / b_up2 and has no depth pooling");
+    WG_REQUIRE(w->multimask_first == 0 || w->multimask_first == 1, "wg_mask_decoder_forward: multimask_first must be 0 or 1");
     const int hw = w->grid_h * w->grid_w;
     WG_REQUIRE(hw > 0 && hw <= 4096, "wg_mask_decoder_forward: grid %dx%d unsupported", w->grid_h, w->grid_w);
     WG_REQUIRE(depth_pool_out == nullptr || hw % 64 == 0, "wg_mask_decoder_forward: depth pooling needs hw %% 64 == 0");
@@ -583,13 +644,15 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     }
     Workspace ws(workspace, workspace_bytes);
     DecBuffers d;
-    WG_REQUIRE(carve(ws, P, hw, d), "wg_mask_decoder_forward: workspace too small (%zu given, %zu needed)", workspace_bytes,
-               wg_mask_decoder_workspace_bytes(P, hw));
+    WG_REQUIRE(carve(ws, P, hw, w->up_stages, d), "wg_mask_decoder_forward: workspace too small (%zu given, %zu needed)", workspace_bytes,
+               wg_mask_decoder_workspace_bytes_ex(P, hw, w->up_stages));
     const long long rows = (long long)P * hw;
     WG_REQUIRE(rows < (1ll << 31), "wg_mask_decoder_forward: too many prompt tokens");
-    const int n_out = multimask_output ? w->n_mask_tokens : 1;
+    // MaskDecoderMultiScale keeps index 0 in both modes (mask_decoder_multi_scale.py:126-132); SAM returns masks 1.. with
+    // multimask_output and mask 0 without (mask_decoder.py:106-111)
+    const int mask_start = multimask_output ? w->multimask_first : 0;
+    const int n_out = multimask_output ? w->n_mask_tokens - mask_start : 1;
     const int T = w->split_terms;
-    const int mask_start = 0;  // MaskDecoderMultiScale keeps index 0 in both modes (mask_decoder_multi_scale.py:126-132)
 
     long long blocks = (rows * (C / 8) + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
@@ -672,21 +735,54 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
         decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
     }
     WG_CHECK_CUDA(cudaGetLastError());
-    // ConvTranspose2d(256 -> 32, k=2, s=2) as a GEMM over positions (N = 4 sub-pixels x 32 channels), fp32 out
-    {
-        wg_gemm_args a = {};
-        a.A = keys; a.lda = 2 * C; a.W = w->w_up; a.ldw = T * C; a.M = (int)rows; a.N = 128; a.K = T * C;
-        a.a_k_wrap = T == 3 ? 2 * C : 0;
-        a.bias = w->b_up; a.bias_period = 1; a.out_mode = WG_OUT_F32; a.out = d.U; a.ldo = 128;
-        WG_TRY(wg_gemm(&a, s));
+    if (w->up_stages == 1) {
+        // ConvTranspose2d(256 -> 32, k=2, s=2) as a GEMM over positions (N = 4 sub-pixels x 32 channels), fp32 out
+        {
+            wg_gemm_args a = {};
+            a.A = keys; a.lda = 2 * C; a.W = w->w_up; a.ldw = T * C; a.M = (int)rows; a.N = 128; a.K = T * C;
+            a.a_k_wrap = T == 3 ? 2 * C : 0;
+            a.bias = w->b_up; a.bias_period = 1; a.out_mode = WG_OUT_F32; a.out = d.U; a.ldo = 128;
+            WG_TRY(wg_gemm(&a, s));
+        }
+        if (depth_pool_out) WG_CHECK_CUDA(cudaMemsetAsync(depth_pool_out, 0, (size_t)P * 33 * sizeof(float), s));
+        {
+            Prof prof("dec_upscale_mask", s, (double)rows * 128 * 12.0, (double)rows * (512.0 + 16.0 * n_out));
+            upscale_mask_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, s>>>(d.U, w->up_ln_g, w->up_ln_b, d.hyper, w->n_mask_tokens, mask_start, n_out,
+                                                                          low_res_out, depth_pool_out, hw, w->grid_w, rows);
+        }
+        WG_CHECK_CUDA(cudaGetLastError());
+    } else {
+        // SAM head (mask_decoder.py:53-63): ConvT(256 -> 64) -> LayerNorm2d -> GELU -> ConvT(64 -> 32) -> GELU, both as GEMMs.
+        // The buffers of the finished transformer are reused: kvq holds the first ConvT output, keys_next its activations.
+        WG_REQUIRE(rows * 4 < (1ll << 31), "wg_mask_decoder_forward: too many up-sampled positions");
+        float* U1 = d.kvq;                 // fp32 [rows, 4 * 64]
+        __nv_bfloat16* A2 = keys_next;     // split-bf16 [rows * 4, 2 * 64]
+        {
+            wg_gemm_args a = {};
+            a.A = keys; a.lda = 2 * C; a.W = w->w_up; a.ldw = T * C; a.M = (int)rows; a.N = 256; a.K = T * C;
+            a.a_k_wrap = T == 3 ? 2 * C : 0;
+            a.bias = w->b_up; a.bias_period = 1; a.out_mode = WG_OUT_F32; a.out = U1; a.ldo = 256;
+            WG_TRY(wg_gemm(&a, s));
+        }
+        {
+            Prof prof("dec_up1_ln_gelu", s, 0.0, (double)rows * (1024.0 + 1024.0));
+            up1_ln_gelu_kernel<<<(unsigned)((rows * 4 + 255) / 256), 256, 0, s>>>(U1, w->up_ln_g, w->up_ln_b, A2, rows * 4);
+        }
+        WG_CHECK_CUDA(cudaGetLastError());
+        {
+            wg_gemm_args a = {};
+            a.A = A2; a.lda = 128; a.W = w->w_up2; a.ldw = T * 64; a.M = (int)(rows * 4); a.N = 128; a.K = T * 64;
+            a.a_k_wrap = T == 3 ? 128 : 0;
+            a.bias = w->b_up2; a.bias_period = 1; a.out_mode = WG_OUT_F32; a.out = d.U; a.ldo = 128;
+            WG_TRY(wg_gemm(&a, s));
+        }
+        {
+            Prof prof("dec_upscale_mask", s, (double)rows * 4 * 128 * 6.0, (double)rows * 4 * (512.0 + 16.0 * n_out));
+            upscale_mask2_kernel<<<(unsigned)((rows * 4 + 63) / 64), 256, 0, s>>>(d.U, d.hyper, w->n_mask_tokens, mask_start, n_out, low_res_out, hw,
+                                                                               w->grid_w, rows * 4);
+        }
+        WG_CHECK_CUDA(cudaGetLastError());
     }
-    if (depth_pool_out) WG_CHECK_CUDA(cudaMemsetAsync(depth_pool_out, 0, (size_t)P * 33 * sizeof(float), s));
-    {
-        Prof prof("dec_upscale_mask", s, (double)rows * 128 * 12.0, (double)rows * (512.0 + 16.0 * n_out));
-    upscale_mask_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, s>>>(d.U, w->up_ln_g, w->up_ln_b, d.hyper, w->n_mask_tokens, mask_start, n_out,
-                                                                  low_res_out, depth_pool_out, hw, w->grid_w, rows);
-    }
-    WG_CHECK_CUDA(cudaGetLastError());
     // iou predictions for the selected masks
     WG_CHECK_CUDA(cudaMemcpy2DAsync(iou_out, n_out * sizeof(float), d.iou_all + mask_start, w->n_mask_tokens * sizeof(float), n_out * sizeof(float), P,
                                     cudaMemcpyDeviceToDevice, s));

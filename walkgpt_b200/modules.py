@@ -667,14 +667,23 @@ class MaskDecoderMultiScale(_SpecModule):
         self._ws = _Workspace()
         self._pe_key = None
 
+    # hooks the SAM MaskDecoder subclass overrides
+    _T = "transformer.0."   # state_dict prefix of the two-way transformer
+    _UP_STAGES = 1          # ConvTranspose stages of output_upscaling
+    _MULTIMASK_FIRST = 0    # mask_decoder_multi_scale.py:126-132 keeps mask 0 in both modes
+
     def _pack_static(self):
         sd, hold = self._sd(), _Holder()
         w = _lib.MaskDecoderWeights()
-        w.n_mask_tokens, w.up_stages = self.num_mask_tokens, 1
-        lvl = sd["level_embed.weight"][0].float()
-        w.out_tokens = hold.f32(torch.cat([sd["iou_token.weight"], sd["mask_tokens.weight"]], 0).float() + lvl[None])
-        w.sparse_add = hold.f32(lvl)
-        T = "transformer.0."
+        w.n_mask_tokens, w.up_stages, w.multimask_first = self.num_mask_tokens, self._UP_STAGES, self._MULTIMASK_FIRST
+        out_tok = torch.cat([sd["iou_token.weight"], sd["mask_tokens.weight"]], 0).float()
+        if "level_embed.weight" in sd:
+            lvl = sd["level_embed.weight"][0].float()
+            w.out_tokens = hold.f32(out_tok + lvl[None])
+            w.sparse_add = hold.f32(lvl)
+        else:
+            w.out_tokens = hold.f32(out_tok)
+        T = self._T
 
         def lin_t(name):  # transposed fp32 weight + fp32 bias (token side, CUDA cores)
             return hold.f32(sd[name + ".weight"].t()), hold.f32(sd[name + ".bias"])
@@ -683,6 +692,8 @@ class MaskDecoderMultiScale(_SpecModule):
                  ("cross_attn_token_to_image.k_proj", "cross_attn_token_to_image.v_proj", "cross_attn_image_to_token.q_proj",
                   "cross_attn_image_to_token.out_proj")]
         img_w += [sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.v_proj.weight"], sd["output_upscaling.0.weight"]]
+        if self._UP_STAGES == 2:
+            img_w.append(sd["output_upscaling.3.weight"])
         terms = split_terms_needed(img_w)
         w.split_terms = terms
 
@@ -713,6 +724,9 @@ class MaskDecoderMultiScale(_SpecModule):
         w_up, b_up = pack_conv_transpose2x2(sd["output_upscaling.0.weight"], sd["output_upscaling.0.bias"])
         w.w_up, w.b_up = hold(split_weight(w_up, terms)), hold.f32(b_up)
         w.up_ln_g, w.up_ln_b = hold.f32(sd["output_upscaling.1.weight"]), hold.f32(sd["output_upscaling.1.bias"])
+        if self._UP_STAGES == 2:
+            w_up2, b_up2 = pack_conv_transpose2x2(sd["output_upscaling.3.weight"], sd["output_upscaling.3.bias"])
+            w.w_up2, w.b_up2 = hold(split_weight(w_up2, terms)), hold.f32(b_up2)
         for j, (wn, bn) in enumerate((("hyp_w0_t", "hyp_b0"), ("hyp_w1_t", "hyp_b1"), ("hyp_w2_t", "hyp_b2"))):
             ws_ = torch.stack([sd[f"output_hypernetworks_mlps.{i}.layers.{j}.weight"].t() for i in range(self.num_mask_tokens)], 0)
             bs_ = torch.stack([sd[f"output_hypernetworks_mlps.{i}.layers.{j}.bias"] for i in range(self.num_mask_tokens)], 0)
@@ -737,7 +751,7 @@ class MaskDecoderMultiScale(_SpecModule):
         sd = self._sd()
         pe32 = pe_tokens.float()
         hw = pe_tokens.shape[0]
-        T = "transformer.0."
+        T = self._T
         self._pe_keep = []
 
         def table(wk, bk, bv, wq=None, bq=None):
@@ -768,14 +782,15 @@ class MaskDecoderMultiScale(_SpecModule):
         w, _ = self._packed
         P = txt_emb_f32.shape[0]
         hw = w.grid_h * w.grid_w
-        n_out = self.num_mask_tokens if multimask_output else 1
+        n_out = self.num_mask_tokens - self._MULTIMASK_FIRST if multimask_output else 1
         dev = emb_tokens_bf16.device
-        low = torch.empty(P, n_out, 2 * w.grid_h, 2 * w.grid_w, device=dev, dtype=torch.float32)
+        up = 2 ** self._UP_STAGES
+        low = torch.empty(P, n_out, up * w.grid_h, up * w.grid_w, device=dev, dtype=torch.float32)
         iou = torch.empty(P, n_out, device=dev, dtype=torch.float32)
         pool = torch.empty(P, 33, device=dev, dtype=torch.float32) if want_depth_pool else None
         if P == 0:
             return low, iou, pool
-        ws = self._ws.get(_lib.lib().wg_mask_decoder_workspace_bytes(P, hw), dev)
+        ws = self._ws.get(_lib.lib().wg_mask_decoder_workspace_bytes_ex(P, hw, self._UP_STAGES), dev)
         _lib.check(_lib.lib().wg_mask_decoder_forward(C.byref(w), emb_tokens_bf16.data_ptr(), txt_emb_f32.data_ptr(), prompt_img_i32.data_ptr(), P,
                                                       int(multimask_output), low.data_ptr(), iou.data_ptr(), None if pool is None else pool.data_ptr(),
                                                       ws.data_ptr(), ws.numel(), _stream()), "wg_mask_decoder_forward")
@@ -806,6 +821,33 @@ class MaskDecoderMultiScale(_SpecModule):
             pimg = torch.zeros(S, dtype=torch.int32, device=image_embeddings.device)
             low, iou, _ = self.run(emb_tok, txt, pimg, multimask_output)
         return low.to(dt), iou.to(dt)
+
+
+class MaskDecoder(MaskDecoderMultiScale):
+    """Drop-in for the standard SAM ``MaskDecoder`` (segment_anything/modeling/mask_decoder.py:16-164) -- the decoder of the
+    released "SAM-1024" wiring (Path B): no level embedding, two ConvTranspose stages (256 -> 64 -> 32, masks
+    at 4x the embedding grid), ``multimask_output`` returns masks 1..3.  Same CUDA kernels as the multi-scale decoder."""
+
+    _T = "transformer."
+    _UP_STAGES = 2
+    _MULTIMASK_FIRST = 1  # mask_decoder.py:106-111
+
+    def __init__(self, *, transformer_dim: int = 256, transformer=None, num_multimask_outputs: int = 3, activation=None,
+                 iou_head_depth: int = 3, iou_head_hidden_dim: int = 256, seed=0):
+        _SpecModule.__init__(self)
+        if transformer_dim != 256 or num_multimask_outputs != 3 or iou_head_depth != 3 or iou_head_hidden_dim != 256:
+            raise ValueError("MaskDecoder: the CUDA path is built for the reference's dimensions (256 / 3 / 3 / 256)")
+        self.transformer_dim = transformer_dim
+        self.num_multimask_outputs = num_multimask_outputs
+        self.num_mask_tokens = num_multimask_outputs + 1
+        self._build(specs.mask_decoder_sam_spec(transformer_dim, num_multimask_outputs), seed)
+        self._ws = _Workspace()
+        self._pe_key = None
+
+    @torch.no_grad()
+    def forward(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, multimask_output: bool):
+        """Reference signature (mask_decoder.py:75-114)."""
+        return MaskDecoderMultiScale.forward(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, multimask_output, 0, None)
 
 
 # --------------------------------------------------------------------------------------------------
