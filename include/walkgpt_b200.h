@@ -297,6 +297,22 @@ WG_API int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const void*
                                    const int32_t* prompt_img, int P, int multimask_output, float* low_res_out, float* iou_out,
                                    float* depth_pool_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Level > 0 of MaskDecoderMultiScale (image_feature_scale_num = 2; mask_decoder_multi_scale.py:165-171).
+ * wg_upsample2x_embedding: upsample_2x = ConvTranspose2d(256 -> 256, k2, s2) + LayerNorm2d + GELU on the image embeddings,
+ *   split-bf16 [B, h*w, 512] -> split-bf16 [B, 4*h*w, 512] (raster order of the 2h x 2w grid); w_up bf16 [4*256][T*256] in the
+ *   (dy, dx, co) row order of the other ConvTranspose weights, b_up fp32 [1024] tiled, ln_g / ln_b fp32 [256].
+ * wg_mask_decoder_forward_level: wg_mask_decoder_forward whose keys are gated by the previous level's masks,
+ *   keys0 = (sigmoid(mean_m prev_masks[p, m]) + 1) * embedding + no_mask;  prev_masks fp32 [P, n_prev, grid_h, grid_w] or NULL.
+ *   `w` then carries the level's own transformer, out_tokens / sparse_add with level_embed[level] and bias tables from pe1. */
+WG_API size_t wg_upsample2x_workspace_bytes(int B, int hw);
+WG_API int wg_upsample2x_embedding(const void* w_up, int split_terms, const float* b_up, const float* ln_g, const float* ln_b,
+                                   const void* emb_tokens_bf16, int B, int grid_h, int grid_w, void* out_tokens_bf16,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+WG_API int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, const float* txt_emb,
+                                         const int32_t* prompt_img, int P, int multimask_output, const float* prev_masks, int n_prev,
+                                         float* low_res_out, float* iou_out, float* depth_pool_out, void* workspace,
+                                         size_t workspace_bytes, void* stream);
+
 /* A6 -- PromptEncoder.get_dense_pe / PositionEmbeddingRandom.forward (prompt_encoder.py:67-76, 216-229).
  * gauss fp32 [2, F]; out_chw fp32 [2F, h, w] (reference layout, nullable); out_tokens fp32 [h*w, 2F] (nullable). */
 WG_API int wg_dense_pe(const float* gauss, int num_pos_feats, int h, int w, float* out_chw, float* out_tokens, void* stream);

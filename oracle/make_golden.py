@@ -174,5 +174,36 @@ def main():
         print("intersectionAndUnionGPU not importable here:", repr(e))
 
 
+@torch.no_grad()
+def make_decoder_two_level():
+    """MaskDecoderMultiScale with image_feature_scale_num = 2 -- level 0, then level 1 fed with the level-0
+    masks (mask_decoder_multi_scale.py:165-171: upsample_2x, previous-mask gating, pe1, transformer[1], level_embed[1]).
+    Writes tests/golden/decoder_ms2_g8.pt only:  python -m oracle.make_golden two_level"""
+    from model.segment_anything.modeling import MaskDecoderMultiScale, PromptEncoder, TwoWayTransformer
+
+    g = 8
+    pe_mod = PromptEncoder(embed_dim=256, image_embedding_size=(g, g), input_image_size=(g * 14, g * 14), mask_in_chans=16).eval()
+    pe_mod.load_state_dict(specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=14), strict=True)
+    dec = MaskDecoderMultiScale(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                                transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256, image_feature_scale_num=2).eval()
+    dec.load_state_dict(specs.make_state_dict(specs.mask_decoder_multiscale_spec(scale_num=2), seed=17), strict=True)
+    emb = rnd((1, 256, g, g), 421)
+    txt = rnd((3, 1, 256), 422, 0.5)
+    sparse, dense = pe_mod(points=None, boxes=None, masks=None, text_embeds=txt)
+    pe = pe_mod.get_dense_pe()
+    m0, i0 = dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=True,
+                 level_num=0)
+    m1, i1 = dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=True,
+                 level_num=1, previous_masks=m0)
+    m1s, i1s = dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=False,
+                   level_num=1, previous_masks=m0)
+    save("decoder_ms2_g8", {"seed_prompt": 14, "seed_dec": 17, "grid": g, "emb": emb, "txt": txt, "masks_l0": m0, "iou_l0": i0,
+                            "masks_l1": m1, "iou_l1": i1, "masks_l1_single": m1s, "iou_l1_single": i1s})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "two_level":
+        make_decoder_two_level()
+    else:
+        main()
+        make_decoder_two_level()

@@ -220,8 +220,31 @@ def test_prompt_encoder_and_mask_decoder_against_reference_golden(grid):
     assert rel_err(m1, g["masks1"]) < 1e-3 and rel_err(i1, g["iou1"]) < 1e-3
     assert rel_err(m4, g["masks4"]) < 1e-3 and rel_err(i4, g["iou4"]) < 1e-3
     assert (m1.cpu() - g["masks1"]).abs().max().item() <= LOGIT_TOL / 4
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):  # level 1 needs image_feature_scale_num = 2
         dec(emb, pe, sparse, dense, False, 1, previous_masks=m1)
+
+
+def test_mask_decoder_two_levels_against_reference_golden():
+    """MaskDecoderMultiScale(image_feature_scale_num=2), level 0 then level 1 fed with the level-0 masks
+    (mask_decoder_multi_scale.py:165-171), against the fixture produced by the reference module."""
+    g = load("decoder_ms2_g8")
+    pe_m = load_into(M.PromptEncoder(256, (8, 8), (112, 112), 16), specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"]))
+    dec = load_into(M.MaskDecoderMultiScale(image_feature_scale_num=2), specs.make_state_dict(specs.mask_decoder_multiscale_spec(scale_num=2), seed=g["seed_dec"]))
+    pe = pe_m.get_dense_pe()
+    sparse, dense = pe_m(None, None, None, g["txt"].to(DEV))
+    emb = g["emb"].to(DEV)
+    m0, i0 = dec(emb, pe, sparse, dense, True, 0)
+    assert rel_err(m0, g["masks_l0"]) < 1e-3 and rel_err(i0, g["iou_l0"]) < 1e-3
+    m1, i1 = dec(emb, pe, sparse, dense, True, 1, previous_masks=g["masks_l0"].to(DEV))
+    assert m1.shape == g["masks_l1"].shape == (3, 4, 32, 32)
+    assert rel_err(m1, g["masks_l1"]) < 1e-3 and rel_err(i1, g["iou_l1"]) < 1e-3
+    m1s, i1s = dec(emb, pe, sparse, dense, False, 1, previous_masks=g["masks_l0"].to(DEV))
+    assert rel_err(m1s, g["masks_l1_single"]) < 1e-3 and rel_err(i1s, g["iou_l1_single"]) < 1e-3
+    # chained on the device: level 1 on this path's own level-0 masks
+    m1c, _ = dec(emb, pe, sparse, dense, True, 1, previous_masks=m0)
+    assert rel_err(m1c, g["masks_l1"]) < 2e-3
+    with pytest.raises(NotImplementedError):
+        dec(emb, pe, sparse, dense, True, 1)  # previous_masks missing
 
 
 def test_sam_mask_decoder_against_reference_golden_and_oracle():

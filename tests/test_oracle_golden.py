@@ -88,6 +88,24 @@ def test_decoder_multiscale(grid):
     close(i4, g["iou4"], 2e-4)
 
 
+def test_decoder_multiscale_two_levels():
+    """level 1 of MaskDecoderMultiScale (upsample_2x, previous-mask gating, pe1, transformer[1]) against the
+    fixture produced by the reference module with image_feature_scale_num=2."""
+    g = load("decoder_ms2_g8")
+    sdp = specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"])
+    sdd = specs.make_state_dict(specs.mask_decoder_multiscale_spec(scale_num=2), seed=g["seed_dec"])
+    pe = path_a.dense_pe(sdp["pe_layer.positional_encoding_gaussian_matrix"], 8, 8)[None]
+    sparse, dense = path_a.prompt_encoder(sdp, g["txt"], (8, 8))
+    m0, i0 = path_a.mask_decoder_multiscale(sdd, g["emb"], pe, sparse, dense, multimask_output=True, level_num=0)
+    close(m0, g["masks_l0"], 2e-4)
+    m1, i1 = path_a.mask_decoder_multiscale(sdd, g["emb"], pe, sparse, dense, multimask_output=True, level_num=1, previous_masks=g["masks_l0"])
+    assert m1.shape == (3, 4, 32, 32)
+    close(m1, g["masks_l1"], 2e-4)
+    close(i1, g["iou_l1"], 2e-4)
+    m1s, _ = path_a.mask_decoder_multiscale(sdd, g["emb"], pe, sparse, dense, multimask_output=False, level_num=1, previous_masks=g["masks_l0"])
+    close(m1s, g["masks_l1_single"], 2e-4)
+
+
 def test_decoder_sam():
     g = load("decoder_sam_g8")
     sdp = specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"])

@@ -366,9 +366,11 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]
     }
 }
 
-// keys0[p, pos, :] = img_emb[img(p), pos, :] + no_mask_embed      (split-bf16 in [B*hw, 512], split-bf16 out [P*hw, 512])
+// keys0[p, pos, :] = gate[p, pos] * img_emb[img(p), pos, :] + no_mask_embed      (split-bf16 in [B*hw, 512], split-bf16 out [P*hw, 512])
+// gate = 1, or sigmoid(mean_m previous_masks[p, m, pos]) + 1 at level > 0 (mask_decoder_multi_scale.py:168-169)
 __global__ void __launch_bounds__(256) expand_keys_kernel(const __nv_bfloat16* __restrict__ emb, const int* __restrict__ prompt_img,
-                                                          const float* __restrict__ no_mask, __nv_bfloat16* __restrict__ keys, int P, int hw) {
+                                                          const float* __restrict__ no_mask, __nv_bfloat16* __restrict__ keys, int P, int hw,
+                                                          const float* __restrict__ prev_masks, int n_prev) {
     const long long total = (long long)P * hw * (C / 8);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c8 = (int)(i % (C / 8));
@@ -376,13 +378,51 @@ __global__ void __launch_bounds__(256) expand_keys_kernel(const __nv_bfloat16* _
         const int p = (int)(row / hw), pos = (int)(row % hw);
         const int img = prompt_img[p];
         const __nv_bfloat16* src = emb + ((size_t)img * hw + pos) * (2 * C) + c8 * 8;
+        float gate = 1.0f;
+        if (prev_masks != nullptr) {
+            float m = 0.f;
+            for (int k = 0; k < n_prev; ++k) m += prev_masks[((size_t)p * n_prev + k) * hw + pos];
+            m /= (float)n_prev;
+            gate = 1.0f / (1.0f + expf(-m)) + 1.0f;
+        }
         float hi[8], lo[8], v[8];
         load8_bf16(src, hi);
         load8_bf16(src + C, lo);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = hi[e] + lo[e] + no_mask[c8 * 8 + e];
+        for (int e = 0; e < 8; ++e) v[e] = gate * (hi[e] + lo[e]) + no_mask[c8 * 8 + e];
         split_store8(keys + row * (2 * C) + c8 * 8, keys + row * (2 * C) + C + c8 * 8, v);
     }
+}
+
+// level > 0 of the multi-scale decoder: upsample_2x = ConvTranspose2d(256 -> 256, k2, s2) (a GEMM) -> LayerNorm2d(256, eps 1e-6)
+// -> GELU on the image embedding.  U fp32 [B*hw, 4 sub-pixels x 256] -> split-bf16 [B, 4*hw raster positions of the 2h x 2w grid, 512].
+// One warp per (position, sub-pixel); lane owns 8 channels.
+__global__ void __launch_bounds__(256) up2x_ln_gelu_kernel(const float* __restrict__ U, const float* __restrict__ g, const float* __restrict__ b,
+                                                           __nv_bfloat16* __restrict__ out, long long rows, int hw, int gw) {
+    const long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);  // (row, sub)
+    const int lane = threadIdx.x & 31;
+    if (item >= rows * 4) return;
+    const long long row = item >> 2;
+    const int sub = (int)(item & 3);
+    const float4* src = reinterpret_cast<const float4*>(U + row * 1024 + sub * 256 + lane * 8);
+    const float4 a0 = src[0], a1 = src[1];
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float s1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1 += v[e];
+    const float mean = warp_sum(s1) * (1.0f / 256);
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q = fmaf(v[e] - mean, v[e] - mean, q);
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 256) + 1e-6f);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = gelu_erf((v[e] - mean) * rstd * g[lane * 8 + e] + b[lane * 8 + e]);
+    const long long img = row / hw;
+    const int pos = (int)(row % hw), y = pos / gw, x = pos % gw;
+    const long long opos = (long long)(2 * y + (sub >> 1)) * (2 * gw) + (2 * x + (sub & 1));
+    __nv_bfloat16* dst = out + (img * 4 * hw + opos) * (2 * C) + lane * 8;
+    split_store8(dst, dst + C, o);
 }
 
 // image -> token attention, one thread per image position (6 keys, 8 heads x 16): q fp32 in, out split-bf16 [P*hw][2*128]
@@ -626,7 +666,50 @@ extern "C" size_t wg_mask_decoder_workspace_bytes(int P, int hw) { return wg_mas
 extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, const float* txt_emb,
                                        const int32_t* prompt_img, int P, int multimask_output, float* low_res_out, float* iou_out,
                                        float* depth_pool_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    return wg_mask_decoder_forward_level(w, img_emb_tokens_bf16, txt_emb, prompt_img, P, multimask_output, nullptr, 0, low_res_out, iou_out,
+                                         depth_pool_out, workspace, workspace_bytes, stream_);
+}
+
+extern "C" size_t wg_upsample2x_workspace_bytes(int B, int hw) { return (B > 0 && hw > 0) ? (size_t)B * hw * 1024 * sizeof(float) : 0; }
+
+extern "C" int wg_upsample2x_embedding(const void* w_up, int split_terms, const float* b_up, const float* ln_g, const float* ln_b,
+                                       const void* emb_tokens_bf16, int B, int grid_h, int grid_w, void* out_tokens_bf16, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    if (B == 0) return WG_OK;
+    WG_REQUIRE(w_up && b_up && ln_g && ln_b && emb_tokens_bf16 && out_tokens_bf16 && workspace, "wg_upsample2x_embedding: null pointer");
+    WG_REQUIRE(B > 0 && grid_h > 0 && grid_w > 0 && (split_terms == 2 || split_terms == 3), "wg_upsample2x_embedding: bad arguments");
+    const int hw = grid_h * grid_w;
+    const long long rows = (long long)B * hw;
+    WG_REQUIRE(rows * 4 < (1ll << 31), "wg_upsample2x_embedding: too many positions");
+    WG_REQUIRE(workspace_bytes >= wg_upsample2x_workspace_bytes(B, hw), "wg_upsample2x_embedding: workspace too small");
+    if (!device_is_sm100()) {
+        set_error("wg_upsample2x_embedding: this library only runs on sm_100 (B200) devices; there is no fallback");
+        return WG_ERR_UNSUPPORTED;
+    }
+    float* U = static_cast<float*>(workspace);
+    const int T = split_terms;
+    {
+        wg_gemm_args a = {};
+        a.A = emb_tokens_bf16; a.lda = 2 * C; a.W = w_up; a.ldw = T * C; a.M = (int)rows; a.N = 4 * C; a.K = T * C;
+        a.a_k_wrap = T == 3 ? 2 * C : 0;
+        a.bias = b_up; a.bias_period = 1; a.out_mode = WG_OUT_F32; a.out = U; a.ldo = 4 * C;
+        WG_TRY(wg_gemm(&a, s));
+    }
+    {
+        Prof prof("dec_up2x_ln_gelu", s, 0.0, (double)rows * (4096.0 + 4096.0));
+        up2x_ln_gelu_kernel<<<(unsigned)((rows * 4 + 7) / 8), 256, 0, s>>>(U, ln_g, ln_b, static_cast<__nv_bfloat16*>(out_tokens_bf16), rows, hw, grid_w);
+    }
+    WG_CHECK_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, const float* txt_emb,
+                                             const int32_t* prompt_img, int P, int multimask_output, const float* prev_masks, int n_prev,
+                                             float* low_res_out, float* iou_out, float* depth_pool_out, void* workspace, size_t workspace_bytes,
+                                             void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    WG_REQUIRE(prev_masks == nullptr || n_prev > 0, "wg_mask_decoder_forward_level: previous masks need n_prev > 0");
     WG_REQUIRE(w != nullptr, "wg_mask_decoder_forward: null weights");
     if (P == 0) return WG_OK;
     WG_REQUIRE(img_emb_tokens_bf16 && txt_emb && prompt_img && low_res_out && iou_out && workspace, "wg_mask_decoder_forward: null pointer");
@@ -658,7 +741,8 @@ extern "C" int wg_mask_decoder_forward(const wg_mask_decoder_weights* w, const v
     if (blocks > 148 * 32) blocks = 148 * 32;
     {
         Prof prof("dec_expand_keys", s, 0.0, (double)rows * C * 8.0);
-    expand_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(img_emb_tokens_bf16), prompt_img, w->no_mask, d.keysA, P, hw);
+    expand_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(img_emb_tokens_bf16), prompt_img, w->no_mask, d.keysA, P, hw,
+                                                        prev_masks, n_prev);
     }
     WG_CHECK_CUDA(cudaGetLastError());
 

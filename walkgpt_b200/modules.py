@@ -665,25 +665,30 @@ class MaskDecoderMultiScale(_SpecModule):
         self.image_feature_scale_num = image_feature_scale_num
         self._build(specs.mask_decoder_multiscale_spec(transformer_dim, num_multimask_outputs, image_feature_scale_num), seed)
         self._ws = _Workspace()
+        self._ws_up = _Workspace()
         self._pe_key = None
+        self._levels = {}
 
     # hooks the SAM MaskDecoder subclass overrides
     _T = "transformer.0."   # state_dict prefix of the two-way transformer
     _UP_STAGES = 1          # ConvTranspose stages of output_upscaling
     _MULTIMASK_FIRST = 0    # mask_decoder_multi_scale.py:126-132 keeps mask 0 in both modes
 
-    def _pack_static(self):
+    def _prefix(self, level: int) -> str:
+        return self._T.replace("0", str(level)) if "0" in self._T else self._T
+
+    def _pack_static(self, level: int = 0):
         sd, hold = self._sd(), _Holder()
         w = _lib.MaskDecoderWeights()
         w.n_mask_tokens, w.up_stages, w.multimask_first = self.num_mask_tokens, self._UP_STAGES, self._MULTIMASK_FIRST
         out_tok = torch.cat([sd["iou_token.weight"], sd["mask_tokens.weight"]], 0).float()
         if "level_embed.weight" in sd:
-            lvl = sd["level_embed.weight"][0].float()
+            lvl = sd["level_embed.weight"][level].float()
             w.out_tokens = hold.f32(out_tok + lvl[None])
             w.sparse_add = hold.f32(lvl)
         else:
             w.out_tokens = hold.f32(out_tok)
-        T = self._T
+        T = self._prefix(level)
 
         def lin_t(name):  # transposed fp32 weight + fp32 bias (token side, CUDA cores)
             return hold.f32(sd[name + ".weight"].t()), hold.f32(sd[name + ".bias"])
@@ -735,31 +740,50 @@ class MaskDecoderMultiScale(_SpecModule):
         for j, (wn, bn) in enumerate((("iou_w0_t", "iou_b0"), ("iou_w1_t", "iou_b1"), ("iou_w2_t", "iou_b2"))):
             setattr(w, wn, hold.f32(sd[f"iou_prediction_head.layers.{j}.weight"].t()))
             setattr(w, bn, hold.f32(sd[f"iou_prediction_head.layers.{j}.bias"]))
-        self._packed = (w, hold)
-        self._pe_key = None
-        return self._packed
+        if level == 0:
+            self._packed = (w, hold)
+            self._pe_key = None
+            self._levels = {}
+            return self._packed
+        if "upsample_2x.0.weight" in sd:  # level > 0: the embedding up-sampler in front of the level's transformer
+            w_u, b_u = pack_conv_transpose2x2(sd["upsample_2x.0.weight"], sd["upsample_2x.0.bias"])
+            up_terms = split_terms_needed([sd["upsample_2x.0.weight"]])
+            hold.up2x = (hold(split_weight(w_u, up_terms)), up_terms, hold.f32(b_u), hold.f32(sd["upsample_2x.1.weight"]), hold.f32(sd["upsample_2x.1.bias"]))
+        self._levels[level] = {"packed": (w, hold), "pe_key": None, "pe_keep": []}
+        return w, hold
 
-    _pack = _pack_static
+    def _pack(self):
+        return self._pack_static(0)
 
-    def bind_prompt_constants(self, pe_tokens: torch.Tensor, no_mask: torch.Tensor, grid: Tuple[int, int]) -> None:
+    def bind_prompt_constants(self, pe_tokens: torch.Tensor, no_mask: torch.Tensor, grid: Tuple[int, int], level: int = 0) -> None:
         """Fold the dense positional encoding into per-position bias tables (pe W^T + b; one-time fp32 constant folding, like
         the LayerNorm-affine folding in MSQP) and record the dense (no-mask) prompt embedding.  Cached until inputs/weights change."""
-        w, hold = self._packed or self._pack()
+        if level == 0:
+            w, hold = self._packed or self._pack()
+        else:
+            self._packed or self._pack()
+            if level not in self._levels:
+                self._pack_static(level)
+            w, hold = self._levels[level]["packed"]
         key = (pe_tokens.data_ptr(), pe_tokens._version, no_mask.data_ptr(), no_mask._version, tuple(grid))
-        if self._pe_key == key:
+        if (self._pe_key if level == 0 else self._levels[level]["pe_key"]) == key:
             return
         sd = self._sd()
         pe32 = pe_tokens.float()
         hw = pe_tokens.shape[0]
-        T = self._T
-        self._pe_keep = []
+        T = self._prefix(level)
+        if level == 0:
+            self._pe_keep = []
+            keep = self._pe_keep
+        else:
+            keep = self._levels[level]["pe_keep"] = []
 
         def table(wk, bk, bv, wq=None, bq=None):
             parts = [pe32 @ wk.float().t() + bk.float(), bv.float()[None].expand(hw, -1)]
             if wq is not None:
                 parts.append(pe32 @ wq.float().t() + bq.float())
             t = torch.cat(parts, dim=1).contiguous()
-            self._pe_keep.append(t)
+            keep.append(t)
             return t.data_ptr()
 
         for l in range(2):
@@ -770,16 +794,20 @@ class MaskDecoderMultiScale(_SpecModule):
         w.b_img_fin = table(sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.k_proj.bias"],
                             sd[T + "final_attn_token_to_image.v_proj.bias"])
         nm = _f32(no_mask.reshape(-1))
-        self._pe_keep.append(nm)
+        keep.append(nm)
         w.no_mask = nm.data_ptr()
         w.grid_h, w.grid_w = grid
-        self._pe_key = key
+        if level == 0:
+            self._pe_key = key
+        else:
+            self._levels[level]["pe_key"] = key
 
     def run(self, emb_tokens_bf16: torch.Tensor, txt_emb_f32: torch.Tensor, prompt_img_i32: torch.Tensor, multimask_output: bool = False,
-            want_depth_pool: bool = False):
+            want_depth_pool: bool = False, level: int = 0, prev_masks: Optional[torch.Tensor] = None):
         """emb tokens split-bf16 [B, hw, 512], txt fp32 [P, 256], prompt_img int32 [P] ->
-        (low_res fp32 [P, n, 2h, 2w], iou fp32 [P, n], depth_pool fp32 [P, 33] | None).  bind_prompt_constants first."""
-        w, _ = self._packed
+        (low_res fp32 [P, n, 2h, 2w], iou fp32 [P, n], depth_pool fp32 [P, 33] | None).  bind_prompt_constants first.
+        level > 0: emb tokens are the up-sampled embeddings and prev_masks fp32 [P, M, h, w] gate them."""
+        w, _ = self._packed if level == 0 else self._levels[level]["packed"]
         P = txt_emb_f32.shape[0]
         hw = w.grid_h * w.grid_w
         n_out = self.num_mask_tokens - self._MULTIMASK_FIRST if multimask_output else 1
@@ -791,17 +819,39 @@ class MaskDecoderMultiScale(_SpecModule):
         if P == 0:
             return low, iou, pool
         ws = self._ws.get(_lib.lib().wg_mask_decoder_workspace_bytes_ex(P, hw, self._UP_STAGES), dev)
-        _lib.check(_lib.lib().wg_mask_decoder_forward(C.byref(w), emb_tokens_bf16.data_ptr(), txt_emb_f32.data_ptr(), prompt_img_i32.data_ptr(), P,
-                                                      int(multimask_output), low.data_ptr(), iou.data_ptr(), None if pool is None else pool.data_ptr(),
-                                                      ws.data_ptr(), ws.numel(), _stream()), "wg_mask_decoder_forward")
+        n_prev = 0
+        if prev_masks is not None:
+            assert prev_masks.dtype == torch.float32 and prev_masks.is_contiguous() and prev_masks.shape[0] == P
+            assert tuple(prev_masks.shape[-2:]) == (w.grid_h, w.grid_w), "previous masks must have this level's grid size"
+            n_prev = prev_masks.shape[1]
+        _lib.check(_lib.lib().wg_mask_decoder_forward_level(C.byref(w), emb_tokens_bf16.data_ptr(), txt_emb_f32.data_ptr(), prompt_img_i32.data_ptr(), P,
+                                                            int(multimask_output), None if prev_masks is None else prev_masks.data_ptr(), n_prev,
+                                                            low.data_ptr(), iou.data_ptr(), None if pool is None else pool.data_ptr(),
+                                                            ws.data_ptr(), ws.numel(), _stream()), "wg_mask_decoder_forward_level")
         return low, iou, pool
+
+    def upsample_embedding(self, emb_tokens_bf16: torch.Tensor, grid: Tuple[int, int]) -> torch.Tensor:
+        """upsample_2x of mask_decoder_multi_scale.py:166 on split-bf16 tokens [B, h*w, 512] -> [B, 4*h*w, 512]."""
+        self._packed or self._pack()
+        if 1 not in self._levels:
+            self._pack_static(1)
+        _, hold = self._levels[1]["packed"]
+        w_u, terms, b_u, g_u, be_u = hold.up2x
+        B, hw, _ = emb_tokens_bf16.shape
+        out = torch.empty(B, 4 * hw, 512, device=emb_tokens_bf16.device, dtype=torch.bfloat16)
+        need = _lib.lib().wg_upsample2x_workspace_bytes(B, hw)
+        ws = self._ws_up.get(need, emb_tokens_bf16.device)
+        _lib.check(_lib.lib().wg_upsample2x_embedding(w_u, terms, b_u, g_u, be_u, emb_tokens_bf16.data_ptr(), B, grid[0], grid[1], out.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), _stream()), "wg_upsample2x_embedding")
+        return out
 
     @torch.no_grad()
     def forward(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, multimask_output: bool, level_num: int = 0,
                 previous_masks=None):
         """Reference signature.  image_embeddings [1,256,h,w]; image_pe [1,256,h,w]; sparse [S,1,256]; dense [S,256,h,w]."""
-        if level_num != 0 or previous_masks is not None:
-            raise NotImplementedError("MaskDecoderMultiScale: only level_num=0 is built (image_feature_scale_num=1 in the released config)")
+        if level_num not in (0, 1) or level_num >= max(self.image_feature_scale_num, 1) or (level_num == 0) != (previous_masks is None):
+            raise NotImplementedError("MaskDecoderMultiScale: level_num 0 (no previous_masks) and, with image_feature_scale_num=2, level_num 1 "
+                                      "(with previous_masks) are built")
         _need_cuda(image_embeddings, "MaskDecoderMultiScale.forward")
         S = sparse_prompt_embeddings.shape[0]
         if sparse_prompt_embeddings.shape[1] != 1:
@@ -815,11 +865,23 @@ class MaskDecoderMultiScale(_SpecModule):
             pe_tok = image_pe.reshape(Cc, h * wd).t().contiguous().float()  # layout change only
             # dense prompt embedding: the reference always passes no_mask_embed broadcast over (h, w)
             dense_vec = dense_prompt_embeddings[0, :, 0, 0].float().contiguous()
-            self.bind_prompt_constants(pe_tok, dense_vec, (h, wd))
             emb_tok = to_split(image_embeddings.reshape(1, Cc, h * wd).permute(0, 2, 1))
             txt = sparse_prompt_embeddings.reshape(S, Cc).float().contiguous()
             pimg = torch.zeros(S, dtype=torch.int32, device=image_embeddings.device)
-            low, iou, _ = self.run(emb_tok, txt, pimg, multimask_output)
+            if level_num == 0:
+                self.bind_prompt_constants(pe_tok, dense_vec, (h, wd))
+                low, iou, _ = self.run(emb_tok, txt, pimg, multimask_output)
+            else:
+                # mask_decoder_multi_scale.py:165-171: up-sampled embedding gated by the previous masks, pe1 on the 2h x 2w grid;
+                # the dense prompt embedding is no_mask_embed broadcast, so its bilinear resize is the same constant
+                gauss = _f32(self._sd()["pe1.positional_encoding_gaussian_matrix"])
+                F_ = gauss.shape[1]
+                pe1_tok = torch.empty(4 * h * wd, 2 * F_, device=image_embeddings.device, dtype=torch.float32)
+                _lib.check(_lib.lib().wg_dense_pe(gauss.data_ptr(), F_, 2 * h, 2 * wd, None, pe1_tok.data_ptr(), _stream()), "wg_dense_pe")
+                self._pe1_keep = (gauss, pe1_tok)
+                self.bind_prompt_constants(pe1_tok, dense_vec, (2 * h, 2 * wd), level=1)
+                up_tok = self.upsample_embedding(emb_tok, (h, wd))
+                low, iou, _ = self.run(up_tok, txt, pimg, multimask_output, level=1, prev_masks=previous_masks.float().contiguous())
         return low.to(dt), iou.to(dt)
 
 
@@ -841,8 +903,11 @@ class MaskDecoder(MaskDecoderMultiScale):
         self.num_multimask_outputs = num_multimask_outputs
         self.num_mask_tokens = num_multimask_outputs + 1
         self._build(specs.mask_decoder_sam_spec(transformer_dim, num_multimask_outputs), seed)
+        self.image_feature_scale_num = 1
         self._ws = _Workspace()
+        self._ws_up = _Workspace()
         self._pe_key = None
+        self._levels = {}
 
     @torch.no_grad()
     def forward(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, multimask_output: bool):
