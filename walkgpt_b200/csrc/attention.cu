@@ -12,12 +12,10 @@
 //             shuffles): tcgen05.ld S -> online softmax in fp32 (exp2 with folded scale, packed FFMA2/FADD2, 3 of 8
 //             exponentials on the FMA pipe) -> P as bf16 pairs back into TMEM (tcgen05.st); O stays in TMEM across
 //             all key blocks (lazy rescale) -> final 1/l, bf16, TMA store.
-// Leftover rows that do not fill a query tile (the 1025th token of the CLIP sequence) run on CUDA cores in
-// attention_tail_rows_kernel instead of costing a whole tensor-core tile per (head, image).
 //
-// Measured on B200 (B=64, T=1025, 16 heads): 0.71 ms (P through smem, 9 query tiles, serial softmax phases)
-// -> 0.54 ms.  What moved it, in order: the tail-row kernel (-11 %), P in TMEM + packed arithmetic + software-pipelined
-// exponentials (-8 %), branch-free key masking only where keys can be invalid (-4 %), polynomial exp2 share (-2 %).
+// Measured on B200 (B=64, T=1025, 16 heads): 0.71 ms (P through smem, serial softmax phases, branchy key masking)
+// -> 0.51 ms (T=1024: 0.43 ms).  What moved it: P in TMEM + packed arithmetic + software-pipelined exponentials, branch-free
+// key masking only where keys can be invalid, narrow last key block, polynomial exp2 share.
 #include "host.h"
 #include "ptx.cuh"
 #include <cstdlib>
@@ -501,101 +499,6 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
 }
 
-// Rows that do not fill a 128-query tile when only a few are left over (T = 1025: the single row 1024 of every head):
-// running them through the tensor-core kernel would cost a full tile of MMAs and softmax per (head, image) -- 1/9 of the
-// whole attention for the CLIP tower.  They go through CUDA cores instead: one CTA of 128 threads per (row, head, image),
-// fp32 scores in shared memory (thread per key), then P V with one warp-wide coalesced 128-byte V row read per key.
-constexpr int TAIL_THREADS = 128;
-constexpr int TAIL_MAX_ROWS = 8;  // leftovers up to this many rows take this path
-
-__global__ void __launch_bounds__(TAIL_THREADS)
-attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const uint8_t* __restrict__ key_valid,
-                           int T, int heads, int row0, float scale_log2) {
-    extern __shared__ float tail_smem[];
-    float* sc = tail_smem;             // [T] scores, then probabilities
-    float* red = tail_smem + T;        // [4 warps][64] partial outputs / reductions
-    const int row = row0 + blockIdx.x;
-    const int head = blockIdx.y;
-    const int img = blockIdx.z;
-    const int HD = heads * ATT_D;
-    const size_t ld = (size_t)3 * HD;
-    const __nv_bfloat16* base = qkv + (size_t)img * T * ld;
-    const uint8_t* kvalid = key_valid ? key_valid + (size_t)img * T : nullptr;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    float q[ATT_D];
-    {
-        const uint4* qp = reinterpret_cast<const uint4*>(base + (size_t)row * ld + head * ATT_D);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldg(qp + c);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h[i]);
-                q[c * 8 + i * 2] = f.x * scale_log2;
-                q[c * 8 + i * 2 + 1] = f.y * scale_log2;
-            }
-        }
-    }
-    float mx = -INFINITY;
-    for (int k = tid; k < T; k += TAIL_THREADS) {
-        const uint4* kp = reinterpret_cast<const uint4*>(base + (size_t)k * ld + HD + head * ATT_D);
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldg(kp + c);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h[i]);
-                a0 = fmaf(q[c * 8 + i * 2], f.x, a0);
-                a1 = fmaf(q[c * 8 + i * 2 + 1], f.y, a1);
-            }
-        }
-        float sv = a0 + a1;
-        if (kvalid != nullptr && kvalid[k] == 0) sv = -INFINITY;
-        sc[k] = sv;
-        mx = fmaxf(mx, sv);
-    }
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    if (mx == -INFINITY) mx = 0.f;
-    __syncthreads();
-    float sum = 0.f;
-    for (int k = tid; k < T; k += TAIL_THREADS) {
-        const float e = ex2_approx(sc[k] - mx);
-        sc[k] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    if (lane == 0) red[warp] = sum;
-    __syncthreads();
-    sum = (red[0] + red[1]) + (red[2] + red[3]);
-    __syncthreads();
-    // O = P V: warp w takes keys w, w+4, ...; lane l owns output dims 2l, 2l+1
-    float o0 = 0.f, o1 = 0.f;
-    const __nv_bfloat16* vbase = base + 2 * HD + head * ATT_D + lane * 2;
-#pragma unroll 8
-    for (int k = warp; k < T; k += 4) {
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)k * ld);
-        const float2 f = __bfloat1622float2(v);
-        const float pk = sc[k];
-        o0 = fmaf(pk, f.x, o0);
-        o1 = fmaf(pk, f.y, o1);
-    }
-    red[warp * ATT_D + lane * 2] = o0;
-    red[warp * ATT_D + lane * 2 + 1] = o1;
-    __syncthreads();
-    if (tid < ATT_D) {
-        const float o = (red[tid] + red[ATT_D + tid]) + (red[2 * ATT_D + tid] + red[3 * ATT_D + tid]);
-        const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-        out[((size_t)img * T + row) * HD + head * ATT_D + tid] = __float2bfloat16(o * inv);
-    }
-}
-
 }  // namespace
 }  // namespace wg
 
@@ -645,14 +548,14 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
         split = e ? atoi(e) : ATT_SPLIT_DEFAULT;
         if (split != 1 && split != 2) split = ATT_SPLIT_DEFAULT;
     }
-    // a few leftover rows (T % 128 <= TAIL_MAX_ROWS) go through the CUDA-core tail kernel instead of a whole tensor-core tile
-    const int rem = T % ATT_BQ;
-    const int tail_rows = (rem > 0 && rem <= TAIL_MAX_ROWS) ? rem : 0;
-    const int row0 = T - tail_rows;
-    Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D,
-              (row0 > 0 ? 1 : 0) + (tail_rows > 0 ? 1 : 0));
-    if (row0 > 0) {
-        dim3 grid((row0 + ATT_BQ - 1) / ATT_BQ, heads, B);
+    // The 1025th token of the CLIP sequence simply gets a ninth (mostly empty) query tile and a ninth, 16-key-wide key block:
+    // idle softmax warps skip the arithmetic and the last S / PV MMAs are narrow.  Measured on B200 (B=64, 16 heads): T=1024
+    // 0.43 ms, T=1025 this way 0.51 ms; a separate CUDA-core kernel for the last query row (it must stream K and V from HBM
+    // once more) 0.53 ms; the leftover key folded into every row on CUDA cores instead of a ninth key block 0.55 ms; the last
+    // row folded into the producer warps 0.65-0.83 ms.
+    Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D);
+    {
+        dim3 grid((T + ATT_BQ - 1) / ATT_BQ, heads, B);
 #define WG_ATT_LAUNCH(P, S)                                                                                                     \
     do {                                                                                                                        \
         static bool attr_set = false;                                                                                           \
@@ -680,18 +583,6 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
             }
         }
 #undef WG_ATT_LAUNCH
-        WG_CHECK_CUDA(cudaGetLastError());
-    }
-    if (tail_rows > 0) {
-        const size_t smem = ((size_t)T + 4 * ATT_D) * sizeof(float);
-        WG_REQUIRE(smem <= 200 * 1024, "wg_attention_d64: T=%d too long for the tail-row kernel", T);
-        static bool tail_attr_set = false;
-        if (!tail_attr_set) {
-            WG_CHECK_CUDA(cudaFuncSetAttribute(attention_tail_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            tail_attr_set = true;
-        }
-        attention_tail_rows_kernel<<<dim3(tail_rows, heads, B), TAIL_THREADS, smem, stream>>>(
-            static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), key_valid, T, heads, row0, p.scale_log2);
         WG_CHECK_CUDA(cudaGetLastError());
     }
     return WG_OK;
