@@ -228,9 +228,11 @@ class CLIPVisionTower(_SpecModule):
         return self.select_layer % n_states, (-11) % n_states
 
     @torch.no_grad()
-    def forward(self, images, attention_mask=None):
+    def forward(self, images, attention_mask=None, want_mid: bool = True):
         """images [B,3,S,S] (or a list of [3,S,S]); attention_mask [B,1+g*g] with 1 = valid key (or None).
-        Returns (hidden_states[select_layer][:,1:], [hidden_states[-11][:,1:]]) cast to images.dtype."""
+        Returns (hidden_states[select_layer][:,1:], [hidden_states[-11][:,1:]]) cast to images.dtype.  want_mid=False (not part
+        of the reference signature) skips the copy of hidden_states[-11], which only image_feature_scale_num=2 consumes; the
+        second element is then the first one again."""
         if isinstance(images, (list, tuple)):
             images = torch.stack(list(images), dim=0)
         if not images.is_cuda:
@@ -244,6 +246,8 @@ class CLIPVisionTower(_SpecModule):
         assert images.shape[1:] == (3, g["image"], g["image"]), f"expected [B,3,{g['image']},{g['image']}], got {tuple(images.shape)}"
         w, _, _ = self._packed or self._pack()
         idx_last, idx_mid = self.hidden_state_indices()
+        if not want_mid:
+            idx_mid = idx_last
         n_run = max(idx_last, idx_mid)
         L = self.num_patches
         kernel_dtype = torch.bfloat16 if out_dtype == torch.bfloat16 else torch.float32
@@ -1032,7 +1036,8 @@ class GroundingPath(nn.Module):
             max_S = max([offs[i + 1] - offs[i] for i in range(B)] + [0])
         out: Dict[str, torch.Tensor] = {}
         with torch.cuda.device(dev):
-            feats, _ = self.vision_tower(images_clip.to(torch.bfloat16) if images_clip.dtype != torch.bfloat16 else images_clip, attention_mask)
+            feats, _ = self.vision_tower(images_clip.to(torch.bfloat16) if images_clip.dtype != torch.bfloat16 else images_clip, attention_mask,
+                                         want_mid=False)
             if want_vis_tokens:
                 out["vis_tokens"] = self.msqp.run(feats, torch.bfloat16)
             _, emb = self.proj_neck.run(feats)
