@@ -361,6 +361,18 @@ WG_API size_t wg_intersection_and_union_workspace_bytes(int n_masks, int K);
 WG_API int wg_intersection_and_union(const uint8_t* output, const uint8_t* target, int n_masks, int64_t pixels, int K,
                                      int ignore_index, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* F4 -- cost matrix of match_pred (utils/matcher.py:93-128), everything up to the host-side linear_sum_assignment:
+ *   pred_logits fp32 [n_pred, H, W]; tgt_masks fp32 (or uint8 when tgt_is_u8) [n_tgt, H, W]; point_coords fp32 [num_points, 2]
+ *   = (x, y) in [0, 1]^2, the ONE point set all masks share (matcher.py:101-102; the caller draws it, torch.rand in the
+ *   reference).  Both mask sets are sampled with point_sample (matcher.py:64-90: F.grid_sample bilinear, zero padding,
+ *   align_corners=False); cost fp32 [n_pred, n_tgt] = batch_sigmoid_ce_loss + batch_dice_loss (matcher.py:10-58, both with
+ *   weight 1 as in match_pred).  Deterministic (fixed-order partial sums); fp32 sums in a different order than torch.einsum,
+ *   so the parity tolerance is 2e-5 absolute on costs of O(1).  1 <= n_pred, n_tgt <= 64. */
+WG_API size_t wg_match_cost_workspace_bytes(int n_pred, int n_tgt, int num_points);
+WG_API int wg_match_cost(const float* pred_logits, const void* tgt_masks, int tgt_is_u8, const float* point_coords, int n_pred,
+                         int n_tgt, int H, int W, int num_points, float* cost, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

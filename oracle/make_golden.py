@@ -201,9 +201,42 @@ def make_decoder_two_level():
                             "masks_l1": m1, "iou_l1": i1, "masks_l1_single": m1s, "iou_l1_single": i1s})
 
 
+@torch.no_grad()
+def make_match_cost():
+    """the point-sampled cost matrix of match_pred (utils/matcher.py:93-128).  match_pred draws its points
+    with torch.rand right after being called, so seeding the global generator before the call and before our own torch.rand
+    gives the same points; the cost matrix is then rebuilt from the reference's own point_sample / batch_*_loss functions and
+    the assignment is the reference's match_pred output.  Writes tests/golden/match_cost.pt:  python -m oracle.make_golden match"""
+    from utils.matcher import batch_dice_loss, batch_sigmoid_ce_loss, match_pred, point_sample
+
+    cases = []
+    for k, (n_pred, n_tgt, H, W) in enumerate(((5, 4, 56, 56), (3, 6, 40, 72), (1, 1, 24, 24))):
+        # blobby targets (discs) and logits that follow a shuffled, noisy version of them: the assignment is non-trivial
+        yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+        g = torch.Generator().manual_seed(500 + k)
+        cx, cy, rr = torch.rand(n_tgt, generator=g) * W, torch.rand(n_tgt, generator=g) * H, 6 + torch.rand(n_tgt, generator=g) * 10
+        tgt = (((xx[None] - cx[:, None, None]) ** 2 + (yy[None] - cy[:, None, None]) ** 2) < rr[:, None, None] ** 2).float()
+        perm = torch.randperm(max(n_pred, n_tgt), generator=g)[:n_pred] % n_tgt
+        out = (tgt[perm] * 2 - 1) * 4 + torch.randn(n_pred, H, W, generator=g) * 3
+        out = out.half().float()  # values exact in fp16: keeps the fixture small
+        torch.manual_seed(900 + k)
+        idx = match_pred(out, tgt)
+        torch.manual_seed(900 + k)
+        pts = torch.rand(1, 12544, 2)
+        t = point_sample(tgt[:, None], pts.repeat(n_tgt, 1, 1), align_corners=False).squeeze(1).float()
+        x = point_sample(out[:, None], pts.repeat(n_pred, 1, 1), align_corners=False).squeeze(1).float()
+        C = batch_sigmoid_ce_loss(x, t) + batch_dice_loss(x, t)
+        cases.append({"out_mask": out.half(), "tgt_mask": tgt.to(torch.uint8), "seed": 900 + k, "cost": C, "pred_idx": torch.as_tensor(idx[0]),
+                      "tgt_idx": torch.as_tensor(idx[1])})
+    save("match_cost", {"cases": cases, "num_points": 12544})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "two_level":
         make_decoder_two_level()
+    elif len(sys.argv) > 1 and sys.argv[1] == "match":
+        make_match_cost()
     else:
         main()
         make_decoder_two_level()
+        make_match_cost()

@@ -460,6 +460,25 @@ def gather_seg_rows(hidden: torch.Tensor, input_ids: torch.Tensor, seg_token_idx
     return pred, counts, off[torch.as_tensor(list(offset), dtype=torch.long)]
 
 
+def point_sample(inp: torch.Tensor, point_coords: torch.Tensor) -> torch.Tensor:
+    """utils/matcher.py:64-90 with align_corners=False: inp [N, C, H, W], point_coords [N, P, 2] in [0, 1]^2 -> [N, C, P]."""
+    out = F.grid_sample(inp.float(), 2.0 * point_coords.float().unsqueeze(2) - 1.0, align_corners=False)
+    return out.squeeze(3)
+
+
+def match_cost(out_mask: torch.Tensor, tgt_mask: torch.Tensor, point_coords: torch.Tensor) -> torch.Tensor:
+    """utils/matcher.py:93-124 up to the cost matrix: out_mask [n_pred, H, W] logits, tgt_mask [n_tgt, H, W], point_coords
+    [1, P, 2] -> C [n_pred, n_tgt] = batch_sigmoid_ce_loss (matcher.py:33-58) + batch_dice_loss (matcher.py:10-26)."""
+    t = point_sample(tgt_mask[:, None], point_coords.repeat(tgt_mask.shape[0], 1, 1)).squeeze(1).float()
+    x = point_sample(out_mask[:, None], point_coords.repeat(out_mask.shape[0], 1, 1)).squeeze(1).float()
+    pos = F.binary_cross_entropy_with_logits(x, torch.ones_like(x), reduction="none")
+    neg = F.binary_cross_entropy_with_logits(x, torch.zeros_like(x), reduction="none")
+    ce = (torch.einsum("nc,mc->nm", pos, t) + torch.einsum("nc,mc->nm", neg, 1 - t)) / x.shape[1]
+    sig = x.sigmoid()
+    dice = 1 - (2 * torch.einsum("nc,mc->nm", sig, t) + 1) / (sig.sum(-1)[:, None] + t.sum(-1)[None, :] + 1)
+    return ce + dice
+
+
 # --------------------------------------------------------------------------------------------------
 # A10 relative-depth head.  NOT IN THE REFERENCE (SURVEY §0, §8c): the reference emits depth as LLM text.
 # This is this repo's own extension, defined here so the CUDA tail has something to be checked against:

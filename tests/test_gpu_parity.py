@@ -484,6 +484,42 @@ def test_intersection_and_union_is_bit_exact():
             assert torch.equal(got[i, 0], ai) and torch.equal(got[i, 1], au) and torch.equal(got[i, 2], at)
 
 
+MATCH_TOL = 2e-5  # fp32 sums of 12544 terms in a different order than torch.einsum; costs are O(1)
+
+
+def test_match_cost_against_reference_golden_and_oracle():
+    """F4 (utils/matcher.py:93-128): cost matrix on the GPU against the reference-generated fixture, u8 and fp32 targets; the
+    assignment scipy derives from it equals the reference's match_pred output; two runs give the same bits."""
+    g = load("match_cost")
+    for case in g["cases"]:
+        torch.manual_seed(case["seed"])
+        pts = torch.rand(1, g["num_points"], 2)
+        out, tgt = case["out_mask"].float(), case["tgt_mask"]
+        c_u8 = ops.match_cost(out.to(DEV), tgt.to(DEV), pts.to(DEV))
+        c_f32 = ops.match_cost(out.to(DEV), tgt.float().to(DEV), pts.to(DEV))
+        assert torch.equal(c_u8, c_f32) and torch.equal(c_u8, ops.match_cost(out.to(DEV), tgt.to(DEV), pts.to(DEV)))
+        assert (c_u8.cpu() - case["cost"]).abs().max().item() < MATCH_TOL
+        r, c = M.match_pred(out.to(DEV), tgt.to(DEV), pts.to(DEV))
+        assert list(r) == case["pred_idx"].tolist() and list(c) == case["tgt_idx"].tolist()
+
+
+def test_match_cost_edge_points_and_sizes():
+    """Points on the border and in the corners of [0, 1]^2 (zero-padded neighbours), soft fp32 targets, a point count that is not
+    a multiple of the chunk size, a 1024 x 1024 map, and the empty cases."""
+    gen = torch.Generator().manual_seed(77)
+    for n_pred, n_tgt, H, W, P in ((7, 3, 33, 65, 1000), (2, 2, 1024, 1024, 12544), (64, 64, 16, 16, 257)):
+        out = torch.randn(n_pred, H, W, generator=gen) * 5
+        tgt = torch.rand(n_tgt, H, W, generator=gen)
+        pts = torch.rand(1, P, 2, generator=gen)
+        pts[0, :9] = torch.tensor([[0., 0.], [1., 1.], [0., 1.], [1., 0.], [0.5, 0.], [0., 0.5], [1., 0.5], [0.5, 1.], [0.5 / W, 0.5 / H]])
+        got = ops.match_cost(out.to(DEV), tgt.to(DEV), pts.to(DEV)).cpu()
+        ref = path_a.match_cost(out, tgt, pts)
+        assert (got - ref).abs().max().item() < MATCH_TOL * max(1.0, ref.abs().max().item())
+    assert ops.match_cost(torch.zeros(0, 8, 8, device=DEV), torch.zeros(3, 8, 8, device=DEV), torch.rand(1, 16, 2, device=DEV)).shape == (0, 3)
+    with pytest.raises(_lib.WalkGPTB200Error, match="1..64"):
+        ops.match_cost(torch.zeros(65, 8, 8, device=DEV), torch.zeros(3, 8, 8, device=DEV), torch.rand(1, 16, 2, device=DEV))
+
+
 def test_torch_custom_ops_call_the_c_abi():
     from walkgpt_b200 import torch_ops
 

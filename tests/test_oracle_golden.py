@@ -163,6 +163,21 @@ def test_iou_histogram():
     assert torch.equal(ai, g["inter"]) and torch.equal(au, g["union"]) and torch.equal(at, g["target_area"])
 
 
+def test_match_cost_against_reference_golden():
+    """oracle.match_cost (utils/matcher.py:93-124) reproduces the cost matrix built from the reference's own
+    point_sample / batch_sigmoid_ce_loss / batch_dice_loss, and scipy's assignment on it is match_pred's output."""
+    from scipy.optimize import linear_sum_assignment
+
+    g = load("match_cost")
+    for case in g["cases"]:
+        torch.manual_seed(case["seed"])
+        pts = torch.rand(1, g["num_points"], 2)
+        C = path_a.match_cost(case["out_mask"].float(), case["tgt_mask"].float(), pts)
+        assert C.shape == case["cost"].shape and (C - case["cost"]).abs().max().item() < 1e-6
+        r, c = linear_sum_assignment(C)
+        assert list(r) == case["pred_idx"].tolist() and list(c) == case["tgt_idx"].tolist()
+
+
 def test_depth_extension_is_self_consistent():
     """No reference exists for depth (parity unpinned): only check the in-repo definition's invariants."""
     sd = specs.make_state_dict(specs.depth_head_spec(), seed=3, prefix="depth_head.")

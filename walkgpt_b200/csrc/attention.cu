@@ -182,6 +182,9 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
                 const int i = g * 8 + k * 2;
                 float x0, x1, e0, e1;
                 upk2(ffma2(pk2(__uint_as_float(sv(i)), __uint_as_float(sv(i + 1))), SC2, NM2), x0, x1);  // -inf for masked keys -> 0
+#ifdef ATT_DBG_NOEXP  // debug build: no exponentials at all (wrong results) -- measures what the rest of the block costs
+                if (true) { e0 = x0; e1 = x1; } else
+#endif
                 if (use_poly((g & 1) * 4 + k, POLY)) {
                     exp2_poly2(x0, x1, e0, e1);
                 } else {

@@ -255,6 +255,123 @@ __global__ void iou_finalize_kernel(const int* __restrict__ acc, float* __restri
     out[((size_t)m * 3 + 2) * K + k] = (float)at;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Matching cost of match_pred (utils/matcher.py:93-128): every predicted and every target mask is sampled at the same P points
+// (point_sample = F.grid_sample, bilinear, zero padding, align_corners=False), then
+//   C[n, m] = (sum_p pos[n,p] t[m,p] + neg[n,p] (1 - t[m,p])) / P  +  1 - (2 sum_p sig[n,p] t[m,p] + 1) / (sum_p sig[n,p] + sum_p t[m,p] + 1)
+// with pos / neg = BCE-with-logits against 1 / 0 (matcher.py:33-58) and sig = sigmoid (matcher.py:10-26).
+// One CTA per chunk of MATCH_PTS points: each thread owns one point (tap offsets and weights computed once, reused for every
+// mask), the sampled values go to shared memory, then the (n, m) pairs are spread over the threads.  Per-chunk partial sums are
+// written to the workspace and added in chunk order by the finalize kernel: no floating-point atomics, the same bits every run.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int MATCH_PTS = 128;
+constexpr int MATCH_LD = MATCH_PTS + 1;  // row pitch of the shared arrays: threads of a warp read different rows at the same point
+
+struct Taps {
+    int o00, o01, o10, o11;    // offsets of the four neighbours (clamped; a neighbour outside the map has weight 0)
+    float w00, w01, w10, w11;  // nw, ne, sw, se
+};
+__device__ __forceinline__ Taps make_taps(float u, float v, int H, int W) {
+    // point_sample: grid = 2 p - 1; grid_sample(align_corners=False): x = ((grid + 1) W - 1) / 2
+    const float gx = 2.0f * u - 1.0f, gy = 2.0f * v - 1.0f;
+    const float x = ((gx + 1.0f) * W - 1.0f) * 0.5f, y = ((gy + 1.0f) * H - 1.0f) * 0.5f;
+    const float xf = floorf(x), yf = floorf(y);
+    const int x0 = (int)xf, y0 = (int)yf, x1 = x0 + 1, y1 = y0 + 1;
+    // weights as grid_sample forms them: differences against the integer corners, not (1 - fraction)
+    Taps t;
+    t.w00 = ((float)x1 - x) * ((float)y1 - y);
+    t.w01 = (x - (float)x0) * ((float)y1 - y);
+    t.w10 = ((float)x1 - x) * (y - (float)y0);
+    t.w11 = (x - (float)x0) * (y - (float)y0);
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    if (!(vx0 && vy0)) t.w00 = 0.f;
+    if (!(vx1 && vy0)) t.w01 = 0.f;
+    if (!(vx0 && vy1)) t.w10 = 0.f;
+    if (!(vx1 && vy1)) t.w11 = 0.f;
+    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1), cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+    t.o00 = cy0 * W + cx0; t.o01 = cy0 * W + cx1; t.o10 = cy1 * W + cx0; t.o11 = cy1 * W + cx1;
+    return t;
+}
+template <typename T>
+__device__ __forceinline__ float sample4(const T* __restrict__ img, const Taps& t) {
+    float acc = (float)__ldg(img + t.o00) * t.w00;
+    acc += (float)__ldg(img + t.o01) * t.w01;
+    acc += (float)__ldg(img + t.o10) * t.w10;
+    acc += (float)__ldg(img + t.o11) * t.w11;
+    return acc;
+}
+
+// partial layout per chunk: [n_pred * n_tgt] ce sums | [n_pred * n_tgt] dice numerators | [n_pred] sigmoid sums | [n_tgt] target sums
+template <typename TT>
+__global__ void __launch_bounds__(MATCH_PTS) match_sample_kernel(const float* __restrict__ pred, const TT* __restrict__ tgt, const float* __restrict__ pts,
+                                                                  int n_pred, int n_tgt, int H, int W, int P, float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    float* s_pos = sm;                          // [n_pred][MATCH_LD]
+    float* s_neg = s_pos + n_pred * MATCH_LD;
+    float* s_sig = s_neg + n_pred * MATCH_LD;
+    float* s_t = s_sig + n_pred * MATCH_LD;     // [n_tgt][MATCH_LD]
+    const int tid = threadIdx.x;
+    const int p = blockIdx.x * MATCH_PTS + tid;
+    const bool live = p < P;
+    const size_t hw = (size_t)H * W;
+    if (live) {
+        const Taps t = make_taps(pts[2 * p], pts[2 * p + 1], H, W);
+        for (int n = 0; n < n_pred; ++n) {
+            const float x = sample4(pred + n * hw, t);
+            // binary_cross_entropy_with_logits(x, y) = (1 - y) x + max(-x, 0) + log1p(exp(-|x|))
+            const float sp = fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+            s_pos[n * MATCH_LD + tid] = sp;
+            s_neg[n * MATCH_LD + tid] = x + sp;
+            s_sig[n * MATCH_LD + tid] = 1.0f / (1.0f + expf(-x));
+        }
+        for (int m = 0; m < n_tgt; ++m) s_t[m * MATCH_LD + tid] = sample4(tgt + m * hw, t);
+    } else {  // past the last point: contributes nothing to any sum
+        for (int n = 0; n < n_pred; ++n) { s_pos[n * MATCH_LD + tid] = 0.f; s_neg[n * MATCH_LD + tid] = 0.f; s_sig[n * MATCH_LD + tid] = 0.f; }
+        for (int m = 0; m < n_tgt; ++m) s_t[m * MATCH_LD + tid] = 0.f;
+    }
+    __syncthreads();
+    const int pairs = n_pred * n_tgt;
+    float* out = partial + (size_t)blockIdx.x * (2 * pairs + n_pred + n_tgt);
+    for (int pr = tid; pr < pairs; pr += MATCH_PTS) {
+        const float* ps = s_pos + (pr / n_tgt) * MATCH_LD;
+        const float* ng = s_neg + (pr / n_tgt) * MATCH_LD;
+        const float* sg = s_sig + (pr / n_tgt) * MATCH_LD;
+        const float* tt = s_t + (pr % n_tgt) * MATCH_LD;
+        float ce = 0.f, dn = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < MATCH_PTS; ++i) {
+            const float t = tt[i];
+            ce += ps[i] * t + ng[i] * (1.0f - t);
+            dn += sg[i] * t;
+        }
+        out[pr] = ce;
+        out[pairs + pr] = dn;
+    }
+    for (int r = tid; r < n_pred + n_tgt; r += MATCH_PTS) {
+        const float* row = r < n_pred ? s_sig + r * MATCH_LD : s_t + (r - n_pred) * MATCH_LD;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < MATCH_PTS; ++i) acc += row[i];
+        out[2 * pairs + r] = acc;
+    }
+}
+__global__ void match_finalize_kernel(const float* __restrict__ partial, int chunks, int n_pred, int n_tgt, int P, float* __restrict__ cost) {
+    const int pr = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pairs = n_pred * n_tgt;
+    if (pr >= pairs) return;
+    const int n = pr / n_tgt, m = pr % n_tgt;
+    const size_t stride = 2 * (size_t)pairs + n_pred + n_tgt;
+    float ce = 0.f, dn = 0.f, ss = 0.f, st = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+        const float* q = partial + c * stride;
+        ce += q[pr];
+        dn += q[pairs + pr];
+        ss += q[2 * pairs + n];
+        st += q[2 * pairs + n_pred + m];
+    }
+    cost[pr] = ce / (float)P + (1.0f - (2.0f * dn + 1.0f) / (ss + st + 1.0f));
+}
+
 }  // namespace
 }  // namespace wg
 
@@ -341,6 +458,44 @@ extern "C" int wg_intersection_and_union(const uint8_t* output, const uint8_t* t
     Prof prof("intersection_and_union", s, 0.0, 2.0 * (double)n_masks * (double)pixels, 2);
     iou_hist_kernel<<<dim3((unsigned)chunks, n_masks), 256, 0, s>>>(output, target, pixels, K, ignore_index, acc);
     iou_finalize_kernel<<<(n_masks * K + 255) / 256, 256, 0, s>>>(acc, out, n_masks, K);
+    WG_CHECK_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+
+static size_t match_chunks(int P) { return (size_t)((P > 0 ? P : 0) + MATCH_PTS - 1) / MATCH_PTS; }
+
+extern "C" size_t wg_match_cost_workspace_bytes(int n_pred, int n_tgt, int num_points) {
+    if (n_pred <= 0 || n_tgt <= 0) return 0;
+    return match_chunks(num_points) * (2 * (size_t)n_pred * n_tgt + n_pred + n_tgt) * sizeof(float);
+}
+
+extern "C" int wg_match_cost(const float* pred_logits, const void* tgt_masks, int tgt_is_u8, const float* point_coords, int n_pred, int n_tgt, int H, int W,
+                             int num_points, float* cost, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    if (n_pred == 0 || n_tgt == 0) return WG_OK;  // empty cost matrix (linear_sum_assignment returns no pairs)
+    WG_REQUIRE(pred_logits && tgt_masks && point_coords && cost && workspace, "wg_match_cost: null pointer");
+    WG_REQUIRE(n_pred > 0 && n_tgt > 0 && n_pred <= 64 && n_tgt <= 64, "wg_match_cost: 1..64 predicted and target masks (got %d, %d)", n_pred, n_tgt);
+    WG_REQUIRE(H > 0 && W > 0 && (long long)H * W < (1ll << 31) && num_points > 0, "wg_match_cost: bad sizes H=%d W=%d points=%d", H, W, num_points);
+    WG_REQUIRE(workspace_bytes >= wg_match_cost_workspace_bytes(n_pred, n_tgt, num_points), "wg_match_cost: workspace too small");
+    if (!device_is_sm100()) {
+        set_error("wg_match_cost: this library only runs on sm_100 (B200) devices; there is no fallback");
+        return WG_ERR_UNSUPPORTED;
+    }
+    const int chunks = (int)match_chunks(num_points);
+    const size_t smem = (size_t)(3 * n_pred + n_tgt) * MATCH_LD * sizeof(float);
+    float* partial = static_cast<float*>(workspace);
+    Prof prof("match_cost", s, 0.0, 16.0 * (double)(n_pred + n_tgt) * num_points, 2);
+    if (tgt_is_u8) {
+        static bool attr_u8 = false;
+        if (!attr_u8) { WG_CHECK_CUDA(cudaFuncSetAttribute(match_sample_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * MATCH_LD * 4)); attr_u8 = true; }
+        match_sample_kernel<uint8_t><<<chunks, MATCH_PTS, smem, s>>>(pred_logits, static_cast<const uint8_t*>(tgt_masks), point_coords, n_pred, n_tgt, H, W, num_points, partial);
+    } else {
+        static bool attr_f = false;
+        if (!attr_f) { WG_CHECK_CUDA(cudaFuncSetAttribute(match_sample_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * MATCH_LD * 4)); attr_f = true; }
+        match_sample_kernel<float><<<chunks, MATCH_PTS, smem, s>>>(pred_logits, static_cast<const float*>(tgt_masks), point_coords, n_pred, n_tgt, H, W, num_points, partial);
+    }
+    match_finalize_kernel<<<(n_pred * n_tgt + 127) / 128, 128, 0, s>>>(partial, chunks, n_pred, n_tgt, num_points, cost);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
 }

@@ -958,6 +958,24 @@ def postprocess_masks(masks: torch.Tensor, input_size: Tuple[int, ...], original
     return logits.reshape(b, c, *logits.shape[-2:]).to(masks.dtype)
 
 
+@torch.no_grad()
+def match_pred(out_mask: torch.Tensor, tgt_mask: torch.Tensor, point_coords: Optional[torch.Tensor] = None, num_points: int = 12544):
+    """Drop-in for ``utils.matcher.match_pred`` (utils/matcher.py:93-128; call sites train_walkgpt.py:937,
+    evaluation_walkgpt.py:751): out_mask [n_pred, H, W] logits, tgt_mask [n_tgt, H, W] -> (pred indices, target indices) of the
+    minimum-cost assignment.  The cost matrix is built on the GPU (``ops.match_cost``); only the [n_pred, n_tgt] matrix crosses
+    to the host for scipy's ``linear_sum_assignment``, as in the reference.  ``point_coords`` defaults to the reference's
+    ``torch.rand(1, 12544, 2)`` drawn on the masks' device; pass it to make a call reproducible."""
+    from scipy.optimize import linear_sum_assignment
+
+    from . import ops
+
+    _need_cuda(out_mask, "match_pred")
+    if point_coords is None:
+        point_coords = torch.rand(1, num_points, 2, device=out_mask.device)
+    cost = ops.match_cost(out_mask, tgt_mask, point_coords)
+    return linear_sum_assignment(cost.cpu())
+
+
 class DepthHead(_SpecModule):
     """Relative-depth head.  THIS REPO'S EXTENSION -- the reference has no depth head (it emits depth as text);
     definition and checker: ``oracle/path_a.py:depth_head``.  Parity with the reference is therefore unpinned."""

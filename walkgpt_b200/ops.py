@@ -152,3 +152,26 @@ def intersection_and_union(output: torch.Tensor, target: torch.Tensor, K: int = 
     _lib.check(_lib.lib().wg_intersection_and_union(output.data_ptr(), target.data_ptr(), n, pixels, K, ignore_index, out.data_ptr(), ws.data_ptr(), need,
                                                     _stream()), "wg_intersection_and_union")
     return out
+
+
+def match_cost(out_mask: torch.Tensor, tgt_mask: torch.Tensor, point_coords: torch.Tensor) -> torch.Tensor:
+    """Cost matrix of match_pred (utils/matcher.py:93-128) before the host-side linear_sum_assignment:
+    out_mask fp32 [n_pred, H, W] logits, tgt_mask fp32 or uint8 [n_tgt, H, W], point_coords fp32 [P, 2] (or [1, P, 2]) in
+    [0, 1]^2 -> fp32 [n_pred, n_tgt] = batch_sigmoid_ce_loss + batch_dice_loss on the point-sampled masks."""
+    _need_cuda(out_mask, tgt_mask, point_coords)
+    assert out_mask.dim() == 3 and tgt_mask.dim() == 3 and out_mask.shape[1:] == tgt_mask.shape[1:]
+    pts = point_coords.reshape(-1, 2).float().contiguous()
+    out_mask = out_mask.float().contiguous()
+    if tgt_mask.dtype != torch.uint8:
+        tgt_mask = tgt_mask.float()
+    tgt_mask = tgt_mask.contiguous()
+    n_pred, H, W = out_mask.shape
+    n_tgt, P = tgt_mask.shape[0], pts.shape[0]
+    cost = torch.empty(n_pred, n_tgt, device=out_mask.device, dtype=torch.float32)
+    if n_pred == 0 or n_tgt == 0:
+        return cost
+    need = _lib.lib().wg_match_cost_workspace_bytes(n_pred, n_tgt, P)
+    ws = torch.empty(need, dtype=torch.uint8, device=out_mask.device)
+    _lib.check(_lib.lib().wg_match_cost(out_mask.data_ptr(), tgt_mask.data_ptr(), int(tgt_mask.dtype == torch.uint8), pts.data_ptr(), n_pred, n_tgt, H, W, P,
+                                        cost.data_ptr(), ws.data_ptr(), need, _stream()), "wg_match_cost")
+    return cost
