@@ -149,8 +149,12 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
         }
     }
     float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
+#ifndef ATT_DBG_NOMAX  // debug builds (wrong results): knock one phase out to measure what it costs
 #pragma unroll
     for (int i = 0; i < NCH * 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv(i)));
+#else
+    mx4[0] = 0.f;
+#endif
     float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     if constexpr (SPLIT == 2) {
         // the two threads of a row agree on the block maximum through smem (double-buffered by block parity: one 64-thread
@@ -181,7 +185,11 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
             for (int k = 0; k < 4; ++k) {  // column pairs: packed scale-and-shift, then MUFU or polynomial
                 const int i = g * 8 + k * 2;
                 float x0, x1, e0, e1;
+#ifndef ATT_DBG_NOSCALE
                 upk2(ffma2(pk2(__uint_as_float(sv(i)), __uint_as_float(sv(i + 1))), SC2, NM2), x0, x1);  // -inf for masked keys -> 0
+#else
+                x0 = __uint_as_float(sv(i)); x1 = __uint_as_float(sv(i + 1));
+#endif
 #ifdef ATT_DBG_NOEXP  // debug build: no exponentials at all (wrong results) -- measures what the rest of the block costs
                 if (true) { e0 = x0; e1 = x1; } else
 #endif
@@ -197,10 +205,14 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
         }
         if (g >= 1) {  // row sum + bf16 packing of the previous group, in place (4 packed words at its first 4 registers)
             const int b = (g - 1) * 8;
+#ifndef ATT_DBG_NOSUM
             rsA = fadd2(rsA, pk2(__uint_as_float(sv(b + 0)), __uint_as_float(sv(b + 1))));
             rsB = fadd2(rsB, pk2(__uint_as_float(sv(b + 2)), __uint_as_float(sv(b + 3))));
             rsA = fadd2(rsA, pk2(__uint_as_float(sv(b + 4)), __uint_as_float(sv(b + 5))));
             rsB = fadd2(rsB, pk2(__uint_as_float(sv(b + 6)), __uint_as_float(sv(b + 7))));
+#else
+            if (b == 0) rsA = fadd2(rsA, pk2(__uint_as_float(sv(b + 0)), __uint_as_float(sv(b + 1))));
+#endif
             const uint32_t w0 = pack_bf16x2(__uint_as_float(sv(b + 0)), __uint_as_float(sv(b + 1)));
             const uint32_t w1 = pack_bf16x2(__uint_as_float(sv(b + 2)), __uint_as_float(sv(b + 3)));
             const uint32_t w2 = pack_bf16x2(__uint_as_float(sv(b + 4)), __uint_as_float(sv(b + 5)));
