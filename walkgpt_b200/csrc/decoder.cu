@@ -31,50 +31,61 @@ constexpr int TK_KEY_GROUPS = TK_THREADS / 16;  // token->image attention: 16 di
 
 
 // out[t][n] = act( base + sum_k in[t][k] * Wt[k][n] ), t < NT.   in/out in shared memory, Wt fp32 [K][N] in global.
-// base = bias[n] (+ out[t][n] when `accumulate`).  Split-K over thread groups; the partial sums go through `part`
-// (>= TK_THREADS * 2 * NT floats of shared memory) and are added in a fixed order, so results are run-to-run deterministic.
-constexpr int TOK_PART_FLOATS = TK_THREADS * 2 * NT;
-__device__ void tok_linear(const float* in, int ldi, int K, const float* __restrict__ Wt, const float* __restrict__ bias, float* out,
-                           int ldo, int N, bool accumulate, bool relu, float* part) {
+// base = bias[n] (+ out[t][n] when `accumulate`).  Split-K over thread groups; the partial sums go through `part` and are added
+// in a fixed order, so results are run-to-run deterministic.  The kernel is bound by the latency of the weight stream from L2
+// (every CTA reads the layer's 6 MB): VEC = 4 issues 16-byte loads, four per thread in flight, and needs 2x the partial-sum
+// buffer; it is used whenever that fits next to the score buffer (hw <= 2048), VEC = 2 otherwise.
+template <int VEC>
+__device__ void tok_linear_v(const float* in, int ldi, int K, const float* __restrict__ Wt, const float* __restrict__ bias, float* out,
+                             int ldo, int N, bool accumulate, bool relu, float* part, int part_floats) {
     const int tid = threadIdx.x;
-    const int pairs = N >> 1;
-    int ks = TK_THREADS / pairs;
+    const int groups = N / VEC;
+    int ks = TK_THREADS / groups;
     if (ks < 1) ks = 1;
     if (ks > K) ks = K;
+    if (ks > 1 && ks * NT * N > part_floats) ks = part_floats / (NT * N);
     const int klen = (K + ks - 1) / ks;
-    for (int item = tid; item < pairs * ks; item += TK_THREADS) {
-        const int pr = item % pairs, kpart = item / pairs;
+    for (int item = tid; item < groups * ks; item += TK_THREADS) {
+        const int gr = item % groups, kpart = item / groups;
         const int k0 = kpart * klen;
         const int k1 = min(K, k0 + klen);
-        float a0[NT], a1[NT];
+        float acc[VEC][NT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) a0[t] = a1[t] = 0.f;
-        const float* wp = Wt + (size_t)k0 * N + pr * 2;
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[v][t] = 0.f;
+        const float* wp = Wt + (size_t)k0 * N + gr * VEC;
 #pragma unroll 4
         for (int k = k0; k < k1; ++k, wp += N) {
-            const float2 w = __ldg(reinterpret_cast<const float2*>(wp));
+            float w[VEC];
+            if constexpr (VEC == 4) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(wp));
+                w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+            } else {
+                const float2 u = __ldg(reinterpret_cast<const float2*>(wp));
+                w[0] = u.x; w[1] = u.y;
+            }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const float x = in[t * ldi + k];
-                a0[t] = fmaf(x, w.x, a0[t]);
-                a1[t] = fmaf(x, w.y, a1[t]);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v][t] = fmaf(x, w[v], acc[v][t]);
             }
         }
         if (ks == 1) {  // this thread owns the whole dot product
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                float b0v = bias ? bias[pr * 2] : 0.f, b1v = bias ? bias[pr * 2 + 1] : 0.f;
-                float v0 = a0[t] + b0v + (accumulate ? out[t * ldo + pr * 2] : 0.f);
-                float v1 = a1[t] + b1v + (accumulate ? out[t * ldo + pr * 2 + 1] : 0.f);
-                out[t * ldo + pr * 2] = relu ? fmaxf(v0, 0.f) : v0;
-                out[t * ldo + pr * 2 + 1] = relu ? fmaxf(v1, 0.f) : v1;
-            }
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const int n = gr * VEC + v;
+                    const float r = acc[v][t] + (bias ? bias[n] : 0.f) + (accumulate ? out[t * ldo + n] : 0.f);
+                    out[t * ldo + n] = relu ? fmaxf(r, 0.f) : r;
+                }
         } else {
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                part[(kpart * NT + t) * N + pr * 2] = a0[t];
-                part[(kpart * NT + t) * N + pr * 2 + 1] = a1[t];
-            }
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) part[(kpart * NT + t) * N + gr * VEC + v] = acc[v][t];
         }
     }
     __syncthreads();
@@ -87,6 +98,15 @@ __device__ void tok_linear(const float* in, int ldi, int K, const float* __restr
         }
         __syncthreads();
     }
+}
+struct TokPart {
+    float* buf;
+    int floats;  // TK_THREADS * 2 * NT (VEC = 2) or twice that (VEC = 4)
+};
+__device__ __forceinline__ void tok_linear(const float* in, int ldi, int K, const float* __restrict__ Wt, const float* __restrict__ bias, float* out,
+                                           int ldo, int N, bool accumulate, bool relu, TokPart part) {
+    if (part.floats >= TK_THREADS * 4 * NT && (N & 3) == 0) tok_linear_v<4>(in, ldi, K, Wt, bias, out, ldo, N, accumulate, relu, part.buf, part.floats);
+    else tok_linear_v<2>(in, ldi, K, Wt, bias, out, ldo, N, accumulate, relu, part.buf, part.floats);
 }
 
 // in-place LayerNorm over C=256 for the NT token rows (warp t handles row t)
@@ -224,6 +244,7 @@ __device__ void tok_t2i_attention(const float* Qt, const float* __restrict__ kv,
 
 struct TokArgs {
     int phase, hw, n_mask_tokens;
+    int part_floats;                     // split-K buffer of tok_linear: TK_THREADS * NT * 2 or * 4 floats
     wg_twoway_layer L;                   // weights of this layer (phases 0/1)
     // final-phase weights
     const void* fin_wq_t; const float* fin_bq; const void* fin_wo_t; const float* fin_bo; const float* nf_g; const float* nf_b;
@@ -250,8 +271,8 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
     float* b2 = b1 + NT * C;
     float* b3 = b2 + NT * C;
     float* big = b3 + NT * C;      // [NT][2048]
-    float* part = big + NT * 2048;       // [TOK_PART_FLOATS] split-K partial sums
-    float* sc = part + TOK_PART_FLOATS;  // [NT][max(hw, 48)]
+    const TokPart part = {big + NT * 2048, a.part_floats};  // split-K partial sums
+    float* sc = part.buf + a.part_floats;                   // [NT][max(hw, 48)]
     const int p = blockIdx.x;
     const int tid = threadIdx.x;
     const float* kv = a.kv + (size_t)p * a.hw * a.ldkv;
@@ -295,7 +316,7 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
         // ---- (2) tokens attend to the image
         tok_add(b3, q, qpe, NT * C);
         tok_linear(b3, C, C, (const float*)L.t2i_wq_t, L.t2i_bq, b0, CI, CI, false, false, part);
-        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part);
+        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part.buf);
         tok_linear(b1, CI, CI, (const float*)L.t2i_wo_t, L.t2i_bo, q, C, C, true, false, part);
         tok_layernorm(q, L.n2_g, L.n2_b, 1e-5f);
         // ---- (3) MLP
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
         // ---- final token->image attention, LayerNorm, hypernetworks, IoU head
         tok_add(b3, q, qpe, NT * C);
         tok_linear(b3, C, C, (const float*)a.fin_wq_t, a.fin_bq, b0, CI, CI, false, false, part);
-        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part);
+        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part.buf);
         tok_linear(b1, CI, CI, (const float*)a.fin_wo_t, a.fin_bo, q, C, C, true, false, part);
         tok_layernorm(q, a.nf_g, a.nf_b, 1e-5f);
         for (int i = tid; i < NT * C; i += TK_THREADS) a.Tq[(size_t)p * NT * C + i] = q[i];
@@ -746,12 +767,15 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     }
     WG_CHECK_CUDA(cudaGetLastError());
 
-    const size_t tk_smem = (size_t)(6 * NT * C + NT * 2048 + TOK_PART_FLOATS + NT * (hw > 48 ? hw : 48)) * sizeof(float);
+    const size_t tk_fixed = (size_t)(6 * NT * C + NT * 2048 + NT * (hw > 48 ? hw : 48)) * sizeof(float);
+    const int tk_part = (tk_fixed + (size_t)TK_THREADS * 4 * NT * sizeof(float) <= 227 * 1024) ? TK_THREADS * 4 * NT : TK_THREADS * 2 * NT;
+    const size_t tk_smem = tk_fixed + (size_t)tk_part * sizeof(float);
     WG_CHECK_CUDA(cudaFuncSetAttribute(decoder_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     WG_REQUIRE(tk_smem <= 227 * 1024, "wg_mask_decoder_forward: token kernel shared memory %zu too large", tk_smem);
 
     TokArgs ta = {};
     ta.hw = hw;
+    ta.part_floats = tk_part;
     ta.n_mask_tokens = w->n_mask_tokens;
     ta.fin_wq_t = w->fin_wq_t; ta.fin_bq = w->fin_bq; ta.fin_wo_t = w->fin_wo_t; ta.fin_bo = w->fin_bo; ta.nf_g = w->nf_g; ta.nf_b = w->nf_b;
     ta.hyp_w0_t = w->hyp_w0_t; ta.hyp_w1_t = w->hyp_w1_t; ta.hyp_w2_t = w->hyp_w2_t;
