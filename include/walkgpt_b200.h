@@ -90,7 +90,14 @@ typedef struct wg_gemm_args {
      * split_out != 0: bf16 output modes write split-bf16 [M, 2N] (ldo >= 2N); in WG_OUT_BF16_LN `resid` is then split-bf16 too. */
     int32_t a_k_wrap;
     int32_t split_out;
-    int32_t reserved;
+    /* Implicit 3x3 / pad 1 convolution (conv_grid = g > 0): A is a channels-last map bf16 [M / g^2 images, g, g, lda] and the
+     * GEMM's k index runs over (term, tap = ky*3+kx, channel < conv_channels): k-block (term, tap, c) of output positions
+     * m0..m0+127 is ONE 4-D TMA box of the map shifted by (kx-1, ky-1), out-of-range neighbours zero-filled by the TMA unit --
+     * no im2col matrix is ever written.  term selects the hi / lo half of a split-bf16 map (channel offset term * conv_channels,
+     * after the a_k_wrap fold, which then counts in units of 9 * conv_channels).  Needs 128 % g == 0, g^2 % 128 == 0,
+     * conv_channels % 64 == 0, K % (9 * conv_channels) == 0; 1-CTA kernels only. */
+    int32_t conv_grid;
+    int32_t conv_channels;
 } wg_gemm_args;
 
 /* tcgen05/TMEM + TMA bf16 GEMM with fused epilogue.  Requirements: K % 8 == 0, lda/ldw % 8 == 0,

@@ -204,6 +204,39 @@ def test_projector_and_neck_against_reference_golden():
     assert rel_err(m.neck(g["proj"].permute(0, 2, 1).reshape(2, g["hidden"], 8, 8).to(DEV)), g["emb"]) < 1e-4  # the neck itself: near-fp32
 
 
+@pytest.mark.parametrize("grid", [16, 32])
+def test_neck_implicit_conv_against_oracle_and_im2col(grid):
+    """The neck's 3x3 convolution as an implicit GEMM (shifted 4-D TMA boxes, zero-filled borders: grids 16 and 32) against the
+    fp32 oracle (walkgpt.py:97-113) at the neck's near-fp32 accuracy, and bit-identical to the explicit im2col path."""
+    import subprocess, sys, textwrap
+    hidden, B = 64, 3
+    sd = {"image_feature_neck." + k: v for k, v in specs.make_state_dict(specs.neck_spec(hidden, 256), seed=21).items()}
+    sd.update({"out_mm_projector." + k: v for k, v in specs.make_state_dict(specs.out_mm_projector_spec(128, hidden), seed=21).items()})
+    m = load_into(M.ProjectorNeck(128, hidden, 256), sd)
+    x = rnd((B, grid * grid, hidden), 77)
+    ref = path_a.image_feature_neck({k[len("image_feature_neck."):]: v for k, v in sd.items() if k.startswith("image_feature_neck.")}, x, grid)
+    x_nchw = x.permute(0, 2, 1).reshape(B, hidden, grid, grid).contiguous()
+    got = m.neck(x_nchw.to(DEV))
+    assert rel_err(got, ref) < 1e-4
+    code = textwrap.dedent("""
+        import sys, torch
+        sys.path.insert(0, sys.argv[3])
+        from walkgpt_b200 import specs
+        from walkgpt_b200 import modules as M
+        grid = int(sys.argv[2]); hidden, B = 64, 3
+        sd = {"image_feature_neck." + k: v for k, v in specs.make_state_dict(specs.neck_spec(hidden, 256), seed=21).items()}
+        sd.update({"out_mm_projector." + k: v for k, v in specs.make_state_dict(specs.out_mm_projector_spec(128, hidden), seed=21).items()})
+        m = M.ProjectorNeck(128, hidden, 256); m.load_state_dict(sd, strict=True); m = m.to("cuda")
+        g = torch.Generator().manual_seed(77)
+        x = torch.randn(B, grid * grid, hidden, generator=g)
+        torch.save(m.neck(x.permute(0, 2, 1).reshape(B, hidden, grid, grid).contiguous().cuda()).cpu(), sys.argv[1])
+    """)
+    path = f"/tmp/wg_neck_im2col_{grid}.pt"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code, path, str(grid), root], check=True, env=dict(os.environ, WG_NECK_IM2COL="1"))
+    assert torch.equal(torch.load(path), got.cpu())
+
+
 @pytest.mark.parametrize("grid", [8, 32])
 def test_prompt_encoder_and_mask_decoder_against_reference_golden(grid):
     g = load(f"decoder_ms_g{grid}")

@@ -1,5 +1,7 @@
 // A5 Calibrated Text Projector (utils/utils_walkgpt.py:321-327), A3 out_mm_projector MLP (llava_arch.py:38-42) and
 // A4 image_feature_neck (model/walkgpt.py:97-113): GEMMs from gemm.cu plus the small row-wise tails defined here.
+#include <stdlib.h>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -159,6 +161,13 @@ extern "C" int wg_ctp_forward(const wg_ctp_weights* w, const void* x, int x_is_b
 
 // neck, computed at near-fp32 accuracy with split-bf16 operands (see wg_gemm_args): 1x1 conv (GEMM) + LayerNorm2d fused in
 // the epilogue; 3x3 conv as im2col GEMM + LayerNorm2d epilogue.  pr: split-bf16 [rows, 2H]; emb: split-bf16 [rows, 512].
+// implicit-GEMM 3x3 convolution needs whole map rows per 128-position GEMM tile (wg_gemm_args.conv_grid); WG_NECK_IM2COL=1 forces
+// the explicit im2col matrix (A/B switch for tests)
+static bool neck_conv_implicit(int g) {
+    static const bool off = getenv("WG_NECK_IM2COL") != nullptr && atoi(getenv("WG_NECK_IM2COL")) != 0;
+    return !off && g > 0 && 128 % g == 0 && (g * g) % 128 == 0;
+}
+
 static int neck_impl(const wg_proj_neck_weights* w, const void* pr, int B, int grid_side, void* emb_tokens_split, void* n1, void* col,
                      cudaStream_t s) {
     const int rows = B * grid_side * grid_side;
@@ -171,7 +180,10 @@ static int neck_impl(const wg_proj_neck_weights* w, const void* pr, int B, int g
         a.out_mode = WG_OUT_BF16_LN; a.split_out = 1; a.out = n1; a.ldo = 512; a.ln_gamma = w->ln1_g; a.ln_beta = w->ln1_b; a.ln_eps = 1e-6f;
         WG_TRY(wg_gemm(&a, s));
     }
-    {
+    // 3x3 convolution: implicit GEMM (the A operand is the channels-last map itself, read through shifted 4-D TMA boxes) when
+    // the grid allows whole rows per 128-position tile; small test grids go through an explicit im2col matrix
+    const bool implicit = neck_conv_implicit(grid_side);
+    if (!implicit) {
         const long long total = (long long)rows * (9 * 256 / 8);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
@@ -184,8 +196,13 @@ static int neck_impl(const wg_proj_neck_weights* w, const void* pr, int B, int g
     }
     {
         wg_gemm_args a = {};
-        a.A = col; a.lda = 2 * 2304; a.W = w->w_conv3; a.ldw = (long long)T * 2304; a.M = rows; a.N = 256; a.K = T * 2304;
+        a.W = w->w_conv3; a.ldw = (long long)T * 2304; a.M = rows; a.N = 256; a.K = T * 2304;
         a.a_k_wrap = T == 3 ? 2 * 2304 : 0;
+        if (implicit) {
+            a.A = n1; a.lda = 512; a.conv_grid = grid_side; a.conv_channels = 256;
+        } else {
+            a.A = col; a.lda = 2 * 2304;
+        }
         a.out_mode = WG_OUT_BF16_LN; a.split_out = 1; a.out = emb_tokens_split; a.ldo = 512; a.ln_gamma = w->ln2_g; a.ln_beta = w->ln2_b;
         a.ln_eps = 1e-6f;
         WG_TRY(wg_gemm(&a, s));

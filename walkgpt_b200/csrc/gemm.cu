@@ -71,6 +71,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                 int ka = kb * BK;
                 if (p.a_k_wrap > 0 && ka >= p.a_k_wrap) ka -= p.a_k_wrap;  // K' <= 2 * wrap by construction
+                if (p.conv_g > 0) {
+                    // implicit 3x3 convolution: k-block = (term, tap, 64-channel slice); the 128 output positions of this tile are
+                    // 128 / g full rows of one image, their (kx-1, ky-1)-shifted neighbours one 4-D box (zero-filled outside the map)
+                    const int per_term = 9 * p.conv_c;
+                    const int term = ka / per_term, r = ka - term * per_term;
+                    const int tap = r / p.conv_c, c = r - tap * p.conv_c;
+                    const int gg = p.conv_g * p.conv_g;
+                    const int img = m0 / gg, y0 = (m0 - img * gg) / p.conv_g;
+                    tma_load_4d(smem + L::OFF_A + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], term * p.conv_c + c, tap % 3 - 1, y0 + tap / 3 - 1, img);
+                } else
                 tma_load_2d(smem + L::OFF_A + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], ka, m0);
                 tma_load_2d(smem + L::OFF_B + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
                 if (++stage == STAGES) {
@@ -146,7 +156,15 @@ template <int BN, int STAGES, int EPI>
 int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     using L = SmemLayout<BN, STAGES>;
     CUtensorMap tmA, tmB, tmC;
-    WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->a_k_wrap > 0 ? a->a_k_wrap : a->K, a->lda, BM, BK));
+    if (a->conv_grid > 0) {
+        const uint64_t g = (uint64_t)a->conv_grid, terms = a->a_k_wrap > 0 ? 2 : (uint64_t)a->K / (9 * (uint64_t)a->conv_channels);
+        uint64_t dims[4] = {terms * (uint64_t)a->conv_channels, g, g, (uint64_t)a->M / (g * g)};
+        uint64_t strides[3] = {(uint64_t)a->lda * 2, g * (uint64_t)a->lda * 2, g * g * (uint64_t)a->lda * 2};
+        uint32_t box[4] = {(uint32_t)BK, (uint32_t)g, (uint32_t)(BM / a->conv_grid), 1};
+        WG_TRY(make_tensor_map(&tmA, a->A, 2, 4, dims, strides, box));
+    } else {
+        WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->a_k_wrap > 0 ? a->a_k_wrap : a->K, a->lda, BM, BK));
+    }
     WG_TRY(make_tmap_2d_bf16(&tmB, a->W, a->N, a->K, a->ldw, BN, BK));
     if (EPI != WG_OUT_F32) {
         WG_TRY(make_tmap_2d_bf16(&tmC, a->out, a->M, a->split_out ? 2 * a->N : a->N, a->ldo, BM, 64));
@@ -171,6 +189,8 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     p.ln_beta = a->ln_beta;
     p.ln_eps = a->ln_eps;
     p.a_k_wrap = a->a_k_wrap;
+    p.conv_g = a->conv_grid;
+    p.conv_c = a->conv_channels;
     p.split_out = (EPI != WG_OUT_F32) ? a->split_out : 0;
 
     auto kern = gemm_bf16_kernel<BN, STAGES, EPI>;
@@ -209,6 +229,13 @@ extern "C" int wg_gemm(const wg_gemm_args* a, void* stream_) {
                "wg_gemm: a_k_wrap=%d must be a multiple of 64 with a_k_wrap < K <= 2*a_k_wrap (K=%d)", a->a_k_wrap, a->K);
     WG_REQUIRE(!a->split_out || (a->out_mode != WG_OUT_F32 && a->N % 64 == 0 && a->ldo >= 2 * (long long)a->N),
                "wg_gemm: split_out needs a bf16 output mode, N %% 64 == 0 and ldo >= 2N");
+    if (a->conv_grid > 0) {
+        const long long g = a->conv_grid, cc = a->conv_channels;
+        WG_REQUIRE(128 % g == 0 && (g * g) % 128 == 0 && a->M % (g * g) == 0, "wg_gemm: conv_grid=%d needs 128 %% g == 0, g^2 %% 128 == 0 and M a multiple of g^2", a->conv_grid);
+        WG_REQUIRE(cc > 0 && cc % 64 == 0 && a->K % (9 * cc) == 0, "wg_gemm: conv_channels=%d must be a multiple of 64 and divide K / 9", a->conv_channels);
+        WG_REQUIRE(a->a_k_wrap == 0 || a->a_k_wrap == 18 * cc, "wg_gemm: with conv_grid, a_k_wrap must be 2 * 9 * conv_channels");
+        WG_REQUIRE(a->lda >= (a->a_k_wrap > 0 ? 2 : a->K / (9 * cc)) * cc, "wg_gemm: conv map row pitch lda too small");
+    }
     if (!device_is_sm100()) {
         set_error("wg_gemm: this library only runs on sm_100 (B200) devices; there is no fallback");
         return WG_ERR_UNSUPPORTED;
@@ -221,7 +248,7 @@ extern "C" int wg_gemm(const wg_gemm_args* a, void* stream_) {
         pair_enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
     }
     const long long tiles_pair = (long long)((a->M + 255) / 256) * ((a->N + 255) / 256);
-    const bool use_pair = pair_enabled && (a->N % 256 == 0) && tiles_pair >= device_sm_count() / 2;
+    const bool use_pair = pair_enabled && a->conv_grid == 0 && (a->N % 256 == 0) && tiles_pair >= device_sm_count() / 2;
     switch (a->out_mode) {
         case WG_OUT_BF16: {
             WG_REQUIRE(a->ldo % 8 == 0, "wg_gemm: bf16 output needs ldo %% 8 == 0");

@@ -31,6 +31,7 @@ struct GemmParams {
     const float* ln_gamma;
     const float* ln_beta;
     float ln_eps;
+    int conv_g, conv_c;  // implicit 3x3 convolution over a channels-last g x g map with conv_c channels per term (conv_g = 0: off)
     int a_k_wrap;   // A's k coordinate wraps at this many columns (0 = off): A' = [hi | lo | hi] of a split-bf16 operand
     int split_out;  // bf16 outputs are written as split-bf16: hi at column c, lo = bf16(x - hi) at column N + c
 };

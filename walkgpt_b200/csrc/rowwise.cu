@@ -137,6 +137,41 @@ __global__ void __launch_bounds__(256) im2col_patch_kernel(const TIn* __restrict
     }
 }
 
+// Same mapping, one CTA per (image, patch row): the 3 x P image rows the patch row needs are read as coalesced 32-bit words (two
+// pixels; P is even) and scattered into a shared-memory copy of the G output rows, which then goes out with 16-byte stores.
+// Needs P % 2 == 0, IMG % 2 == 0 and KPAD % 8 == 0 (CLIP-L/14@448: P 14, IMG 448, KPAD 640); other shapes use the kernel above.
+template <typename TIn>
+__global__ void __launch_bounds__(256) im2col_patch_rows_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ out, int IMG, int P, int KPAD) {
+    extern __shared__ __align__(16) uint32_t rowbuf[];  // [G][pitch] words; pitch = KPAD / 2 + 4 keeps rows 16-byte aligned and
+    const int G = IMG / P;                              // spreads the scattered word stores over the banks
+    const int py = blockIdx.x, b = blockIdx.y;
+    const int pitch = KPAD / 2 + 4;
+    const int HP = P / 2, words_per_row = IMG / 2, kv_words = 3 * P * P / 2;
+    for (int i = threadIdx.x; i < 3 * P * words_per_row; i += 256) {
+        const int r = i / words_per_row, j = i - r * words_per_row;  // r = c * P + dy, j = word within the image row
+        const int c = r / P, dy = r - c * P;
+        const int pxi = j / HP, dxp = j - pxi * HP;
+        const TIn* src = px + (((size_t)b * 3 + c) * IMG + (py * P + dy)) * IMG + 2 * j;
+        uint32_t w;
+        if constexpr (sizeof(TIn) == 2) {
+            w = __ldg(reinterpret_cast<const uint32_t*>(src));
+        } else {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(src));
+            w = pack_bf16x2(a.x, a.y);
+        }
+        rowbuf[pxi * pitch + (c * P * P + dy * P) / 2 + dxp] = w;
+    }
+    const int pad_words = KPAD / 2 - kv_words;
+    for (int i = threadIdx.x; i < G * pad_words; i += 256) rowbuf[(i / pad_words) * pitch + kv_words + i % pad_words] = 0u;
+    __syncthreads();
+    const int vec_per_patch = KPAD / 8;
+    __nv_bfloat16* orow = out + ((size_t)b * G * G + (size_t)py * G) * KPAD;
+    for (int i = threadIdx.x; i < G * vec_per_patch; i += 256) {
+        const int pxi = i / vec_per_patch, k8 = i - pxi * vec_per_patch;
+        *reinterpret_cast<uint4*>(orow + (size_t)pxi * KPAD + k8 * 8) = *reinterpret_cast<const uint4*>(rowbuf + pxi * pitch + k8 * 4);
+    }
+}
+
 // x[b, 0] = LN(cls + pos[0]);  x[b, 1+i] = LN(patch_emb[b*L + i] + pos[1+i])   (D = 1024)
 template <int CH>
 __global__ void __launch_bounds__(256) embed_ln_kernel(const float* __restrict__ patch_emb, const float* __restrict__ cls,
@@ -202,7 +237,19 @@ int launch_im2col_patch(const void* pixels, int is_bf16, void* out_bf16, int B, 
     const int G = IMG / P;
     const long long rows = (long long)B * G * G;
     Prof prof("im2col_patch", s, 0.0, (double)B * 3 * IMG * IMG * (is_bf16 ? 2 : 4) + (double)rows * KPAD * 2);
-    if (is_bf16)
+    const size_t slab_bytes = (size_t)G * (KPAD / 2 + 4) * sizeof(uint32_t);
+    if (P % 2 == 0 && IMG % 2 == 0 && KPAD % 8 == 0 && slab_bytes <= 200 * 1024 && B <= 65535) {
+        const dim3 grid(G, B);
+        if (is_bf16) {
+            static bool attr = false;
+            if (!attr) { WG_CHECK_CUDA(cudaFuncSetAttribute(im2col_patch_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+            im2col_patch_rows_kernel<__nv_bfloat16><<<grid, 256, slab_bytes, s>>>(static_cast<const __nv_bfloat16*>(pixels), static_cast<__nv_bfloat16*>(out_bf16), IMG, P, KPAD);
+        } else {
+            static bool attr = false;
+            if (!attr) { WG_CHECK_CUDA(cudaFuncSetAttribute(im2col_patch_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+            im2col_patch_rows_kernel<float><<<grid, 256, slab_bytes, s>>>(static_cast<const float*>(pixels), static_cast<__nv_bfloat16*>(out_bf16), IMG, P, KPAD);
+        }
+    } else if (is_bf16)
         im2col_patch_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(pixels),
                                                                          static_cast<__nv_bfloat16*>(out_bf16), B, IMG, P, KPAD);
     else
