@@ -12,7 +12,8 @@
 //   full[s]  (L, count 1)  : the leader's producer arrives with expect_tx(64 KB = both CTAs); both CTAs' TMA loads complete_tx on it
 //   empty[s] (per CTA)     : tcgen05.commit multicast from the leader after the MMAs that read stage s
 //   tmem_full[a] (per CTA) : tcgen05.commit multicast after the last k-block of a tile
-//   tmem_empty[a] (L, 16)  : one arrival per epilogue warp of both CTAs
+//   tmem_empty[a] (L, 2)   : one arrival per CTA, forwarded by its warp 3 once the CTA's 8 epilogue warps arrived on epi_done[a] (local):
+//                            the remote arrive costs ~1100-1800 cycles, which the epilogue warps used to pay once per tile
 #include "gemm_common.cuh"
 
 namespace wg {
@@ -27,8 +28,12 @@ constexpr int B_HALF_BYTES = 128 * BK * 2;    // this CTA's half of the W tile
 #ifdef GEMM2_TRACE
 __device__ long long g_gemm2_trace[3][64][4];  // role (0 MMA, 1 producer rank 0, 2 producer rank 1) x k-block x stamp
 #define TR2(role, i, slot) do { if (trace_on && (i) < 64) g_gemm2_trace[role][i][slot] = clock64(); } while (0)
+__device__ long long g_gemm2_epi[16][8];  // per tile of pair 5: MMA warp {0 wait tmem_empty, 1 got it, 2 committed}, epilogue warp 4 of
+                                          // rank 0 {3 wait tmem_full, 4 got it, 5 tile drained}
+#define TRE(i, slot) do { if (trace_pair && (i) < 16) g_gemm2_epi[i][slot] = clock64(); } while (0)
 #else
 #define TR2(role, i, slot) do { } while (0)
+#define TRE(i, slot) do { } while (0)
 #endif
 
 template <int STAGES>
@@ -37,7 +42,7 @@ struct SmemLayout2 {
     static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
     static constexpr int OFF_C = OFF_B + STAGES * B_HALF_BYTES;
     static constexpr int OFF_BAR = OFF_C + 2 * C_BUF_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 4;
+    static constexpr int NUM_BARS = 2 * STAGES + 6;
     static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
 };
@@ -58,6 +63,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint64_t* epi_done = bars + 2 * STAGES + 4;  // [2] local: this CTA's 8 epilogue warps have drained accumulator a
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
@@ -81,7 +87,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 16);  // one arrival per epilogue warp of both CTAs
+            mbar_init(&tmem_empty[a], 2);   // one (forwarded) arrival per CTA of the pair
+            mbar_init(&epi_done[a], 8);     // one arrival per epilogue warp of this CTA
         }
         fence_mbar_init();
     }
@@ -132,7 +139,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
+            TRE(iter, 0);
             mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1);
+            TRE(iter, 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN2;
 #ifdef GEMM2_TRACE
@@ -159,6 +168,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
             umma_commit_cg2(&tmem_full[acc], 0b11);  // accumulators of both CTAs complete -> both epilogues
+            TRE(iter, 2);
         }
     } else if (warp >= 4) {
         // ===================== epilogue: 2 groups x 4 warps per CTA, on this CTA's 128 rows =====================
@@ -172,16 +182,34 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int m0 = (tile / p.num_n_tiles) * (2 * BM) + rank * BM;
             const int n0 = (tile % p.num_n_tiles) * BN2;
+#ifdef GEMM2_TRACE
+            const bool tre = trace_pair && rank == 0 && warp == 4 && lane == 0;
+            if (tre) TRE(iter, 3);
+#endif
             mbar_wait_relaxed(&tmem_full[acc], acc_phase);
+#ifdef GEMM2_TRACE
+            if (tre) TRE(iter, 4);
+#endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
 
             epilogue_tile<BN2, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+#ifdef GEMM2_TRACE
+            if (tre) TRE(iter, 5);
+#endif
+            if (lane == 0) mbar_arrive(&epi_done[acc]);
         }
         if (EPI != WG_OUT_F32 && epi_tid == 0) tma_store_wait_all<0>();
+    } else if (warp == 3 && lane == 0) {
+        // ===================== forwards "accumulator drained" to the leader's MMA warp =====================
+        int iter = 0;
+        for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++iter) {
+            const int acc = iter & 1;
+            mbar_wait_relaxed(&epi_done[acc], (iter >> 1) & 1);
+            mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        }
     }
 
     // neither CTA may leave (or free its TMEM) while the peer can still signal its barriers or read its shared memory
@@ -256,5 +284,8 @@ int launch_gemm_pair(const wg_gemm_args* a, cudaStream_t stream) {
 #ifdef GEMM2_TRACE
 extern "C" __attribute__((visibility("default"))) int wg_debug_gemm2_trace(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, wg::g_gemm2_trace, sizeof(long long) * 3 * 64 * 4);
+}
+extern "C" __attribute__((visibility("default"))) int wg_debug_gemm2_epi(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, wg::g_gemm2_epi, sizeof(long long) * 16 * 8);
 }
 #endif

@@ -131,6 +131,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         // per-warp 32x32 fp32 tile, 16-byte chunks XOR-swizzled by row (conflict-free float4 writes by row and reads by line)
         float* stg = reinterpret_cast<float*>(cbufs) + (grp * 4 + q) * (32 * 32);
         const int rr0 = lane >> 3, cj = lane & 7, cc = cj * 4;
+        // the residual rows of a chunk do not depend on the accumulator: they are requested one chunk ahead (the first chunk's
+        // before the TMEM load), so that their HBM latency overlaps the TMEM load, the transpose and the previous chunk's stores
+        // instead of being paid once per chunk (the epilogue of the K = 1024 out-proj GEMM is longer than its main loop)
+        float4 rsd[8];
+        auto load_resid = [&](int c, float4 (&dst)[8]) {
+            const int gcol = n0 + c * 32 + cc;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int grow = m0 + q * 32 + it * 4 + rr0;
+                dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < p.M && gcol < p.N) dst[it] = *reinterpret_cast<const float4*>(p.resid_f32 + (size_t)grow * p.ldo + gcol);
+            }
+        };
+        if (p.resid_f32) load_resid(grp, rsd);
 #pragma unroll 1
         for (int c = grp; c < BN / 32; c += 2) {
             uint32_t v[32];
@@ -139,6 +153,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
             tmem_ld_wait();
             const int col0 = n0 + c * 32;
             if (col0 >= p.N) continue;
+#ifdef GEMM_DBG_NOEPI  // debug build (wrong results): the fp32 epilogue only drains tensor memory -- what the main loop alone costs
+            if (v[0] != 0x7fc12345u) continue;
+#endif
             add_bias32(v, f, p, row, col0);
             if (p.act != WG_ACT_NONE) {
 #pragma unroll
@@ -149,23 +166,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
                 *reinterpret_cast<float4*>(stg + lane * 32 + ((g ^ (lane & 7)) * 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
             __syncwarp();
             const int gcol = col0 + cc;
-            float4 o[8], rsd[8];
+            float4 o[8], nxt[8];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int grow = m0 + q * 32 + it * 4 + rr0;
+            for (int it = 0; it < 8; ++it)
                 o[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rr0) * 32 + ((cj ^ ((it * 4 + rr0) & 7)) * 4));
-                rsd[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.resid_f32 && grow < p.M && gcol < p.N)
-                    rsd[it] = *reinterpret_cast<const float4*>(p.resid_f32 + (size_t)grow * p.ldo + gcol);
-            }
+            if (p.resid_f32 && c + 2 < BN / 32) load_resid(c + 2, nxt);
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int grow = m0 + q * 32 + it * 4 + rr0;
                 if (grow < p.M && gcol < p.N) {
-                    o[it].x += rsd[it].x; o[it].y += rsd[it].y; o[it].z += rsd[it].z; o[it].w += rsd[it].w;
+                    if (p.resid_f32) { o[it].x += rsd[it].x; o[it].y += rsd[it].y; o[it].z += rsd[it].z; o[it].w += rsd[it].w; }
                     *reinterpret_cast<float4*>(p.out_f32 + (size_t)grow * p.ldo + gcol) = o[it];
                 }
             }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rsd[it] = nxt[it];
             __syncwarp();
         }
     } else {
