@@ -311,7 +311,7 @@ def main():
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     peak = peaks["bf16_sustained"]
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01b_ncu_full_summary.json")
+    tpath = os.path.join(ROOT, "profiles", "r01c_ncu_full_summary.json")
     if os.path.exists(tpath):  # dram__bytes_read+write of the dominant launch (ViT fc1), one `ncu --set full` capture
         tj = json.load(open(tpath))["gemm2_fc1"]
         traffic = tj["dram_bytes"]
