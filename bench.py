@@ -20,6 +20,16 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first communicator
+# when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to the saved one.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 sys.path.insert(0, ROOT)
 
 METRIC = "grounding_images_per_sec_448px_bs64"
@@ -124,7 +134,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{n_img} images x {S_PER_IMG} [SEG] per step, fp32 PyTorch eager, torch {torch.__version__}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -358,7 +368,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         if gather_ms is not None:
             line["gather_ms"] = gather_ms
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
