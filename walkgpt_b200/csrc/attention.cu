@@ -108,6 +108,7 @@ struct AttnParams {
     int n_last;  // keys covered by the last key block, rounded up to 16 (T = 1025: 16 -- the block holds only the 1025th token)
     float scale_log2;
     const uint8_t* key_valid;  // [B, T] or null
+    int n_items, n_full_tiles, batch;  // persistent kernel: work items = (image, head, query tile), full tiles first
 };
 
 struct SoftmaxState {
@@ -124,8 +125,10 @@ struct SoftmaxState {
 // the MUFU-paced stretch).  The wait for the previous PV MMA (P buffer free) sits in the middle of the phase: the first 64
 // columns are packed into registers before it, so that the tensor core's latency is covered by exponentials, not by a stall.
 template <int NCH, int POLY, int SPLIT>
-__device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const AttnParams& p, const uint32_t* kmask, uint32_t tmem_S, uint32_t tmem_O,
+__device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, int gblk, const AttnParams& p, const uint32_t* kmask, uint32_t tmem_S, uint32_t tmem_O,
                                               uint32_t tmem_P, uint32_t lane_off, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready, int tr, int half, int r, float* xch) {
+    // j = key block within the current query tile; gblk = key blocks this CTA has processed before it (barrier phases; == j in
+    // the one-tile-per-CTA kernel, a running count in the persistent one)
     // NCH = number of 32-column chunks THIS thread handles (SPLIT = 2: the thread owns columns [64 half, 64 half + 32 NCH))
     constexpr int NG = NCH * 4;                  // groups of 8 columns
     constexpr int HALF_NG = 4 * (4 / SPLIT) / 2; // the P-buffer wait happens once this many groups are packed (half a full row share)
@@ -222,7 +225,7 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, const Att
         if (g == WAIT_AT) {
             if (j > 0) {
                 TR(0, j, 3);
-                mbar_wait(p_free, (j - 1) & 1);  // PV_{j-1} finished: P buffer free, O quiescent
+                mbar_wait(p_free, (gblk - 1) & 1);  // PV_{j-1} finished: P buffer free, O quiescent
                 TR(0, j, 4);
                 if (__any_sync(0xffffffffu, refresh)) {
                     tc_fence_after();
@@ -455,7 +458,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             const int nch_tot = (ncols + 31) >> 5;                       // 32-column chunks that hold keys in this block
             int nch = nch_tot - half * 2;                                // ... of which this thread owns
             nch = nch < 0 ? 0 : (nch > 4 / SPLIT ? 4 / SPLIT : nch);
-#define WG_SM_ARGS st, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr, half, r, xch
+#define WG_SM_ARGS st, j, j, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr, half, r, xch
             if constexpr (SPLIT == 1) {
                 if (nch == 4) softmax_block<4, POLY, 1>(WG_SM_ARGS);
                 else if (nch == 3) softmax_block<3, POLY, 1>(WG_SM_ARGS);
@@ -504,6 +507,291 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tma_store_commit();
             tma_store_wait_all<0>();
         }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Persistent variant: 2 CTAs per SM, each walking a strided list of (image, head, query tile) items with barriers, tensor memory
+// and the K/V rings kept alive across items.  A one-tile CTA costs ~2.1 us of launch, TMEM allocation, first Q/K load latency and
+// O drain next to 1.6 us per key block (14 % of the kernel at the CLIP length); here the next item's Q and first K block are
+// requested while the current item's last key blocks are processed, S_0 of the next item is issued as soon as the last S has been
+// pulled into registers, and the O tile leaves through the (finished) Q buffer while the next item's first key block is computed.
+// Two Q buffers: Q_it lives in buffer it & 1, which then stages O_it; it is handed back to the producer (q_free) by the storing
+// thread once the bulk store has read it, one item later.  Needs >= 4 key blocks per tile (the hand-backs assume it).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int PQ_OFF_Q = 0;                              // 2 buffers
+constexpr int PQ_OFF_K = PQ_OFF_Q + 2 * TILE_BYTES;      // 2 stages
+constexpr int PQ_OFF_V = PQ_OFF_K + 2 * TILE_BYTES;      // 2 stages
+constexpr int PQ_OFF_BAR = PQ_OFF_V + 2 * TILE_BYTES;
+constexpr int PQ_NUM_BARS = 16;
+constexpr int PQ_OFF_KMASK = PQ_OFF_BAR + PQ_NUM_BARS * 8 + 16;
+constexpr int PQ_SMEM_BYTES = PQ_OFF_KMASK + (ATT_MAX_T / 32) * 4;
+
+struct AttnItem {
+    int qt, head, img;
+};
+__device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int w) {
+    AttnItem it;
+    const int full = p.batch * p.heads * p.n_full_tiles;
+    if (w < full) {
+        it.qt = w % p.n_full_tiles;
+        const int r = w / p.n_full_tiles;
+        it.head = r % p.heads;
+        it.img = r / p.heads;
+    } else {  // the partial last tile of every (image, head) comes after all full tiles: short items fill the end of the schedule
+        const int r = w - full;
+        it.qt = p.n_full_tiles;
+        it.head = r % p.heads;
+        it.img = r / p.heads;
+    }
+    return it;
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(192, 2)
+attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PQ_OFF_BAR);
+    uint64_t* q_full = bars + 0;    // [2]
+    uint64_t* q_free = bars + 2;    // [2]  O tile staged in this Q buffer has been read by its bulk store
+    uint64_t* k_full = bars + 4;    // [2]
+    uint64_t* v_full = bars + 6;    // [2]
+    uint64_t* k_empty = bars + 8;   // [2]
+    uint64_t* v_empty = bars + 10;  // [2]
+    uint64_t* s_full = bars + 12;
+    uint64_t* s_free = bars + 13;
+    uint64_t* p_ready = bars + 14;
+    uint64_t* p_free = bars + 15;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + PQ_NUM_BARS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int HD = p.heads * ATT_D;
+    const int nkb = p.num_kv_blocks;
+    const int stride = gridDim.x;
+    const int tr = -1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmO);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&q_full[s], 1);
+            mbar_init(&q_free[s], 1);
+            mbar_init(&k_full[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 128);
+        mbar_init(p_ready, 128);
+        mbar_init(p_free, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base;
+    const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_P = tmem_base + 192;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int g = 0, it = 0;
+            for (int w = blockIdx.x; w < p.n_items; w += stride, ++it) {
+                const AttnItem cur = attn_item(p, w);
+                const bool has_next = w + stride < p.n_items;
+                const AttnItem nxt = has_next ? attn_item(p, w + stride) : cur;
+                if (it == 0) {
+                    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
+                    tma_load_3d(smem + PQ_OFF_Q, &tmQKV, &q_full[0], cur.head * ATT_D, cur.qt * ATT_BQ, cur.img);
+                    mbar_arrive_expect_tx(&k_full[0], TILE_BYTES);
+                    tma_load_3d(smem + PQ_OFF_K, &tmQKV, &k_full[0], HD + cur.head * ATT_D, 0, cur.img);
+                }
+                for (int j = 0; j < nkb; ++j, ++g) {
+                    // K of the next key block of this CTA's stream: this tile's block j + 1, or block 0 of the next item
+                    const bool last = j + 1 == nkb;
+                    if (!last || has_next) {
+                        const int s1 = (g + 1) & 1;
+                        mbar_wait_relaxed(&k_empty[s1], (((g + 1) >> 1) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&k_full[s1], TILE_BYTES);
+                        if (!last) tma_load_3d(smem + PQ_OFF_K + s1 * TILE_BYTES, &tmQKV, &k_full[s1], HD + cur.head * ATT_D, (j + 1) * ATT_BKV, cur.img);
+                        else tma_load_3d(smem + PQ_OFF_K + s1 * TILE_BYTES, &tmQKV, &k_full[s1], HD + nxt.head * ATT_D, 0, nxt.img);
+                    }
+                    const int s = g & 1;
+                    mbar_wait_relaxed(&v_empty[s], ((g >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+                    tma_load_3d(smem + PQ_OFF_V + s * TILE_BYTES, &tmQKV, &v_full[s], 2 * HD + cur.head * ATT_D, j * ATT_BKV, cur.img);
+                    if (last && has_next) {
+                        // Q of the next item into the other buffer; from the third item on that buffer last staged an O tile
+                        const int qb = (it + 1) & 1;
+                        if (it + 1 >= 2) mbar_wait_relaxed(&q_free[qb], (((it + 1) >> 1) - 1) & 1);
+                        mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES);
+                        tma_load_3d(smem + PQ_OFF_Q + qb * TILE_BYTES, &tmQKV, &q_full[qb], nxt.head * ATT_D, nxt.qt * ATT_BQ, nxt.img);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform protocol, one elected lane issues) =====================
+        constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, false, false);
+        constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 64, false, true);
+        const uint32_t idesc_s_last = umma_idesc_bf16(128, p.n_last, false, false);
+        const int pv_steps_last = p.n_last / 16;
+        const uint64_t q_desc0 = umma_desc_sw128(smem_u32(smem + PQ_OFF_Q));
+        const uint64_t k_desc0 = umma_desc_sw128(smem_u32(smem + PQ_OFF_K));
+        const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + PQ_OFF_V));
+        int g = 0, it = 0;
+        for (int w = blockIdx.x; w < p.n_items; w += stride, ++it) {
+            const bool has_next = w + stride < p.n_items;
+            if (it == 0) {
+                mbar_wait(&q_full[0], 0);
+                mbar_wait(&k_full[0], 0);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc0 + k * 2, k_desc0 + k * 2, IDESC_S, k != 0);
+                    umma_commit(s_full);
+                    umma_commit(&k_empty[0]);
+                }
+                __syncwarp();
+            }
+            for (int j = 0; j < nkb; ++j, ++g) {
+                const bool last = j + 1 == nkb;
+                if (!last || has_next) {
+                    // S of the next key block of the stream as soon as the softmax threads have pulled the current S out of TMEM
+                    const int s1 = (g + 1) & 1;
+                    mbar_wait(s_free, g & 1);
+                    const int qb = last ? (it + 1) & 1 : it & 1;
+                    if (last) mbar_wait(&q_full[qb], ((it + 1) >> 1) & 1);
+                    mbar_wait(&k_full[s1], ((g + 1) >> 1) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t q_desc = q_desc0 + qb * (TILE_BYTES >> 4);
+                        const uint64_t k_desc = k_desc0 + s1 * (TILE_BYTES >> 4);
+                        const uint32_t idesc = (!last && j + 2 == nkb) ? idesc_s_last : IDESC_S;  // nkb >= 4: block 0 of a tile is full
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc + k * 2, k_desc + k * 2, idesc, k != 0);
+                        umma_commit(s_full);
+                        umma_commit(&k_empty[s1]);
+                    }
+                    __syncwarp();
+                }
+                const int s = g & 1;
+                mbar_wait(p_ready, g & 1);  // (for j == 0 this also says: the softmax threads have drained the previous tile's O)
+                mbar_wait(&v_full[s], (g >> 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t v_desc = v_desc0 + s * (TILE_BYTES >> 4);
+                    const int pv_steps = last ? pv_steps_last : 8;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < pv_steps) umma_f16_ts(tmem_O, tmem_P + k * 8, v_desc + k * (2048 >> 4), IDESC_O, (j | k) != 0);
+                    }
+                    umma_commit(&v_empty[s]);
+                    umma_commit(p_free);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== softmax warps: one thread per query row =====================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        uint32_t* words = reinterpret_cast<uint32_t*>(smem + PQ_OFF_KMASK);
+        const bool need_mask = p.key_valid != nullptr || (p.T % ATT_BKV) != 0;
+        int g = 0, it = 0, mask_img = -1;
+        for (int w = blockIdx.x; w < p.n_items; w += stride, ++it) {
+            const AttnItem cur = attn_item(p, w);
+            const uint32_t* kmask = nullptr;
+            if (need_mask) {
+                // validity words: per image when there is a key mask, once otherwise (keys past T)
+                if (mask_img < 0 || (p.key_valid != nullptr && mask_img != cur.img)) {
+                    if (mask_img >= 0) named_bar_sync(1, 128);  // nobody still reads the previous image's words
+                    const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)cur.img * p.T : nullptr;
+                    for (int x = warp - 2; x < nkb * (ATT_BKV / 32); x += 4) {
+                        const int key = x * 32 + lane;
+                        const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
+                        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+                        if (lane == 0) words[x] = word;
+                    }
+                    named_bar_sync(1, 128);
+                    mask_img = cur.img;
+                }
+                kmask = words;
+            }
+            const bool warp_active = cur.qt * ATT_BQ + quarter * 32 < p.T;
+            SoftmaxState st{0.f, 0.f};
+            for (int j = 0; j < nkb; ++j, ++g) {
+                mbar_wait(s_full, g & 1);
+                tc_fence_after();
+                if (!warp_active) {
+                    tc_fence_before();
+                    mbar_arrive(s_free);
+                    if (j > 0) mbar_wait(p_free, (g - 1) & 1);
+                    mbar_arrive(p_ready);
+                } else {
+                    const int ncols = (j + 1 == nkb) ? p.n_last : ATT_BKV;
+                    const uint32_t* km = (p.key_valid != nullptr || j + 1 == nkb) ? kmask : nullptr;
+                    const int nch = (ncols + 31) >> 5;
+#define WG_SM_ARGS st, j, g, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr, 0, r, nullptr
+                    if (nch == 4) softmax_block<4, POLY, 1>(WG_SM_ARGS);
+                    else if (nch == 3) softmax_block<3, POLY, 1>(WG_SM_ARGS);
+                    else if (nch == 2) softmax_block<2, POLY, 1>(WG_SM_ARGS);
+                    else softmax_block<1, POLY, 1>(WG_SM_ARGS);
+#undef WG_SM_ARGS
+                }
+                if (j == 1 && it > 0 && threadIdx.x == 64) {
+                    // the previous item's O tile has long left its staging buffer: hand that Q buffer back to the producer
+                    tma_store_wait_read<0>();
+                    mbar_arrive(&q_free[(it - 1) & 1]);
+                }
+            }
+            // ---- epilogue: O / l, bf16, staged in this item's (finished) Q buffer, bulk store left in flight
+            mbar_wait(p_free, (g - 1) & 1);
+            tc_fence_after();
+            const float inv_l = st.l_run > 0.f ? 1.0f / st.l_run : 0.f;
+            uint8_t* o_tile = smem + PQ_OFF_Q + (it & 1) * TILE_BYTES;
+            uint8_t* o_row = o_tile + r * 128;
+            if (warp_active) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t ov[32];
+                    tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 0]) * inv_l, __uint_as_float(ov[q4 * 8 + 1]) * inv_l);
+                        u.y = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 2]) * inv_l, __uint_as_float(ov[q4 * 8 + 3]) * inv_l);
+                        u.z = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 4]) * inv_l, __uint_as_float(ov[q4 * 8 + 5]) * inv_l);
+                        u.w = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 6]) * inv_l, __uint_as_float(ov[q4 * 8 + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(o_row + (((c * 4 + q4) ^ (r & 7)) * 16)) = u;
+                    }
+                }
+            }
+            tc_fence_before();  // the next tile's first PV overwrites O: ordered behind these loads through p_ready
+            fence_proxy_async_smem();
+            named_bar_sync(2, 128);
+            if (threadIdx.x == 64) {
+                tma_store_3d(&tmO, o_tile, cur.head * ATT_D, cur.qt * ATT_BQ, cur.img);
+                tma_store_commit();
+            }
+        }
+        if (threadIdx.x == 64) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -569,6 +857,40 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     // once more) 0.53 ms; the leftover key folded into every row on CUDA cores instead of a ninth key block 0.55 ms; the last
     // row folded into the producer warps 0.65-0.83 ms.
     Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D);
+    // persistent kernel (two CTAs per SM walking the work list) from 4 key blocks per tile on; WG_ATTN_PERSIST=0 falls back to one
+    // CTA per (tile, head, image)
+    static int persist = -1;
+    if (persist < 0) {
+        const char* e = getenv("WG_ATTN_PERSIST");
+        persist = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    }
+    const long long n_items = (long long)B * heads * ((T + ATT_BQ - 1) / ATT_BQ);
+    if (persist && split == 1 && p.num_kv_blocks >= 4 && n_items < (1ll << 30)) {
+        p.n_full_tiles = T / ATT_BQ;
+        p.batch = B;
+        p.n_items = (int)n_items;
+        const int slots = 2 * device_sm_count();
+        const int grid = p.n_items < slots ? p.n_items : slots;
+#define WG_ATT_PLAUNCH(P)                                                                                                       \
+    do {                                                                                                                        \
+        static bool attr_set = false;                                                                                           \
+        if (!attr_set) {                                                                                                        \
+            WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_persist_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, PQ_SMEM_BYTES)); \
+            attr_set = true;                                                                                                    \
+        }                                                                                                                       \
+        attention_d64_persist_kernel<P><<<grid, 192, PQ_SMEM_BYTES, stream>>>(tmQKV, tmO, p);                                   \
+    } while (0)
+        switch (poly) {
+            case 1: WG_ATT_PLAUNCH(1); break;
+            case 2: WG_ATT_PLAUNCH(2); break;
+            case 3: WG_ATT_PLAUNCH(3); break;
+            case 4: WG_ATT_PLAUNCH(4); break;
+            default: WG_ATT_PLAUNCH(0); break;
+        }
+#undef WG_ATT_PLAUNCH
+        WG_CHECK_CUDA(cudaGetLastError());
+        return WG_OK;
+    }
     {
         dim3 grid((T + ATT_BQ - 1) / ATT_BQ, heads, B);
 #define WG_ATT_LAUNCH(P, S)                                                                                                     \
