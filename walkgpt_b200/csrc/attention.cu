@@ -1,8 +1,9 @@
 // Fused flash-style multi-head attention for the CLIP ViT-L/14@448 tower: head_dim 64,
 // T = 1025 tokens, optional key-padding mask (custom_clip.py:27-38 semantics: masked KEYS never receive weight).
 //
-// One CTA per (128-query tile, head, image); two CTAs co-reside per SM so that one CTA's softmax overlaps the
-// other's tensor work.  Per CTA:
+// Two CTAs co-reside per SM so that one CTA's softmax overlaps the other's tensor work.  From 4 key blocks per tile on they
+// are persistent and walk a list of (image, head, 128-query tile) items (attention_d64_persist_kernel, bottom of the file);
+// shorter sequences get one CTA per item (attention_d64_kernel).  Per CTA:
 //   warp 0  : TMA producer  (Q once, K/V blocks of 128 keys through 2-stage rings with separate K / V release;
 //             3-D tensor map over [image, token, 3*heads*64] so rows past T are zero-filled by the hardware)
 //   warp 1  : TMEM allocation + single-thread tcgen05.mma issue:  S = Q K^T (128x128x64, both operands from smem)
