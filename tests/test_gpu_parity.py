@@ -129,10 +129,13 @@ def _attn_ref(qkv, heads, scale, kv=None):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, heads * 64)
 
 
-# T = 1025 / 130 / 5 / 1 leave 1-8 rows past the last full query tile: those rows run in the CUDA-core tail kernel; T = 300 / 264
-# have a partial tensor-core tile; masked cases exercise the key-validity words in every key block.
+# T = 1025 / 130 / 5 / 1 / 300 / 264 / 1032 end in a partial query tile and a narrow last key block; masked cases exercise the
+# key-validity words in every key block.  Sequences of >= 4 key blocks run the persistent kernel: (2, 1025, 16) gives every CTA one
+# item, (6, 1025, 16) and (9, 640, 8) several items per CTA with the image (and, when masked, the validity words) changing between
+# items, (40, 512, 8) ten items per CTA without a partial tile; shorter sequences run one CTA per tile.
 @pytest.mark.parametrize("B,T,H,masked", [(1, 128, 1, False), (1, 1, 2, False), (2, 1025, 16, False), (2, 1025, 16, True), (1, 300, 3, True),
-                                          (2, 130, 2, True), (1, 5, 2, False), (1, 264, 1, False), (1, 1024, 4, False), (1, 1032, 2, True)])
+                                          (2, 130, 2, True), (1, 5, 2, False), (1, 264, 1, False), (1, 1024, 4, False), (1, 1032, 2, True),
+                                          (6, 1025, 16, True), (6, 1025, 16, False), (9, 640, 8, True), (40, 512, 8, False)])
 def test_attention(B, T, H, masked):
     torch.manual_seed(3)
     qkv = torch.randn(B, T, 3 * H * 64, device=DEV).bfloat16()
