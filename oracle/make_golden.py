@@ -231,12 +231,34 @@ def make_match_cost():
     save("match_cost", {"cases": cases, "num_points": 12544})
 
 
+@torch.no_grad()
+def make_sam_encoder():
+    """SURVEY 8(f) row 1 groundwork: the reference ImageEncoderViT at a small configuration that keeps every mechanism of SAM ViT-H
+    (head_dim 80, windows that need padding: 12 -> 15 with window 5, one global block, decomposed relative position in both kinds of
+    block, neck).  Writes tests/golden/sam_encoder_small.pt:  python -m oracle.make_golden sam_encoder"""
+    from model.segment_anything.modeling.image_encoder import ImageEncoderViT
+
+    cfg = dict(img_size=192, patch=16, embed=160, depth=3, heads=2, window_size=5, global_attn_indexes=(1,), out_chans=256)
+    ref = ImageEncoderViT(img_size=cfg["img_size"], patch_size=cfg["patch"], embed_dim=cfg["embed"], depth=cfg["depth"], num_heads=cfg["heads"],
+                          out_chans=cfg["out_chans"], use_rel_pos=True, window_size=cfg["window_size"],
+                          global_attn_indexes=cfg["global_attn_indexes"], norm_layer=lambda d: nn.LayerNorm(d, eps=1e-6)).eval()
+    # build_sam.py:73 builds the blocks with LayerNorm(eps=1e-6)
+    spec = specs.sam_image_encoder_spec(cfg["img_size"], cfg["patch"], cfg["embed"], cfg["depth"], cfg["heads"], 4.0, cfg["out_chans"],
+                                        cfg["window_size"], cfg["global_attn_indexes"])
+    ref.load_state_dict(specs.make_state_dict(spec, seed=31), strict=True)
+    x = rnd((2, 3, cfg["img_size"], cfg["img_size"]), 611)
+    save("sam_encoder_small", {"cfg": cfg, "seed": 31, "pixels_seed": 611, "out": ref(x), "ln_eps": 1e-6})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "two_level":
         make_decoder_two_level()
     elif len(sys.argv) > 1 and sys.argv[1] == "match":
         make_match_cost()
+    elif len(sys.argv) > 1 and sys.argv[1] == "sam_encoder":
+        make_sam_encoder()
     else:
         main()
         make_decoder_two_level()
         make_match_cost()
+        make_sam_encoder()

@@ -178,6 +178,27 @@ def test_match_cost_against_reference_golden():
         assert list(r) == case["pred_idx"].tolist() and list(c) == case["tgt_idx"].tolist()
 
 
+def test_sam_image_encoder_oracle_against_reference_golden():
+    """SURVEY 8(f) row 1 groundwork (no CUDA path yet): oracle.path_b.image_encoder_vit reproduces the reference
+    ImageEncoderViT -- head_dim 80, padded 5 x 5 windows on a 12 x 12 map, one global block, decomposed relative position, neck --
+    and the parameter table loads into the reference module strictly (make_golden.make_sam_encoder)."""
+    from oracle import path_b
+
+    g = load("sam_encoder_small")
+    cfg = g["cfg"]
+    spec = specs.sam_image_encoder_spec(cfg["img_size"], cfg["patch"], cfg["embed"], cfg["depth"], cfg["heads"], 4.0, cfg["out_chans"],
+                                        cfg["window_size"], cfg["global_attn_indexes"])
+    sd = specs.make_state_dict(spec, seed=g["seed"])
+    x = rnd((2, 3, cfg["img_size"], cfg["img_size"]), g["pixels_seed"])
+    out = path_b.image_encoder_vit(sd, x, cfg["heads"], cfg["window_size"], cfg["global_attn_indexes"], ln_eps=g["ln_eps"])
+    assert out.shape == g["out"].shape == (2, 256, 12, 12)
+    close(out, g["out"], 2e-5)
+    # the full-size table has the released checkpoint's shapes (SAM ViT-H, build_sam.py:15-22)
+    full = specs.sam_image_encoder_spec()
+    assert full["blocks.7.attn.rel_pos_h"][0] == (127, 80) and full["blocks.0.attn.rel_pos_h"][0] == (27, 80)
+    assert full["pos_embed"][0] == (1, 64, 64, 1280) and full["neck.2.weight"][0] == (256, 256, 3, 3)
+
+
 def test_depth_extension_is_self_consistent():
     """No reference exists for depth (parity unpinned): only check the in-repo definition's invariants."""
     sd = specs.make_state_dict(specs.depth_head_spec(), seed=3, prefix="depth_head.")

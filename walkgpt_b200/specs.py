@@ -168,6 +168,32 @@ def mask_decoder_sam_spec(dim: int = 256, num_multimask_outputs: int = 3, depth:
     return s
 
 
+def sam_image_encoder_spec(img_size: int = 1024, patch: int = 16, embed: int = 1280, depth: int = 32, heads: int = 16, mlp_ratio: float = 4.0,
+                           out_chans: int = 256, window_size: int = 14, global_attn_indexes: Sequence[int] = (7, 15, 23, 31)) -> Spec:
+    """ImageEncoderViT (segment_anything/modeling/image_encoder.py:17-116; defaults = SAM ViT-H, build_sam.py:15-22).  SURVEY 8(f) row 1:
+    only the parameter table and the oracle exist so far."""
+    g = img_size // patch
+    hd = embed // heads
+    s: Spec = {"pos_embed": ((1, g, g, embed), False), "patch_embed.proj.weight": ((embed, 3, patch, patch), False),
+               "patch_embed.proj.bias": ((embed,), False)}
+    for i in range(depth):
+        p = f"blocks.{i}."
+        side = g if i in global_attn_indexes else window_size
+        _ln(s, p + "norm1", embed)
+        s[p + "attn.rel_pos_h"] = ((2 * side - 1, hd), False)
+        s[p + "attn.rel_pos_w"] = ((2 * side - 1, hd), False)
+        _lin(s, p + "attn.qkv", 3 * embed, embed)
+        _lin(s, p + "attn.proj", embed, embed)
+        _ln(s, p + "norm2", embed)
+        _lin(s, p + "mlp.lin1", int(embed * mlp_ratio), embed)
+        _lin(s, p + "mlp.lin2", embed, int(embed * mlp_ratio))
+    s["neck.0.weight"] = ((out_chans, embed, 1, 1), False)
+    _ln(s, "neck.1", out_chans)
+    s["neck.2.weight"] = ((out_chans, out_chans, 3, 3), False)
+    _ln(s, "neck.3", out_chans)
+    return s
+
+
 def depth_head_spec(in_ch: int = 32, hidden: int = 256) -> Spec:
     """Relative-depth head: THIS REPO'S EXTENSION (no reference counterpart; see oracle.path_a.depth_head)."""
     s: Spec = {}
@@ -204,6 +230,8 @@ def init_tensor(name: str, shape: Sequence[int], seed: int = 0) -> torch.Tensor:
     if len(shape) == 1:  # biases, class_embedding
         return 0.02 * r if leaf == "bias" else 0.5 * r
     fan_in = n // shape[0]
+    if leaf == "pos_embed":  # absolute position table of the SAM encoder [1, g, g, C]
+        return 0.1 * r
     if len(shape) == 4:  # convolutions
         if "upscaling" in name or "upsample_2x" in name:
             fan_in = shape[0]  # ConvTranspose2d weight is [Cin, Cout, kh, kw]
