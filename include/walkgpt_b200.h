@@ -262,6 +262,10 @@ typedef struct wg_twoway_layer {
     const float* b_img;                             /* fp32 [hw][384] = (pe Wk^T + bk | bv | pe Wq^T + bq): dense PE folded in */
     const void* i2t_wo; const float* i2t_bo;        /* cross_attn_image_to_token.out_proj: bf16 [256][T*128] */
     const float* n4_g; const float* n4_b;
+    /* optional: the token MLP (71 % of the token side's weight bytes) as two tensor-core GEMMs over the token rows of ALL prompts
+     * instead of inside the one-CTA-per-prompt token kernel: bf16 [2048][T*256] and [256][T*2048] in the [W_hi | W_hi | W_lo]
+     * layout of wg_gemm_args.a_k_wrap.  NULL = the token kernel multiplies with mlp_w1_t / mlp_w2_t itself. */
+    const void* mlp_w1_split; const void* mlp_w2_split;
 } wg_twoway_layer;
 
 typedef struct wg_mask_decoder_weights {

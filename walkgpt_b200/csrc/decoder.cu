@@ -244,6 +244,7 @@ __device__ void tok_t2i_attention(const float* Qt, const float* __restrict__ kv,
 
 struct TokArgs {
     int phase, hw, n_mask_tokens;
+    int part;                            // phases 0/1: 0 = whole layer, 1 = up to norm2 (then the MLP runs as GEMMs), 2 = from norm3 on
     int part_floats;                     // split-K buffer of tok_linear: TK_THREADS * NT * 2 or * 4 floats
     wg_twoway_layer L;                   // weights of this layer (phases 0/1)
     // final-phase weights
@@ -256,6 +257,7 @@ struct TokArgs {
     const float* kv;           // image-side projections of this phase, fp32 [P*hw][ldkv]
     int ldkv;
     float* Tq;                 // [P][NT][256] running queries
+    __nv_bfloat16* Xs;         // part 1: the queries after norm2 once more as split-bf16 [P*NT][512] (A operand of the MLP GEMMs)
     float* Tpe;                // [P][NT][256] token positional term (= initial tokens)
     float* KT; float* VT;      // [P][NT][128] token-side K/V for image->token attention
     float* hyper;              // [P][n_mask][32]
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
     const float* kv = a.kv + (size_t)p * a.hw * a.ldkv;
     const float* W;
 
-    if (a.phase == 0) {
+    if (a.phase == 0 && a.part != 2) {
         for (int i = tid; i < NT * C; i += TK_THREADS) {
             const int t = i / C, c = i % C;
             float v = (t < NT - 1) ? a.out_tokens[t * C + c] : a.txt[(size_t)p * C + c] + (a.sparse_add ? a.sparse_add[c] : 0.f);
@@ -296,6 +298,7 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
 
     if (a.phase < 2) {
         const wg_twoway_layer& L = a.L;
+        if (a.part != 2) {
         // ---- (1) self attention on the tokens
         if (a.phase == 0) {
             for (int i = tid; i < NT * C; i += TK_THREADS) b3[i] = q[i];
@@ -319,9 +322,22 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
         tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part.buf);
         tok_linear(b1, CI, CI, (const float*)L.t2i_wo_t, L.t2i_bo, q, C, C, true, false, part);
         tok_layernorm(q, L.n2_g, L.n2_b, 1e-5f);
+        if (a.part == 1) {
+            // the MLP runs as two GEMMs over all prompts' token rows: hand the queries over in fp32 (residual) and split-bf16 (operand)
+            for (int i = tid; i < NT * C; i += TK_THREADS) {
+                const float v = q[i];
+                const __nv_bfloat16 hi = __float2bfloat16(v);
+                a.Tq[(size_t)p * NT * C + i] = v;
+                __nv_bfloat16* xr = a.Xs + ((size_t)p * NT + i / C) * (2 * C) + (i % C);
+                xr[0] = hi;
+                xr[C] = __float2bfloat16(v - __bfloat162float(hi));
+            }
+            return;
+        }
         // ---- (3) MLP
         tok_linear(q, C, C, (const float*)L.mlp_w1_t, L.mlp_b1, big, 2048, 2048, false, true, part);
         tok_linear(big, 2048, 2048, (const float*)L.mlp_w2_t, L.mlp_b2, q, C, C, true, false, part);
+        }
         tok_layernorm(q, L.n3_g, L.n3_b, 1e-5f);
         // ---- (4) token-side K/V for the image->token attention
         tok_add(b3, q, qpe, NT * C);
@@ -646,6 +662,7 @@ __global__ void __launch_bounds__(256) upscale_mask2_kernel(const float* __restr
 struct DecBuffers {
     __nv_bfloat16 *keysA, *keysB, *a2;   // split-bf16: [rows, 512], [rows, 512], [rows, 256]
     float *kvq, *U, *Tq, *Tpe, *KT, *VT, *hyper, *iou_all;
+    __nv_bfloat16 *Xs, *Hs;  // token rows of all prompts as split-bf16: MLP input [P*NT, 512], hidden [P*NT, 4096]
 };
 
 bool carve(Workspace& ws, int P, int hw, int up_stages, DecBuffers& d) {
@@ -667,6 +684,8 @@ bool carve(Workspace& ws, int P, int hw, int up_stages, DecBuffers& d) {
     d.VT = (float*)take((size_t)P * NT * CI * 4);
     d.hyper = (float*)take((size_t)P * 4 * 32 * 4);
     d.iou_all = (float*)take((size_t)P * 4 * 4);
+    d.Xs = (__nv_bfloat16*)take((size_t)P * NT * 2 * C * 2);
+    d.Hs = (__nv_bfloat16*)take((size_t)P * NT * 2 * 2048 * 2);
     return ok;
 }
 
@@ -776,6 +795,7 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     TokArgs ta = {};
     ta.hw = hw;
     ta.part_floats = tk_part;
+    ta.Xs = d.Xs;
     ta.n_mask_tokens = w->n_mask_tokens;
     ta.fin_wq_t = w->fin_wq_t; ta.fin_bq = w->fin_bq; ta.fin_wo_t = w->fin_wo_t; ta.fin_bo = w->fin_bo; ta.nf_g = w->nf_g; ta.nf_b = w->nf_b;
     ta.hyp_w0_t = w->hyp_w0_t; ta.hyp_w1_t = w->hyp_w1_t; ta.hyp_w2_t = w->hyp_w2_t;
@@ -807,7 +827,33 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
         }
         WG_DBG_STEP();
         ta.phase = l; ta.L = L; ta.kv = d.kvq; ta.ldkv = 384;
-        {
+        if (L.mlp_w1_split != nullptr && L.mlp_w2_split != nullptr) {
+            // token MLP as two GEMMs over the P * NT token rows (hidden = relu(x W1^T + b1) in split-bf16; queries += hidden W2^T + b2
+            // in place in fp32), between the two halves of the token kernel
+            ta.part = 1;
+            {
+                Prof prof("dec_token", s, (double)P * 2.0 * 3.0e6, (double)P * (hw * 512.0 + 1.0e6));
+                decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+            }
+            WG_CHECK_CUDA(cudaGetLastError());
+            wg_gemm_args g1 = {};
+            g1.A = d.Xs; g1.lda = 2 * C; g1.W = L.mlp_w1_split; g1.ldw = (long long)T * C; g1.M = P * NT; g1.N = 2048; g1.K = T * C;
+            g1.a_k_wrap = T == 3 ? 2 * C : 0;
+            g1.bias = L.mlp_b1; g1.act = WG_ACT_RELU; g1.out_mode = WG_OUT_BF16; g1.split_out = 1; g1.out = d.Hs; g1.ldo = 2 * 2048;
+            WG_TRY(wg_gemm(&g1, s));
+            wg_gemm_args g2 = {};
+            g2.A = d.Hs; g2.lda = 2 * 2048; g2.W = L.mlp_w2_split; g2.ldw = (long long)T * 2048; g2.M = P * NT; g2.N = C; g2.K = T * 2048;
+            g2.a_k_wrap = T == 3 ? 2 * 2048 : 0;
+            g2.bias = L.mlp_b2; g2.out_mode = WG_OUT_F32; g2.out = d.Tq; g2.ldo = C; g2.resid = d.Tq;
+            WG_TRY(wg_gemm(&g2, s));
+            ta.part = 2;
+            {
+                Prof prof("dec_token", s, (double)P * 2.0 * 0.4e6, (double)P * 0.3e6);
+                decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+            }
+            ta.part = 0;
+        } else {
+            ta.part = 0;
             Prof prof("dec_token", s, (double)P * 2.0 * 10.2e6, (double)P * (hw * 512.0 + 3.0e6));
             decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
         }

@@ -703,6 +703,7 @@ class MaskDecoderMultiScale(_SpecModule):
         img_w += [sd[T + "final_attn_token_to_image.k_proj.weight"], sd[T + "final_attn_token_to_image.v_proj.weight"], sd["output_upscaling.0.weight"]]
         if self._UP_STAGES == 2:
             img_w.append(sd["output_upscaling.3.weight"])
+        img_w += [sd[T + f"layers.{l}.mlp.{n}.weight"] for l in range(2) for n in ("lin1", "lin2")]  # token MLP: tensor-core GEMMs too
         terms = split_terms_needed(img_w)
         w.split_terms = terms
 
@@ -718,6 +719,8 @@ class MaskDecoderMultiScale(_SpecModule):
             L.n2_g, L.n2_b = hold.f32(sd[lp + "norm2.weight"]), hold.f32(sd[lp + "norm2.bias"])
             L.mlp_w1_t, L.mlp_b1 = lin_t(lp + "mlp.lin1")
             L.mlp_w2_t, L.mlp_b2 = lin_t(lp + "mlp.lin2")
+            L.mlp_w1_split = hold(split_weight(sd[lp + "mlp.lin1.weight"], terms))
+            L.mlp_w2_split = hold(split_weight(sd[lp + "mlp.lin2.weight"], terms))
             L.n3_g, L.n3_b = hold.f32(sd[lp + "norm3.weight"]), hold.f32(sd[lp + "norm3.bias"])
             L.i2t_wk_t, L.i2t_bk = lin_t(lp + "cross_attn_image_to_token.k_proj")
             L.i2t_wv_t, L.i2t_bv = lin_t(lp + "cross_attn_image_to_token.v_proj")
