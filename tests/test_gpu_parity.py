@@ -260,6 +260,25 @@ def test_prompt_encoder_and_mask_decoder_against_reference_golden(grid):
         dec(emb, pe, sparse, dense, False, 1, previous_masks=m1)
 
 
+def test_mask_decoder_token_mlp_gemm_path_matches_in_kernel_path():
+    """The token MLP as split-bf16 GEMMs over all prompts' rows (default) against the fp32 MLP inside the token kernel
+    (wg_twoway_layer.mlp_w*_split = NULL): same masks to near-fp32 accuracy, both within the golden tolerance."""
+    g = load("decoder_ms_g32")
+    pe_m = load_into(M.PromptEncoder(256, (32, 32), (448, 448), 16), specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"]))
+    sd = specs.make_state_dict(specs.mask_decoder_multiscale_spec(), seed=g["seed_dec"])
+    pe = pe_m.get_dense_pe()
+    sparse, dense = pe_m(None, None, None, g["txt"].to(DEV))
+    emb = rnd(g["emb_shape"], g["emb_seed"]).to(DEV)
+    outs = []
+    for use_gemm in (True, False):
+        dec = load_into(M.MaskDecoderMultiScale(), sd)
+        dec._MLP_GEMM = use_gemm
+        m4, i4 = dec(emb, pe, sparse, dense, True, 0)
+        assert rel_err(m4, g["masks4"]) < 1e-3 and rel_err(i4, g["iou4"]) < 1e-3
+        outs.append((m4, i4))
+    assert rel_err(outs[0][0], outs[1][0]) < 2e-4 and rel_err(outs[0][1], outs[1][1]) < 2e-4
+
+
 def test_mask_decoder_two_levels_against_reference_golden():
     """MaskDecoderMultiScale(image_feature_scale_num=2), level 0 then level 1 fed with the level-0 masks
     (mask_decoder_multi_scale.py:165-171), against the fixture produced by the reference module."""

@@ -677,6 +677,7 @@ class MaskDecoderMultiScale(_SpecModule):
     _T = "transformer.0."   # state_dict prefix of the two-way transformer
     _UP_STAGES = 1          # ConvTranspose stages of output_upscaling
     _MULTIMASK_FIRST = 0    # mask_decoder_multi_scale.py:126-132 keeps mask 0 in both modes
+    _MLP_GEMM = True        # token MLP as tensor-core GEMMs over all prompts' rows (False: inside the per-prompt token kernel, fp32)
 
     def _prefix(self, level: int) -> str:
         return self._T.replace("0", str(level)) if "0" in self._T else self._T
@@ -719,8 +720,9 @@ class MaskDecoderMultiScale(_SpecModule):
             L.n2_g, L.n2_b = hold.f32(sd[lp + "norm2.weight"]), hold.f32(sd[lp + "norm2.bias"])
             L.mlp_w1_t, L.mlp_b1 = lin_t(lp + "mlp.lin1")
             L.mlp_w2_t, L.mlp_b2 = lin_t(lp + "mlp.lin2")
-            L.mlp_w1_split = hold(split_weight(sd[lp + "mlp.lin1.weight"], terms))
-            L.mlp_w2_split = hold(split_weight(sd[lp + "mlp.lin2.weight"], terms))
+            if self._MLP_GEMM:
+                L.mlp_w1_split = hold(split_weight(sd[lp + "mlp.lin1.weight"], terms))
+                L.mlp_w2_split = hold(split_weight(sd[lp + "mlp.lin2.weight"], terms))
             L.n3_g, L.n3_b = hold.f32(sd[lp + "norm3.weight"]), hold.f32(sd[lp + "norm3.bias"])
             L.i2t_wk_t, L.i2t_bk = lin_t(lp + "cross_attn_image_to_token.k_proj")
             L.i2t_wv_t, L.i2t_bv = lin_t(lp + "cross_attn_image_to_token.v_proj")
