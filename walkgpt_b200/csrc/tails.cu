@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(BIL_THREADS) bilinear_kernel(const float* __re
     const int xg = blockIdx.x * blockDim.x + threadIdx.x;  // group of VEC pixels
     const int x0 = xg * VEC;
     float ssum = 0.f, scnt = 0.f;
+    const unsigned row_lanes = __ballot_sync(0xffffffffu, x0 < dw);  // lanes of this warp that own pixels (the row loop's votes)
     if (x0 < dw) {
         int xa[VEC], xb[VEC];
         float lx[VEC];
@@ -93,17 +94,28 @@ __global__ void __launch_bounds__(BIL_THREADS) bilinear_kernel(const float* __re
                         if (SCORE && mask) mask[off + v] = o[v] > 0.f;
                     }
             }
-            if (SCORE) {
+            if (SCORE && accum != nullptr) {
+                // one warp-uniform test per row: real masks are mostly negative, so most warps (128 consecutive pixels of a row)
+                // skip the sigmoids altogether; a warp that holds a positive pixel evaluates all of its lanes branch-free.
+                // The scoring variant of this kernel is issue-bound, not write-bound (mask-only: 42 us for 192 masks, with the
+                // IEEE division 1.0f / (1.0f + __expf(-o)): 92 us): the reciprocal is MUFU.RCP (1 ulp) like the exponential is
+                // MUFU.EX2 -- far inside the 1e-5 the score is compared at; exp(-o) = inf gives 1 / inf = 0, no NaN.
+                bool any_pos = false;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    if (x0 + v < dw && o[v] > 0.f) {
-                        ssum += 1.0f / (1.0f + __expf(-o[v]));
-                        scnt += 1.f;
+                for (int v = 0; v < VEC; ++v) any_pos = any_pos || (x0 + v < dw && o[v] > 0.f);
+                if (__any_sync(row_lanes, any_pos)) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const bool pos = x0 + v < dw && o[v] > 0.f;
+                        const float sg = __fdividef(1.0f, 1.0f + __expf(-o[v]));
+                        ssum += pos ? sg : 0.f;
+                        scnt += pos ? 1.f : 0.f;
                     }
+                }
             }
         }
     }
-    if (SCORE) {
+    if (SCORE && accum != nullptr) {
         __shared__ float red[2][BIL_THREADS / 32];
         ssum = warp_sum(ssum);
         scnt = warp_sum(scnt);
@@ -194,11 +206,12 @@ int launch_bilinear(const float* src, int n, int sh, int sw, float* dst, int dh,
     // algorithmic bytes: read the source once, write fp32 logits (+ u8 mask)
     Prof prof(SCORE ? "postprocess_bilinear_score" : "postprocess_bilinear", s, 0.0,
               (double)n * ((double)sh * sw * 4.0 + (double)dh * dw * (SCORE && mask ? 5.0 : 4.0)));
-    // bands of rows: enough CTAs for ~8 per SM, at least 8 rows each so the per-thread column set-up is amortised
+    // bands of rows: ~32 CTAs per SM, i.e. several waves at the 7-12 CTAs an SM holds (with ~9 per SM the scoring variant ran 1.3
+    // waves: a second, 30 % full round), at least 8 rows each so the per-thread column set-up is amortised
     const int vec = (dw % 4 == 0) ? 4 : 1;
     const int groups = (dw + vec - 1) / vec;
     const int xblocks = (groups + BIL_THREADS - 1) / BIL_THREADS;
-    int bands = (8 * device_sm_count() + n * xblocks - 1) / (n * xblocks);
+    int bands = (32 * device_sm_count() + n * xblocks - 1) / (n * xblocks);
     if (bands < 1) bands = 1;
     int rows_per_band = (dh + bands - 1) / bands;
     if (rows_per_band < 8) rows_per_band = 8;
@@ -246,13 +259,13 @@ extern "C" int wg_postprocess_masks(const float* low_res, int n_masks, int Hm, i
     if (in_h == out_h && in_w == out_w) {
         // the second interpolation is the identity (scale 1 => lambda 0): one fused pass
         if (want_score)
-            WG_TRY(launch_bilinear<true>(low_res, n_masks, Hm, Wm, logits_out, in_h, in_w, target, target, mask_out, accum, s));
+            WG_TRY(launch_bilinear<true>(low_res, n_masks, Hm, Wm, logits_out, in_h, in_w, target, target, mask_out, score_out ? accum : nullptr, s));
         else
             WG_TRY(launch_bilinear<false>(low_res, n_masks, Hm, Wm, logits_out, in_h, in_w, target, target, nullptr, nullptr, s));
     } else {
         WG_TRY(launch_bilinear<false>(low_res, n_masks, Hm, Wm, mid, in_h, in_w, target, target, nullptr, nullptr, s));
         if (want_score)
-            WG_TRY(launch_bilinear<true>(mid, n_masks, in_h, in_w, logits_out, out_h, out_w, out_h, out_w, mask_out, accum, s));
+            WG_TRY(launch_bilinear<true>(mid, n_masks, in_h, in_w, logits_out, out_h, out_w, out_h, out_w, mask_out, score_out ? accum : nullptr, s));
         else
             WG_TRY(launch_bilinear<false>(mid, n_masks, in_h, in_w, logits_out, out_h, out_w, out_h, out_w, nullptr, nullptr, s));
     }
