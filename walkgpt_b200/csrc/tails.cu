@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(BIL_THREADS) bilinear_kernel(const float* __re
         // band reuses each pair for several output rows): 4 * VEC L1 loads per CHANGE instead of per output row
         float h0[VEC], h1[VEC];
         int cur0 = -1, cur1 = -1;
+        float* drow = dst + ((size_t)n * dh + ya) * dw + x0;
+        uint8_t* mrow = mask + ((size_t)n * dh + ya) * dw + x0;  // only dereferenced when mask != nullptr
         for (int y = ya; y < yb; ++y) {
             int y0, y1;
             float ly;
@@ -78,22 +80,23 @@ __global__ void __launch_bounds__(BIL_THREADS) bilinear_kernel(const float* __re
             float o[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) o[v] = (1.f - ly) * h0[v] + ly * h1[v];
-            const size_t off = ((size_t)n * dh + y) * dw + x0;
             if (full_vec) {
-                __stcs(reinterpret_cast<float4*>(dst + off), make_float4(o[0], o[1], o[2], o[3]));
+                __stcs(reinterpret_cast<float4*>(drow), make_float4(o[0], o[1], o[2], o[3]));
                 if (SCORE && mask) {
                     uchar4 m;
                     m.x = o[0] > 0.f; m.y = o[1] > 0.f; m.z = o[2] > 0.f; m.w = o[3] > 0.f;
-                    __stcs(reinterpret_cast<uchar4*>(mask + off), m);
+                    __stcs(reinterpret_cast<uchar4*>(mrow), m);
                 }
             } else {
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
                     if (x0 + v < dw) {
-                        dst[off + v] = o[v];
-                        if (SCORE && mask) mask[off + v] = o[v] > 0.f;
+                        drow[v] = o[v];
+                        if (SCORE && mask) mrow[v] = o[v] > 0.f;
                     }
             }
+            drow += dw;  // one pointer bump per output row instead of a 64-bit multiply-add chain
+            mrow += dw;
             if (SCORE && accum != nullptr) {
                 // one warp-uniform test per row: real masks are mostly negative, so most warps (128 consecutive pixels of a row)
                 // skip the sigmoids altogether; a warp that holds a positive pixel evaluates all of its lanes branch-free.
@@ -107,7 +110,8 @@ __global__ void __launch_bounds__(BIL_THREADS) bilinear_kernel(const float* __re
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         const bool pos = x0 + v < dw && o[v] > 0.f;
-                        const float sg = __fdividef(1.0f, 1.0f + __expf(-o[v]));
+                        float sg;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + __expf(-o[v])));
                         ssum += pos ? sg : 0.f;
                         scnt += pos ? 1.f : 0.f;
                     }
