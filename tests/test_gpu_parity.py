@@ -207,9 +207,9 @@ def test_projector_and_neck_against_reference_golden():
     assert rel_err(m.neck(g["proj"].permute(0, 2, 1).reshape(2, g["hidden"], 8, 8).to(DEV)), g["emb"]) < 1e-4  # the neck itself: near-fp32
 
 
-@pytest.mark.parametrize("grid", [16, 32])
+@pytest.mark.parametrize("grid", [16, 32, 64])
 def test_neck_implicit_conv_against_oracle_and_im2col(grid):
-    """The neck's 3x3 convolution as an implicit GEMM (shifted 4-D TMA boxes, zero-filled borders: grids 16 and 32) against the
+    """The neck's 3x3 convolution as an implicit GEMM (shifted 4-D TMA boxes, zero-filled borders: grids 16, 32 and SAM's 64) against the
     fp32 oracle (walkgpt.py:97-113) at the neck's near-fp32 accuracy, and bit-identical to the explicit im2col path."""
     import subprocess, sys, textwrap
     hidden, B = 64, 3
