@@ -96,3 +96,32 @@ def image_encoder_vit(sd: SD, pixels: torch.Tensor, heads: int, window_size: int
     y = F.conv2d(y.permute(0, 3, 1, 2), sd[p + "neck.2.weight"], padding=1).permute(0, 2, 3, 1)
     y = ln2d(y, sd[p + "neck.3.weight"], sd[p + "neck.3.bias"])
     return y.permute(0, 3, 1, 2).contiguous()
+
+
+def path_b_from_embeddings(weights, image_embeddings: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, input_size=(1024, 1024),
+                           original_size=(1024, 1024), image: int = 1024):
+    """The released wiring after the image encoder (SURVEY section 8 "Path B"): MSQP(sam_dim=256) over the embedding tokens; CTP ->
+    PromptEncoder -> SAM MaskDecoder (mask_decoder.py:75-164, multimask_output=False) -> Sam.postprocess_masks (sam.py:137-172) ->
+    score (model/walkgpt.py:541).  weights: {"msqp","ctp","prompt","decoder"} state dicts.  Composition of oracle.path_a functions."""
+    from . import path_a
+
+    B, C, h, w = image_embeddings.shape
+    out = {"vis_tokens": path_a.msqp_forward(weights["msqp"], image_embeddings.flatten(2).permute(0, 2, 1), target_square_side=6)}
+    txt = path_a.ctp_forward(weights["ctp"], seg_hidden[None])[0]
+    out["txt_emb"] = txt
+    pe = path_a.dense_pe(weights["prompt"]["pe_layer.positional_encoding_gaussian_matrix"], h, w)[None]
+    low, iou, logits, scores = [], [], [], []
+    for b in range(B):
+        t = txt[seg_offsets[b]:seg_offsets[b + 1]]
+        if t.shape[0] == 0:
+            continue
+        sparse, dense = path_a.prompt_encoder(weights["prompt"], t[:, None], (h, w))
+        m, i = path_a.mask_decoder_sam(weights["decoder"], image_embeddings[b:b + 1], pe, sparse, dense, multimask_output=False)
+        low.append(m)
+        iou.append(i)
+        pm = path_a.postprocess_masks(m, input_size, original_size, target_size=image)
+        logits.append(pm[:, 0])
+        scores.append(path_a.mask_score(pm[:, 0]))
+    out["low_res"], out["iou"] = torch.cat(low), torch.cat(iou)
+    out["logits"], out["scores"] = torch.cat(logits), torch.cat(scores)
+    return out

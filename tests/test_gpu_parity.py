@@ -402,6 +402,39 @@ def test_path_a_end_to_end_gates(path_model):
     assert rel_err(out["iou"], ref["iou"]) < 2e-2 or (out["iou"].cpu() - ref["iou"]).abs().max().item() < 1e-2
 
 
+def test_path_b_from_image_embeddings_end_to_end_gates():
+    """Path B (the released SAM-1024 wiring) from the image embeddings on -- MSQP(sam_dim=256) over 4096 tokens, CTP, PromptEncoder 64 x 64,
+    SAM MaskDecoder, Sam.postprocess_masks to a non-square original size -- against the fp32 oracle, ragged [SEG] counts, same gates
+    as Path A.  (The SAM ViT-H encoder that produces the embeddings is not built: DESIGN 8a.)"""
+    from oracle import path_b
+
+    m = M.GroundingPathB(hidden_size=4096, seed=2)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() >= 2:
+                p.copy_(p.to(torch.bfloat16).float())
+    m = m.to(DEV)
+    B, offs = 3, [0, 2, 2, 5]
+    emb = rnd((B, 256, 64, 64), 21)
+    seg = rnd((5, 4096), 22)
+    input_size, original_size = (768, 1024), (480, 640)
+    out = m(emb.to(DEV), seg.to(DEV), offs, input_size=input_size, original_size=original_size)
+    w = {"msqp": sd_cpu(m.msqp), "ctp": sd_cpu(m.text_hidden_fcs[0]), "prompt": sd_cpu(m.prompt_encoder), "decoder": sd_cpu(m.mask_decoder)}
+    ref = path_b.path_b_from_embeddings(w, emb, seg, offs, input_size=input_size, original_size=original_size)
+    assert out["low_res"].shape == (5, 1, 256, 256) and out["logits"].shape == (5, 480, 640) and out["masks"].dtype == torch.uint8
+    assert rel_err(out["vis_tokens"], ref["vis_tokens"]) < 2e-2
+    assert rel_err(out["txt_emb"], ref["txt_emb"]) < 1e-2
+    err = (out["logits"].cpu() - ref["logits"]).abs().max().item()
+    got_m, ref_m = out["masks"].cpu().bool(), ref["logits"] > 0
+    decided = ref["logits"].abs() > LOGIT_TOL
+    iou = _mask_iou(got_m & decided, ref_m & decided)
+    print(f"path B: mask logits max-abs err {err:.4f} (abs-max {ref['logits'].abs().max():.2f}); IoU on decided pixels {iou.tolist()}")
+    assert err <= LOGIT_TOL and iou.min().item() >= IOU_MIN
+    assert torch.equal(got_m, out["logits"].cpu() > 0)
+    assert (out["scores"].cpu() - ref["scores"]).abs().max().item() < 1e-2
+    assert rel_err(out["iou"], ref["iou"]) < 2e-2 or (out["iou"].cpu() - ref["iou"]).abs().max().item() < 1e-2
+
+
 @pytest.mark.parametrize("H,S", [(4096, 12), (5120, 16)])
 def test_path_a_other_baseline_configs(H, S):
     """BASELINE.json configs[2] (12 [SEG] per image, H=4096) and configs[4] (LLaVA-13B width 5120, 16 [SEG] per image), one image each,

@@ -1078,3 +1078,50 @@ class GroundingPath(nn.Module):
             if self.depth_head is not None:
                 out["depth"] = self.depth_head(pool, offs_dev, max_S)
         return out
+
+
+class GroundingPathB(nn.Module):
+    """Path B, the released wiring ("SAM-1024 branch"), from the SAM image embeddings on: MSQP(sam_dim=256) over the
+    [B, 4096, 256] embedding tokens ; [SEG] hidden states -> CTP -> PromptEncoder(64 x 64 grid, 1024-pixel input) -> standard SAM
+    MaskDecoder -> Sam.postprocess_masks (1024^2 -> crop -> original) / threshold / score, batched over all images and prompts.
+    The SAM ViT-H image encoder that produces the embeddings is not built yet: the caller passes its output."""
+
+    def __init__(self, hidden_size: int = 4096, grid: int = 64, image: int = 1024, seed: int = 0):
+        super().__init__()
+        self.grid, self.image, self.hidden_size = grid, image, hidden_size
+        self.msqp = MultiScaleQFormerProjector(sam_dim=256, llama_dim=hidden_size, pad_to_square=True, target_square_side=6, seed=seed)
+        self.text_hidden_fcs = nn.ModuleList([CalibratedTextProjector(hidden_size, 256, widen=2, use_residual=False, seed=seed)])
+        self.prompt_encoder = PromptEncoder(256, (grid, grid), (image, image), 16, seed=seed)
+        self.mask_decoder = MaskDecoder(transformer_dim=256, num_multimask_outputs=3, iou_head_depth=3, iou_head_hidden_dim=256, seed=seed)
+
+    @torch.no_grad()
+    def forward(self, image_embeddings: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, input_size: Optional[Tuple[int, int]] = None,
+                original_size: Optional[Tuple[int, int]] = None, want_vis_tokens: bool = True):
+        """image_embeddings [B, 256, g, g] (output of the SAM image encoder, model/walkgpt.py:713-743); seg_hidden [sum S, H];
+        seg_offsets int sequence [B+1].  Returns a dict of device tensors (low_res [P, 1, 4g, 4g], logits at original_size, ...)."""
+        _need_cuda(image_embeddings, "GroundingPathB.forward")
+        dev = image_embeddings.device
+        B, Cc, h, wd = image_embeddings.shape
+        assert Cc == 256 and (h, wd) == (self.grid, self.grid)
+        input_size = input_size or (self.image, self.image)
+        original_size = original_size or input_size
+        offs = [int(v) for v in seg_offsets]
+        assert len(offs) == B + 1 and offs[0] == 0 and offs[-1] == seg_hidden.shape[0]
+        counts = torch.tensor([offs[i + 1] - offs[i] for i in range(B)], dtype=torch.long, device=dev)
+        P = offs[-1]
+        out: Dict[str, torch.Tensor] = {}
+        with torch.cuda.device(dev):
+            tokens = image_embeddings.reshape(B, Cc, h * wd).permute(0, 2, 1)       # [B, hw, 256] (layout change only)
+            if want_vis_tokens:
+                out["vis_tokens"] = self.msqp.run(tokens.to(torch.bfloat16).contiguous(), torch.bfloat16)
+            txt = self.text_hidden_fcs[0].run(_as_kernel_input(seg_hidden), torch.float32)
+            out["txt_emb"] = txt
+            prompt_img = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), counts, output_size=P)
+            _, pe_tok = self.prompt_encoder.dense_pe_tokens()
+            self.mask_decoder._packed or self.mask_decoder._pack()
+            self.mask_decoder.bind_prompt_constants(pe_tok, self.prompt_encoder.no_mask_embed.weight, (h, wd))
+            low, iou, _ = self.mask_decoder.run(to_split(tokens), txt, prompt_img, False)
+            out["low_res"], out["iou"] = low, iou
+            logits, mask, score = postprocess_masks_fused(low[:, 0], input_size, original_size, target_size=self.image)
+            out["logits"], out["masks"], out["scores"] = logits, mask, score
+        return out
