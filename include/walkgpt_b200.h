@@ -364,6 +364,12 @@ WG_API int wg_seg_gather(const int64_t* input_ids, int rows, int Lin, const void
                          const int64_t* seg_ids, int n_seg_ids, int shift, const int32_t* img_rows, int n_img_p1, void* out,
                          int max_out, int32_t* counts, int32_t* row_offsets, int32_t* img_offsets, void* stream);
 
+/* Batched-composition glue (replaces the reference's per-image Python loop over `seg_token_offset`, model/walkgpt.py:414-420,
+ * 511-541): prompt_img[p] = the image b with seg_offsets[b] <= p < seg_offsets[b+1]; seg_offsets int32 [B+1] on the device.
+ * Inconsistent offsets (not non-decreasing from 0 to P) never index out of bounds: results are clamped to [0, B-1] and
+ * *status (device int32, nullable) is set to 1, else 0.  No host synchronisation. */
+WG_API int wg_prompt_index(const int32_t* seg_offsets, int B, int P, int32_t* prompt_img, int32_t* status, void* stream);
+
 /* F4 -- intersectionAndUnionGPU (utils/utils.py:192-204) for n_masks (output, target) pairs of `pixels` uint8 class ids:
  *   output[target == ignore_index] = ignore_index; out fp32 [n_masks, 3, K] = per-class histograms (area_intersection,
  *   area_union = area_output + area_target - area_intersection, area_target), exactly as torch.histc(bins=K, min=0, max=K-1)

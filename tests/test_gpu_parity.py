@@ -710,6 +710,25 @@ def test_torch_custom_ops_call_the_c_abi():
     assert _lib.lib().wg_launch_count(0) > before and rel_err(y, g["y3"]) < 1e-2
     lg, mk, sc = torch.ops.walkgpt_b200.postprocess_masks(torch.randn(2, 64, 64, device=DEV), 448, 448, 448, 448)
     assert torch.equal(mk.bool(), lg > 0)
+    assert torch_ops.register(m) == h  # stable handle, registry holds no strong reference
+    # mask decoder + projector/neck ops (SURVEY 8(b) "Torch layer"): same results as the module calls, fake kernels give the shapes
+    gd = load("decoder_ms_g8")
+    pe = load_into(M.PromptEncoder(256, (8, 8), (112, 112), 16), specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=gd["seed_prompt"]))
+    dec = load_into(M.MaskDecoderMultiScale(), specs.make_state_dict(specs.mask_decoder_multiscale_spec(), seed=gd["seed_dec"]))
+    sparse, dense = pe(None, None, None, gd["txt"].to(DEV))
+    hd = torch_ops.register(dec)
+    args = (rnd(gd["emb_shape"], gd["emb_seed"]).to(DEV), pe.get_dense_pe(), sparse, dense.contiguous())
+    m_op, i_op = torch.ops.walkgpt_b200.mask_decoder_forward(*args, True, hd)
+    m_mod, i_mod = dec(*args, True, 0, None)
+    assert torch.equal(m_op, m_mod) and torch.equal(i_op, i_mod) and rel_err(m_op, gd["masks4"]) < 1e-3
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode(allow_non_fake_inputs=False) as mode:
+        fk = [mode.from_tensor(a) for a in args]
+        fm, fi = torch.ops.walkgpt_b200.mask_decoder_forward(*fk, True, hd)
+    assert fm.shape == m_op.shape and fi.shape == i_op.shape
+    pn = M.ProjectorNeck(1024, 512, seed=4).to(DEV)
+    feats = rnd((1, 256, 1024), 5).to(DEV)
+    assert torch.equal(torch.ops.walkgpt_b200.proj_neck_forward(feats, torch_ops.register(pn)), pn(feats))
 
 
 def test_native_library_is_what_ran():

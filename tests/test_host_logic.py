@@ -129,3 +129,27 @@ def test_torch_custom_ops_have_shape_inference():
         assert last.shape == mid.shape == (2, 1024, 1024)
         lg, mk, sc = torch.ops.walkgpt_b200.postprocess_masks(torch.empty(4, 64, 64), 448, 448, 360, 640)
         assert lg.shape == (4, 360, 640) and mk.dtype == torch.uint8 and sc.shape == (4,)
+        h_ms, h_sam = torch_ops.register(M.MaskDecoderMultiScale()), torch_ops.register(M.MaskDecoder())
+        dec_args = (torch.empty(1, 256, 32, 32), torch.empty(1, 256, 32, 32), torch.empty(5, 1, 256), torch.empty(5, 256, 32, 32))
+        m, i = torch.ops.walkgpt_b200.mask_decoder_forward(*dec_args, False, h_ms)
+        assert m.shape == (5, 1, 64, 64) and i.shape == (5, 1)
+        m, i = torch.ops.walkgpt_b200.mask_decoder_forward(*dec_args, True, h_sam)  # SAM decoder: masks 1..3 at 4x the grid
+        assert m.shape == (5, 3, 128, 128) and i.shape == (5, 3)
+        h_pn = torch_ops.register(M.ProjectorNeck(1024, 512))
+        assert torch.ops.walkgpt_b200.proj_neck_forward(torch.empty(2, 1024, 1024), h_pn).shape == (2, 256, 32, 32)
+    torch_ops.unregister(h_pn)
+    with pytest.raises(KeyError):
+        torch_ops._get(h_pn)
+
+
+def test_prompt_index_validates_host_offsets_and_caches_by_value():
+    pi = M._PromptIndex(capacity=2)
+    offs_dev, img, P, max_S = pi.index([0, 2, 2, 5], 3, 5, "cpu")
+    assert offs_dev.tolist() == [0, 2, 2, 5] and img.tolist() == [0, 0, 2, 2, 2] and (P, max_S) == (5, 3)
+    assert pi.index((0, 2, 2, 5), 3, 5, "cpu")[1] is img  # same offsets: the cached device tensors
+    for bad in ([0, 2, 5], [1, 2, 2, 5], [0, 3, 2, 5], [0, 2, 2, 4]):
+        with pytest.raises(ValueError):
+            pi.index(bad, 3, 5, "cpu")
+    pi.index([0, 1, 2, 5], 3, 5, "cpu")
+    pi.index([0, 0, 0, 5], 3, 5, "cpu")
+    assert len(pi.cache) == 2  # bounded

@@ -841,17 +841,22 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     p.key_valid = key_valid;
     // tuning knobs (defaults measured on B200): WG_ATTN_POLY = exponentials per 8 evaluated on the FMA pipe,
     // WG_ATTN_SPLIT = softmax threads per query row
-    static int poly = -1, split = -1, smem_pad = 0;
-    if (poly < 0) {
+    struct Knobs { int poly, split, smem_pad, persist; };
+    static const Knobs knobs = [] {  // read once (C++11 guarantees a thread-safe initialisation)
+        Knobs k;
         const char* pad = getenv("WG_ATTN_SMEM_PAD");  // debug: extra dynamic smem (forces one CTA per SM when large)
-        smem_pad = pad ? atoi(pad) : 0;
+        k.smem_pad = pad ? atoi(pad) : 0;
         const char* e = getenv("WG_ATTN_POLY");
-        poly = e ? atoi(e) : ATT_POLY_DEFAULT;
-        if (poly < 0 || poly > 4) poly = ATT_POLY_DEFAULT;
+        k.poly = e ? atoi(e) : ATT_POLY_DEFAULT;
+        if (k.poly < 0 || k.poly > 4) k.poly = ATT_POLY_DEFAULT;
         e = getenv("WG_ATTN_SPLIT");
-        split = e ? atoi(e) : ATT_SPLIT_DEFAULT;
-        if (split != 1 && split != 2) split = ATT_SPLIT_DEFAULT;
-    }
+        k.split = e ? atoi(e) : ATT_SPLIT_DEFAULT;
+        if (k.split != 1 && k.split != 2) k.split = ATT_SPLIT_DEFAULT;
+        e = getenv("WG_ATTN_PERSIST");
+        k.persist = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+        return k;
+    }();
+    const int poly = knobs.poly, split = knobs.split, smem_pad = knobs.smem_pad, persist = knobs.persist;
     // The 1025th token of the CLIP sequence simply gets a ninth (mostly empty) query tile and a ninth, 16-key-wide key block:
     // idle softmax warps skip the arithmetic and the last S / PV MMAs are narrow.  Measured on B200 (B=64, 16 heads): T=1024
     // 0.43 ms, T=1025 this way 0.51 ms; a separate CUDA-core kernel for the last query row (it must stream K and V from HBM
@@ -860,11 +865,6 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D);
     // persistent kernel (two CTAs per SM walking the work list) from 4 key blocks per tile on; WG_ATTN_PERSIST=0 falls back to one
     // CTA per (tile, head, image)
-    static int persist = -1;
-    if (persist < 0) {
-        const char* e = getenv("WG_ATTN_PERSIST");
-        persist = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-    }
     const long long n_items = (long long)B * heads * ((T + ATT_BQ - 1) / ATT_BQ);
     if (persist && split == 1 && p.num_kv_blocks >= 4 && n_items < (1ll << 30)) {
         p.n_full_tiles = T / ATT_BQ;
@@ -874,11 +874,7 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
         const int grid = p.n_items < slots ? p.n_items : slots;
 #define WG_ATT_PLAUNCH(P)                                                                                                       \
     do {                                                                                                                        \
-        static bool attr_set = false;                                                                                           \
-        if (!attr_set) {                                                                                                        \
-            WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_persist_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, PQ_SMEM_BYTES)); \
-            attr_set = true;                                                                                                    \
-        }                                                                                                                       \
+        WG_SMEM_OPT_IN(attention_d64_persist_kernel<P>, PQ_SMEM_BYTES);                                                         \
         attention_d64_persist_kernel<P><<<grid, 192, PQ_SMEM_BYTES, stream>>>(tmQKV, tmO, p);                                   \
     } while (0)
         switch (poly) {
@@ -896,11 +892,7 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
         dim3 grid((T + ATT_BQ - 1) / ATT_BQ, heads, B);
 #define WG_ATT_LAUNCH(P, S)                                                                                                     \
     do {                                                                                                                        \
-        static bool attr_set = false;                                                                                           \
-        if (!attr_set) {                                                                                                        \
-            WG_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES + smem_pad)); \
-            attr_set = true;                                                                                                    \
-        }                                                                                                                       \
+        WG_SMEM_OPT_IN((attention_d64_kernel<P, S>), ATT_SMEM_BYTES + smem_pad);                                                \
         attention_d64_kernel<P, S><<<grid, att_threads(S), ATT_SMEM_BYTES + smem_pad, stream>>>(tmQKV, tmO, p);                            \
     } while (0)
         if (split == 2) {

@@ -789,7 +789,7 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     const size_t tk_fixed = (size_t)(6 * NT * C + NT * 2048 + NT * (hw > 48 ? hw : 48)) * sizeof(float);
     const int tk_part = (tk_fixed + (size_t)TK_THREADS * 4 * NT * sizeof(float) <= 227 * 1024) ? TK_THREADS * 4 * NT : TK_THREADS * 2 * NT;
     const size_t tk_smem = tk_fixed + (size_t)tk_part * sizeof(float);
-    WG_CHECK_CUDA(cudaFuncSetAttribute(decoder_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    WG_SMEM_OPT_IN(decoder_token_kernel, 227 * 1024);
     WG_REQUIRE(tk_smem <= 227 * 1024, "wg_mask_decoder_forward: token kernel shared memory %zu too large", tk_smem);
 
     TokArgs ta = {};
@@ -805,14 +805,22 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     ta.out_tokens = w->out_tokens; ta.sparse_add = w->sparse_add; ta.txt = txt_emb;
     ta.Tq = d.Tq; ta.Tpe = d.Tpe; ta.KT = d.KT; ta.VT = d.VT; ta.hyper = d.hyper; ta.iou = d.iou_all;
 
-    // bring-up aid: WG_DEBUG_DECODER_STOP=<n> returns after the n-th launch group so intermediates can be inspected
+    // bring-up aid, compiled out of release builds (-DWG_DEBUG): WG_DEBUG_DECODER_STOP=<n> stops after the n-th launch group so
+    // intermediates can be inspected; the call then reports WG_ERR_INVALID because the outputs were not produced
+#ifdef WG_DEBUG
     const char* dbg = getenv("WG_DEBUG_DECODER_STOP");
     const int stop_at = dbg ? atoi(dbg) : 0;
     int step = 0;
-#define WG_DBG_STEP()                         \
-    do {                                      \
-        if (stop_at && ++step == stop_at) return WG_OK; \
+#define WG_DBG_STEP()                                                                                   \
+    do {                                                                                                \
+        if (stop_at && ++step == stop_at) {                                                             \
+            set_error("wg_mask_decoder_forward: stopped after launch group %d (WG_DEBUG_DECODER_STOP)", step); \
+            return WG_ERR_INVALID;                                                                      \
+        }                                                                                               \
     } while (0)
+#else
+#define WG_DBG_STEP() do { } while (0)
+#endif
 
     __nv_bfloat16* keys = d.keysA;
     __nv_bfloat16* keys_next = d.keysB;

@@ -194,11 +194,7 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     p.split_out = (EPI != WG_OUT_F32) ? a->split_out : 0;
 
     auto kern = gemm_bf16_kernel<BN, STAGES, EPI>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        WG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-        attr_set = true;
-    }
+    WG_SMEM_OPT_IN(kern, L::DYN_BYTES);  // per instantiation and device
     int sms = device_sm_count();
     int grid = p.num_tiles < sms ? p.num_tiles : sms;
     static const char* kname = EPI == WG_OUT_BF16 ? (BN == 256 ? "gemm_bf16_bn256" : "gemm_bf16_bn128")
@@ -242,11 +238,10 @@ extern "C" int wg_gemm(const wg_gemm_args* a, void* stream_) {
     }
     const long long tiles256 = (long long)((a->M + 127) / 128) * ((a->N + 255) / 256);
     // CTA-pair kernel (256 x 256 tiles over two SMs) once there is at least one full wave of pair tiles; WG_GEMM_PAIR=0 disables
-    static int pair_enabled = -1;
-    if (pair_enabled < 0) {
+    static const int pair_enabled = [] {
         const char* e = getenv("WG_GEMM_PAIR");
-        pair_enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-    }
+        return (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    }();
     const long long tiles_pair = (long long)((a->M + 255) / 256) * ((a->N + 255) / 256);
     const bool use_pair = pair_enabled && a->conv_grid == 0 && (a->N % 256 == 0) && tiles_pair >= device_sm_count() / 2;
     switch (a->out_mode) {

@@ -253,11 +253,7 @@ int launch2(const wg_gemm_args* a, cudaStream_t stream) {
     p.split_out = (EPI != WG_OUT_F32) ? a->split_out : 0;
 
     auto kern = gemm2_bf16_kernel<STAGES, EPI>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        WG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-        attr_set = true;
-    }
+    WG_SMEM_OPT_IN(kern, L::DYN_BYTES);  // per instantiation and device
     const int max_pairs = device_sm_count() / 2;
     const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
     static const char* kname = EPI == WG_OUT_BF16 ? "gemm2_bf16" : EPI == WG_OUT_F32 ? "gemm2_f32" : "gemm2_bf16ln";

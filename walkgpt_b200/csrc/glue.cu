@@ -397,6 +397,41 @@ extern "C" int wg_resample_tokens(const void* tokens, int is_bf16, int n, int p,
     return WG_OK;
 }
 
+// prompt -> image index from the per-image [SEG] offsets, on the device (no host list, no synchronisation).  One thread per
+// prompt: binary search for the image whose [offsets[b], offsets[b+1]) holds it.  Offsets that are not a non-decreasing
+// sequence from 0 to P cannot index out of bounds: the result is clamped to [0, B-1] and *status is set to 1.
+namespace wg {
+__global__ void __launch_bounds__(256) prompt_index_kernel(const int* __restrict__ offs, int B, int P, int* __restrict__ prompt_img, int* __restrict__ status) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0 && status != nullptr) {
+        int bad = (offs[0] != 0) || (offs[B] != P);
+        for (int b = 0; b < B; ++b) bad |= (offs[b + 1] < offs[b]);
+        *status = bad;
+    }
+    if (p >= P) return;
+    int lo = 0, hi = B;  // largest b in [0, B-1] with offs[b] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offs[mid] <= p) lo = mid; else hi = mid;
+    }
+    prompt_img[p] = lo;
+}
+}  // namespace wg
+
+extern "C" int wg_prompt_index(const int32_t* seg_offsets, int B, int P, int32_t* prompt_img, int32_t* status, void* stream_) {
+    using namespace wg;
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    WG_REQUIRE(seg_offsets && prompt_img && B > 0 && P >= 0, "wg_prompt_index: bad arguments");
+    if (!device_is_sm100()) {
+        set_error("wg_prompt_index: this library only runs on sm_100 (B200) devices; there is no fallback");
+        return WG_ERR_UNSUPPORTED;
+    }
+    Prof prof("prompt_index", s);
+    prompt_index_kernel<<<(P > 0 ? (P + 255) / 256 : 1), 256, 0, s>>>(seg_offsets, B, P, prompt_img, status);
+    WG_CHECK_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
 extern "C" int wg_seg_gather(const int64_t* input_ids, int rows, int Lin, const void* hidden, int hidden_is_bf16, int L, int H, const int64_t* seg_ids,
                              int n_seg_ids, int shift, const int32_t* img_rows, int n_img_p1, void* out, int max_out, int32_t* counts,
                              int32_t* row_offsets, int32_t* img_offsets, void* stream_) {
@@ -422,13 +457,11 @@ extern "C" int wg_seg_gather(const int64_t* input_ids, int rows, int Lin, const 
     const size_t smem = (size_t)L * sizeof(int);
     WG_REQUIRE(smem <= 200 * 1024, "wg_seg_gather: sequence length %d too long", L);
     if (hidden_is_bf16) {
-        static bool attr = false;
-        if (!attr) { WG_CHECK_CUDA(cudaFuncSetAttribute(seg_gather_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        WG_SMEM_OPT_IN((seg_gather_kernel<__nv_bfloat16>), 200 * 1024);
         seg_gather_kernel<__nv_bfloat16><<<rows, 256, smem, s>>>(ids, Lin, L, shift, seg, row_offsets, static_cast<const __nv_bfloat16*>(hidden), H,
                                                                static_cast<__nv_bfloat16*>(out), max_out);
     } else {
-        static bool attr = false;
-        if (!attr) { WG_CHECK_CUDA(cudaFuncSetAttribute(seg_gather_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        WG_SMEM_OPT_IN((seg_gather_kernel<float>), 200 * 1024);
         seg_gather_kernel<float><<<rows, 256, smem, s>>>(ids, Lin, L, shift, seg, row_offsets, static_cast<const float*>(hidden), H, static_cast<float*>(out), max_out);
     }
     WG_CHECK_CUDA(cudaGetLastError());
@@ -487,12 +520,10 @@ extern "C" int wg_match_cost(const float* pred_logits, const void* tgt_masks, in
     float* partial = static_cast<float*>(workspace);
     Prof prof("match_cost", s, 0.0, 16.0 * (double)(n_pred + n_tgt) * num_points, 2);
     if (tgt_is_u8) {
-        static bool attr_u8 = false;
-        if (!attr_u8) { WG_CHECK_CUDA(cudaFuncSetAttribute(match_sample_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * MATCH_LD * 4)); attr_u8 = true; }
+        WG_SMEM_OPT_IN((match_sample_kernel<uint8_t>), 4 * 64 * MATCH_LD * 4);
         match_sample_kernel<uint8_t><<<chunks, MATCH_PTS, smem, s>>>(pred_logits, static_cast<const uint8_t*>(tgt_masks), point_coords, n_pred, n_tgt, H, W, num_points, partial);
     } else {
-        static bool attr_f = false;
-        if (!attr_f) { WG_CHECK_CUDA(cudaFuncSetAttribute(match_sample_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * MATCH_LD * 4)); attr_f = true; }
+        WG_SMEM_OPT_IN((match_sample_kernel<float>), 4 * 64 * MATCH_LD * 4);
         match_sample_kernel<float><<<chunks, MATCH_PTS, smem, s>>>(pred_logits, static_cast<const float*>(tgt_masks), point_coords, n_pred, n_tgt, H, W, num_points, partial);
     }
     match_finalize_kernel<<<(n_pred * n_tgt + 127) / 128, 128, 0, s>>>(partial, chunks, n_pred, n_tgt, num_points, cost);

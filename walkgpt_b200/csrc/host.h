@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/walkgpt_b200.h"
 
 namespace wg {
@@ -29,6 +31,20 @@ void set_error(const char* fmt, ...);  // thread-local message for wg_last_error
             ::wg::set_error(__VA_ARGS__);            \
             return WG_ERR_INVALID;                   \
         }                                            \
+    } while (0)
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so the
+// "already done" flag of each call site is one bit per device ordinal; safe to race (setting the attribute twice is harmless).
+#define WG_SMEM_OPT_IN(kern, bytes)                                                                              \
+    do {                                                                                                         \
+        static std::atomic<unsigned long long> _wg_done{0};                                                      \
+        int _wg_dev = 0;                                                                                         \
+        WG_CHECK_CUDA(cudaGetDevice(&_wg_dev));                                                                  \
+        const unsigned long long _wg_bit = 1ull << (_wg_dev & 63);                                               \
+        if (_wg_dev >= 64 || !(_wg_done.load(std::memory_order_acquire) & _wg_bit)) {                            \
+            WG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _wg_done.fetch_or(_wg_bit, std::memory_order_release);                                               \
+        }                                                                                                        \
     } while (0)
 
 #define WG_TRY(expr)                 \

@@ -418,7 +418,7 @@ extern "C" int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16,
         WG_CHECK_CUDA(cudaGetLastError());
         const size_t smem = (size_t)(MAXQ * 128 + (size_t)QPAD * Nkv + 4 * MAXQ * 128) * sizeof(float);
         WG_REQUIRE(smem <= 227 * 1024, "wg_msqp_forward: %d kv tokens x %d queries exceed shared memory", Nkv, S.nq);
-        WG_CHECK_CUDA(cudaFuncSetAttribute(msqp_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        WG_SMEM_OPT_IN(msqp_attention_kernel, 227 * 1024);
         for (int l = 0; l < 2; ++l) {
             const wg_msqp_block& Bk = S.blocks[l];
             WG_TRY(wg_layernorm(m.q[sc], 0, D, Bk.qn_g, Bk.qn_b, 1e-5f, m.qn, D, Mq, D, s));

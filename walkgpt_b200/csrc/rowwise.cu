@@ -241,12 +241,10 @@ int launch_im2col_patch(const void* pixels, int is_bf16, void* out_bf16, int B, 
     if (P % 2 == 0 && IMG % 2 == 0 && KPAD % 8 == 0 && slab_bytes <= 200 * 1024 && B <= 65535) {
         const dim3 grid(G, B);
         if (is_bf16) {
-            static bool attr = false;
-            if (!attr) { WG_CHECK_CUDA(cudaFuncSetAttribute(im2col_patch_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+            WG_SMEM_OPT_IN((im2col_patch_rows_kernel<__nv_bfloat16>), 200 * 1024);
             im2col_patch_rows_kernel<__nv_bfloat16><<<grid, 256, slab_bytes, s>>>(static_cast<const __nv_bfloat16*>(pixels), static_cast<__nv_bfloat16*>(out_bf16), IMG, P, KPAD);
         } else {
-            static bool attr = false;
-            if (!attr) { WG_CHECK_CUDA(cudaFuncSetAttribute(im2col_patch_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+            WG_SMEM_OPT_IN((im2col_patch_rows_kernel<float>), 200 * 1024);
             im2col_patch_rows_kernel<float><<<grid, 256, slab_bytes, s>>>(static_cast<const float*>(pixels), static_cast<__nv_bfloat16*>(out_bf16), IMG, P, KPAD);
         }
     } else if (is_bf16)

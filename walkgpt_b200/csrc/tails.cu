@@ -151,13 +151,13 @@ __global__ void finalize_score_kernel(const float* __restrict__ accum, float* __
 // depth extension: pooled [P][33] -> raw[p] = W2 . gelu(W1 . pooled_c + b1) + b2 ; min-max normalised inside each image
 __global__ void __launch_bounds__(256) depth_head_kernel(const float* __restrict__ pooled, const int* __restrict__ seg_offsets, const float* __restrict__ w1,
                                                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                                                         float* __restrict__ depth) {
-    extern __shared__ float raw[];  // [S]
+                                                         float* __restrict__ depth, int max_S) {
+    extern __shared__ float raw[];  // [max_S]
     __shared__ float red[8];
     const int img = blockIdx.x;
     const int p0 = seg_offsets[img], p1 = seg_offsets[img + 1];
-    const int S = p1 - p0;
-    if (S <= 0) return;
+    if (p1 <= p0 || p0 < 0) return;
+    const int S = min(p1 - p0, max_S);  // raw[] holds max_S entries: inconsistent offsets cannot overrun it
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int sidx = 0; sidx < S; ++sidx) {
         const float* pp = pooled + (size_t)(p0 + sidx) * 33;
@@ -292,7 +292,7 @@ extern "C" int wg_depth_head(const float* pooled, const int32_t* seg_offsets, in
         return WG_ERR_UNSUPPORTED;
     }
     Prof prof("depth_head", s);
-    depth_head_kernel<<<B, 256, (size_t)(max_S > 0 ? max_S : 1) * sizeof(float), s>>>(pooled, seg_offsets, w1, b1, w2, b2, depth_out);
+    depth_head_kernel<<<B, 256, (size_t)(max_S > 0 ? max_S : 1) * sizeof(float), s>>>(pooled, seg_offsets, w1, b1, w2, b2, depth_out, max_S > 0 ? max_S : 1);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
 }

@@ -74,15 +74,21 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 
 class _Workspace:
-    """Grow-only device scratch buffer owned by a module (torch owns the memory, the C side only borrows it)."""
+    """Grow-only device scratch owned by a module (torch owns the memory, the C side only borrows it), one buffer per
+    (device, CUDA stream): kernels on one stream are ordered, so consecutive calls may share scratch; calls issued on different
+    streams (or devices) never share it.  A buffer that has to grow is replaced through torch's stream-aware caching allocator,
+    which does not hand the old block to another stream while this stream's kernels may still be using it."""
 
     def __init__(self):
-        self.buf: Optional[torch.Tensor] = None
+        self.bufs: Dict[Tuple[int, int], torch.Tensor] = {}
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
-            self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-        return self.buf
+        device = torch.device(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = self.bufs[key] = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        return buf
 
 
 # --------------------------------------------------------------------------------------------------
@@ -764,9 +770,14 @@ class MaskDecoderMultiScale(_SpecModule):
     def _pack(self):
         return self._pack_static(0)
 
-    def bind_prompt_constants(self, pe_tokens: torch.Tensor, no_mask: torch.Tensor, grid: Tuple[int, int], level: int = 0) -> None:
+    def bind_prompt_constants(self, pe_tokens: torch.Tensor, no_mask: torch.Tensor, grid: Tuple[int, int], level: int = 0,
+                              identity: Optional[Tuple[torch.Tensor, ...]] = None) -> None:
         """Fold the dense positional encoding into per-position bias tables (pe W^T + b; one-time fp32 constant folding, like
-        the LayerNorm-affine folding in MSQP) and record the dense (no-mask) prompt embedding.  Cached until inputs/weights change."""
+        the LayerNorm-affine folding in MSQP) and record the dense (no-mask) prompt embedding.  Cached until inputs/weights change.
+
+        The cache is keyed by the address and version counter of the ``identity`` tensors (default: the two inputs), and the
+        cache keeps those tensors ALIVE: a freed temporary's address could otherwise be handed to a different tensor with the
+        same version counter and hit a stale entry."""
         if level == 0:
             w, hold = self._packed or self._pack()
         else:
@@ -774,7 +785,8 @@ class MaskDecoderMultiScale(_SpecModule):
             if level not in self._levels:
                 self._pack_static(level)
             w, hold = self._levels[level]["packed"]
-        key = (pe_tokens.data_ptr(), pe_tokens._version, no_mask.data_ptr(), no_mask._version, tuple(grid))
+        identity = tuple(identity) if identity is not None else (pe_tokens, no_mask)
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride())) for t in identity) + (tuple(grid),)
         if (self._pe_key if level == 0 else self._levels[level]["pe_key"]) == key:
             return
         sd = self._sd()
@@ -804,6 +816,7 @@ class MaskDecoderMultiScale(_SpecModule):
                             sd[T + "final_attn_token_to_image.v_proj.bias"])
         nm = _f32(no_mask.reshape(-1))
         keep.append(nm)
+        keep.append(identity)  # pins the keyed tensors' storage for as long as the key is cached
         w.no_mask = nm.data_ptr()
         w.grid_h, w.grid_w = grid
         if level == 0:
@@ -877,18 +890,24 @@ class MaskDecoderMultiScale(_SpecModule):
             emb_tok = to_split(image_embeddings.reshape(1, Cc, h * wd).permute(0, 2, 1))
             txt = sparse_prompt_embeddings.reshape(S, Cc).float().contiguous()
             pimg = torch.zeros(S, dtype=torch.int32, device=image_embeddings.device)
+            # the cache identity is the CALLER's tensors (pe_tok / dense_vec are temporaries derived from them)
+            ident = (image_pe, dense_prompt_embeddings)
             if level_num == 0:
-                self.bind_prompt_constants(pe_tok, dense_vec, (h, wd))
+                self.bind_prompt_constants(pe_tok, dense_vec, (h, wd), identity=ident)
                 low, iou, _ = self.run(emb_tok, txt, pimg, multimask_output)
             else:
                 # mask_decoder_multi_scale.py:165-171: up-sampled embedding gated by the previous masks, pe1 on the 2h x 2w grid;
                 # the dense prompt embedding is no_mask_embed broadcast, so its bilinear resize is the same constant
-                gauss = _f32(self._sd()["pe1.positional_encoding_gaussian_matrix"])
-                F_ = gauss.shape[1]
-                pe1_tok = torch.empty(4 * h * wd, 2 * F_, device=image_embeddings.device, dtype=torch.float32)
-                _lib.check(_lib.lib().wg_dense_pe(gauss.data_ptr(), F_, 2 * h, 2 * wd, None, pe1_tok.data_ptr(), _stream()), "wg_dense_pe")
-                self._pe1_keep = (gauss, pe1_tok)
-                self.bind_prompt_constants(pe1_tok, dense_vec, (2 * h, 2 * wd), level=1)
+                g_param = self.pe1.positional_encoding_gaussian_matrix
+                pe1_key = (g_param.data_ptr(), g_param._version, h, wd)
+                if getattr(self, "_pe1_cache", None) is None or self._pe1_cache[0] != pe1_key:
+                    gauss = _f32(g_param)
+                    F_ = gauss.shape[1]
+                    pe1_tok = torch.empty(4 * h * wd, 2 * F_, device=image_embeddings.device, dtype=torch.float32)
+                    _lib.check(_lib.lib().wg_dense_pe(gauss.data_ptr(), F_, 2 * h, 2 * wd, None, pe1_tok.data_ptr(), _stream()), "wg_dense_pe")
+                    self._pe1_cache = (pe1_key, pe1_tok)
+                pe1_tok = self._pe1_cache[1]
+                self.bind_prompt_constants(pe1_tok, dense_vec, (2 * h, 2 * wd), level=1, identity=(pe1_tok, dense_prompt_embeddings))
                 up_tok = self.upsample_embedding(emb_tok, (h, wd))
                 low, iou, _ = self.run(up_tok, txt, pimg, multimask_output, level=1, prev_masks=previous_masks.float().contiguous())
         return low.to(dt), iou.to(dt)
@@ -1009,6 +1028,44 @@ class DepthHead(_SpecModule):
         return out
 
 
+class _PromptIndex:
+    """Per-image [SEG] offsets -> (offsets int32 [B+1] on the device, prompt -> image index int32 [P], P, max prompts per image).
+
+    A host sequence is validated on the host and its device copies are cached by value (a fixed number of [SEG] per image -- the
+    benchmark, most evaluation batches -- then costs no launch and no copy at all); a device tensor goes through the
+    ``wg_prompt_index`` kernel, which clamps inconsistent offsets instead of indexing out of bounds (no host synchronisation, so
+    the number of prompts per image is bounded by P for the depth head's shared memory)."""
+
+    def __init__(self, capacity: int = 32):
+        self.cache: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
+        self.capacity = capacity
+
+    def index(self, seg_offsets, B: int, n_rows: int, dev) -> Tuple[torch.Tensor, torch.Tensor, int, int]:
+        dev = torch.device(dev)
+        if torch.is_tensor(seg_offsets):
+            if seg_offsets.numel() != B + 1:
+                raise ValueError(f"seg_offsets must have B + 1 = {B + 1} entries, got {seg_offsets.numel()}")
+            offs_dev = seg_offsets.to(device=dev, dtype=torch.int32).contiguous()
+            P = n_rows
+            prompt_img = torch.empty(P, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().wg_prompt_index(offs_dev.data_ptr(), B, P, prompt_img.data_ptr(), None, _stream()), "wg_prompt_index")
+            return offs_dev, prompt_img, P, P
+        offs = tuple(int(v) for v in seg_offsets)
+        if len(offs) != B + 1 or offs[0] != 0 or offs[-1] != n_rows or any(offs[i + 1] < offs[i] for i in range(B)):
+            raise ValueError(f"seg_offsets must be B + 1 = {B + 1} non-decreasing offsets from 0 to the number of [SEG] rows ({n_rows})")
+        key = (offs, dev.index)
+        hit = self.cache.get(key)
+        if hit is None:
+            if len(self.cache) >= self.capacity:
+                self.cache.pop(next(iter(self.cache)))
+            counts = [offs[i + 1] - offs[i] for i in range(B)]
+            host = torch.tensor(offs, dtype=torch.int32)
+            img = torch.repeat_interleave(torch.arange(B, dtype=torch.int32), torch.tensor(counts, dtype=torch.long))
+            hit = self.cache[key] = (host.to(dev), img.to(dev), offs[-1], max(counts + [0]))
+        return hit
+
+
 # --------------------------------------------------------------------------------------------------
 # Path A composition (SURVEY §8): the batched grounding forward a caller uses instead of the reference's
 # per-image Python loops (model/walkgpt.py:511-541, 713-743).
@@ -1034,6 +1091,7 @@ class GroundingPath(nn.Module):
                                                   image_feature_scale_num=1, seed=seed)
         self.depth_head = DepthHead(seed=seed) if with_depth else None
         self.hidden_size = hidden_size
+        self._prompts = _PromptIndex()
 
     @torch.no_grad()
     def forward(self, images_clip: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, attention_mask: Optional[torch.Tensor] = None,
@@ -1045,18 +1103,7 @@ class GroundingPath(nn.Module):
         B = images_clip.shape[0]
         input_size = input_size or (self.image, self.image)
         original_size = original_size or input_size
-        if torch.is_tensor(seg_offsets):
-            offs_dev = seg_offsets.to(device=dev, dtype=torch.int32)
-            counts = (offs_dev[1:] - offs_dev[:-1]).long()
-            P = seg_hidden.shape[0]
-            max_S = P
-        else:
-            offs = [int(v) for v in seg_offsets]
-            assert len(offs) == B + 1 and offs[0] == 0 and offs[-1] == seg_hidden.shape[0]
-            offs_dev = torch.tensor(offs, dtype=torch.int32, device=dev)
-            counts = (offs_dev[1:] - offs_dev[:-1]).long()
-            P = offs[-1]
-            max_S = max([offs[i + 1] - offs[i] for i in range(B)] + [0])
+        offs_dev, prompt_img, P, max_S = self._prompts.index(seg_offsets, B, seg_hidden.shape[0], dev)
         out: Dict[str, torch.Tensor] = {}
         with torch.cuda.device(dev):
             feats, _ = self.vision_tower(images_clip.to(torch.bfloat16) if images_clip.dtype != torch.bfloat16 else images_clip, attention_mask,
@@ -1067,7 +1114,6 @@ class GroundingPath(nn.Module):
             out["img_emb_split"] = emb  # split-bf16 [B, hw, 512]; merge_split() gives the fp32 [B, hw, 256] embedding
             txt = self.text_hidden_fcs[0].run(_as_kernel_input(seg_hidden), torch.float32)
             out["txt_emb"] = txt
-            prompt_img = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), counts, output_size=P)
             _, pe_tok = self.prompt_encoder.dense_pe_tokens()
             self.mask_decoder._packed or self.mask_decoder._pack()
             self.mask_decoder.bind_prompt_constants(pe_tok, self.prompt_encoder.no_mask_embed.weight, (self.grid, self.grid))
@@ -1093,6 +1139,7 @@ class GroundingPathB(nn.Module):
         self.text_hidden_fcs = nn.ModuleList([CalibratedTextProjector(hidden_size, 256, widen=2, use_residual=False, seed=seed)])
         self.prompt_encoder = PromptEncoder(256, (grid, grid), (image, image), 16, seed=seed)
         self.mask_decoder = MaskDecoder(transformer_dim=256, num_multimask_outputs=3, iou_head_depth=3, iou_head_hidden_dim=256, seed=seed)
+        self._prompts = _PromptIndex()
 
     @torch.no_grad()
     def forward(self, image_embeddings: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, input_size: Optional[Tuple[int, int]] = None,
@@ -1105,10 +1152,7 @@ class GroundingPathB(nn.Module):
         assert Cc == 256 and (h, wd) == (self.grid, self.grid)
         input_size = input_size or (self.image, self.image)
         original_size = original_size or input_size
-        offs = [int(v) for v in seg_offsets]
-        assert len(offs) == B + 1 and offs[0] == 0 and offs[-1] == seg_hidden.shape[0]
-        counts = torch.tensor([offs[i + 1] - offs[i] for i in range(B)], dtype=torch.long, device=dev)
-        P = offs[-1]
+        _, prompt_img, P, _ = self._prompts.index(seg_offsets, B, seg_hidden.shape[0], dev)
         out: Dict[str, torch.Tensor] = {}
         with torch.cuda.device(dev):
             tokens = image_embeddings.reshape(B, Cc, h * wd).permute(0, 2, 1)       # [B, hw, 256] (layout change only)
@@ -1116,7 +1160,6 @@ class GroundingPathB(nn.Module):
                 out["vis_tokens"] = self.msqp.run(tokens.to(torch.bfloat16).contiguous(), torch.bfloat16)
             txt = self.text_hidden_fcs[0].run(_as_kernel_input(seg_hidden), torch.float32)
             out["txt_emb"] = txt
-            prompt_img = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), counts, output_size=P)
             _, pe_tok = self.prompt_encoder.dense_pe_tokens()
             self.mask_decoder._packed or self.mask_decoder._pack()
             self.mask_decoder.bind_prompt_constants(pe_tok, self.prompt_encoder.no_mask_embed.weight, (h, wd))
