@@ -200,7 +200,10 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     static const char* kname = EPI == WG_OUT_BF16 ? (BN == 256 ? "gemm_bf16_bn256" : "gemm_bf16_bn128")
                                : EPI == WG_OUT_F32 ? (BN == 256 ? "gemm_f32_bn256" : "gemm_f32_bn128") : "gemm_bf16ln_bn256";
     const double out_bytes = (double)a->M * a->N * (EPI == WG_OUT_F32 ? (a->resid ? 8.0 : 4.0) : (a->resid ? 4.0 : 2.0));
-    Prof prof(kname, stream, 2.0 * a->M * a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
+    // ALGORITHMIC flops: a split-bf16 operand ([hi | lo | hi] against [W_hi | W_hi | W_lo], K = 2C or 3C executed) stands for ONE
+    // fp32-accurate product over C = a_k_wrap / 2 columns
+    const double k_alg = a->a_k_wrap > 0 ? 0.5 * a->a_k_wrap : (double)a->K;
+    Prof prof(kname, stream, 2.0 * a->M * a->N * k_alg, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
     kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, p);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;

@@ -258,7 +258,10 @@ int launch2(const wg_gemm_args* a, cudaStream_t stream) {
     const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
     static const char* kname = EPI == WG_OUT_BF16 ? "gemm2_bf16" : EPI == WG_OUT_F32 ? "gemm2_f32" : "gemm2_bf16ln";
     const double out_bytes = (double)a->M * a->N * (EPI == WG_OUT_F32 ? (a->resid ? 8.0 : 4.0) : (a->resid ? 4.0 : 2.0));
-    Prof prof(kname, stream, 2.0 * a->M * a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
+    // ALGORITHMIC flops: a split-bf16 operand ([hi | lo | hi] against [W_hi | W_hi | W_lo], K = 2C or 3C executed) stands for ONE
+    // fp32-accurate product over C = a_k_wrap / 2 columns
+    const double k_alg = a->a_k_wrap > 0 ? 0.5 * a->a_k_wrap : (double)a->K;
+    Prof prof(kname, stream, 2.0 * a->M * a->N * k_alg, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
     kern<<<2 * pairs, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, p);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;

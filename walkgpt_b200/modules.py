@@ -1094,35 +1094,53 @@ class GroundingPath(nn.Module):
         self._prompts = _PromptIndex()
 
     @torch.no_grad()
-    def forward(self, images_clip: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, attention_mask: Optional[torch.Tensor] = None,
-                input_size: Optional[Tuple[int, int]] = None, original_size: Optional[Tuple[int, int]] = None, want_vis_tokens: bool = True):
-        """images_clip [B,3,448,448]; seg_hidden [sum S, H] (LLM hidden states at the [SEG] positions);
-        seg_offsets: int sequence / tensor [B+1].  Returns a dict of device tensors."""
-        _need_cuda(images_clip, "GroundingPath.forward")
-        dev = images_clip.device
-        B = images_clip.shape[0]
-        input_size = input_size or (self.image, self.image)
-        original_size = original_size or input_size
-        offs_dev, prompt_img, P, max_S = self._prompts.index(seg_offsets, B, seg_hidden.shape[0], dev)
+    def encode_images(self, images_clip: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, want_vis_tokens: bool = True):
+        """First half (before the LLM): CLIP tower -> MSQP visual tokens [B,36,H] (handed to the reference LLM, which resamples them to
+        16 x 16, llava_arch.py:252-259) and out_mm_projector + neck -> image embedding, split-bf16 tokens [B, hw, 512]."""
+        _need_cuda(images_clip, "GroundingPath.encode_images")
         out: Dict[str, torch.Tensor] = {}
-        with torch.cuda.device(dev):
+        with torch.cuda.device(images_clip.device):
             feats, _ = self.vision_tower(images_clip.to(torch.bfloat16) if images_clip.dtype != torch.bfloat16 else images_clip, attention_mask,
                                          want_mid=False)
             if want_vis_tokens:
                 out["vis_tokens"] = self.msqp.run(feats, torch.bfloat16)
             _, emb = self.proj_neck.run(feats)
             out["img_emb_split"] = emb  # split-bf16 [B, hw, 512]; merge_split() gives the fp32 [B, hw, 256] embedding
+        return out
+
+    @torch.no_grad()
+    def ground(self, img_emb_split: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, input_size: Optional[Tuple[int, int]] = None,
+               original_size: Optional[Tuple[int, int]] = None):
+        """Second half (after the LLM): [SEG] hidden states [sum S, H] -> CTP -> prompt encoder + mask decoder on the image embeddings
+        of ``encode_images`` -> postprocess / threshold / score (+ depth extension)."""
+        _need_cuda(img_emb_split, "GroundingPath.ground")
+        dev = img_emb_split.device
+        B = img_emb_split.shape[0]
+        input_size = input_size or (self.image, self.image)
+        original_size = original_size or input_size
+        offs_dev, prompt_img, P, max_S = self._prompts.index(seg_offsets, B, seg_hidden.shape[0], dev)
+        out: Dict[str, torch.Tensor] = {}
+        with torch.cuda.device(dev):
             txt = self.text_hidden_fcs[0].run(_as_kernel_input(seg_hidden), torch.float32)
             out["txt_emb"] = txt
             _, pe_tok = self.prompt_encoder.dense_pe_tokens()
             self.mask_decoder._packed or self.mask_decoder._pack()
             self.mask_decoder.bind_prompt_constants(pe_tok, self.prompt_encoder.no_mask_embed.weight, (self.grid, self.grid))
-            low, iou, pool = self.mask_decoder.run(emb, txt, prompt_img, False, want_depth_pool=self.depth_head is not None)
+            low, iou, pool = self.mask_decoder.run(img_emb_split, txt, prompt_img, False, want_depth_pool=self.depth_head is not None)
             out["low_res"], out["iou"] = low, iou
             logits, mask, score = postprocess_masks_fused(low[:, 0], input_size, original_size)
             out["logits"], out["masks"], out["scores"] = logits, mask, score
             if self.depth_head is not None:
                 out["depth"] = self.depth_head(pool, offs_dev, max_S)
+        return out
+
+    @torch.no_grad()
+    def forward(self, images_clip: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, attention_mask: Optional[torch.Tensor] = None,
+                input_size: Optional[Tuple[int, int]] = None, original_size: Optional[Tuple[int, int]] = None, want_vis_tokens: bool = True):
+        """images_clip [B,3,448,448]; seg_hidden [sum S, H] (LLM hidden states at the [SEG] positions);
+        seg_offsets: int sequence / tensor [B+1].  Returns a dict of device tensors (encode_images + ground)."""
+        out = self.encode_images(images_clip, attention_mask, want_vis_tokens)
+        out.update(self.ground(out["img_emb_split"], seg_hidden, seg_offsets, input_size, original_size))
         return out
 
 
