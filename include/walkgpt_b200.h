@@ -346,6 +346,44 @@ WG_API int wg_postprocess_masks(const float* low_res, int n_masks, int Hm, int W
 WG_API int wg_depth_head(const float* pooled, const int32_t* seg_offsets, int B, int max_S, const float* w1, const float* b1,
                          const float* w2, const float* b2, float* depth_out, void* stream);
 
+/* ---- the SAM ViT image encoder (Path B's pixel encoder) ------------------------------------------------- */
+
+/* Attention.forward + add_decomposed_rel_pos (segment_anything/modeling/image_encoder.py:222-247, 325-361), head_dim 80, SAM geometry
+ * (64 x 64 map; mode 0 = 14 x 14 windows of the zero-padded 70 x 70 map, mode 1 = global).
+ *   qkv bf16 [rows, 3*heads*80], columns [Q main (heads x 64) | K main | V main | Q rem (heads x 16) | K rem | V rem]: head h's vector is
+ *       its 64 main columns followed by its 16 rem columns; rows: mode 0 = WINDOW-major [image, 25 windows, 196 tokens] (pad tokens
+ *       included -- they are keys, as in the reference), mode 1 = image-major [image, 4096].
+ *   rel_table bf16: mode 0 [64, 80] = rel_pos_h (27 rows) at row 0 and rel_pos_w at row 32, other rows zero;
+ *                   mode 1 [256, 80] = rel_pos_h (127 rows) at row 0 and rel_pos_w at row 128.
+ *   out bf16 [n_images * 4096, heads * 80], image-major (mode 0 un-partitions and drops the pad tokens). */
+WG_API int wg_sam_attention(const void* qkv, const void* rel_table, void* out, int n_images, int mode, int heads, void* stream);
+
+typedef struct wg_sam_block {
+    const float* ln1_g; const float* ln1_b;
+    const void* w_qkv;  const float* b_qkv;   /* bf16 [3*hidden, hidden], fp32 [3*hidden]: rows in the column order wg_sam_attention reads */
+    const void* rel_table;                     /* see wg_sam_attention */
+    const void* w_proj; const float* b_proj;  /* bf16 [hidden, hidden] */
+    const float* ln2_g; const float* ln2_b;
+    const void* w_fc1;  const float* b_fc1;   /* bf16 [mlp, hidden]  (MLPBlock lin1, erf GELU) */
+    const void* w_fc2;  const float* b_fc2;   /* bf16 [hidden, mlp] */
+    int32_t is_global; int32_t reserved;
+} wg_sam_block;
+
+typedef struct wg_sam_encoder_weights {
+    int32_t hidden, heads, mlp, image, patch, depth, out_chans, reserved;  /* ViT-H: 1280, 16, 5120, 1024, 16, 32, 256 */
+    const void* patch_w;                      /* bf16 [hidden, 3*patch*patch]: conv weight flattened (c, dy, dx) */
+    const float* pos_bias;                    /* fp32 [4096, hidden] = pos_embed + patch_embed.proj.bias */
+    const wg_sam_block* blocks;               /* HOST array of `depth` entries */
+    wg_proj_neck_weights neck;                /* neck.0 / neck.1 / neck.2 / neck.3 in the fields w_conv1, ln1, w_conv3, ln2; hidden = this hidden */
+} wg_sam_encoder_weights;
+
+WG_API size_t wg_sam_encoder_workspace_bytes(const wg_sam_encoder_weights* w, int B);
+/* ImageEncoderViT.forward (image_encoder.py:107-116): pixels [B,3,1024,1024] fp32 or bf16 -> image embedding TOKENS, split-bf16
+ * [B*4096, 512] (channels-last, hi | lo; nullable) after `n_run` blocks + neck; x_out (nullable) fp32 [B*4096, hidden] receives the
+ * residual stream after the n_run blocks (what the reference's blocks return before the neck). */
+WG_API int wg_sam_encoder_forward(const wg_sam_encoder_weights* w, const void* pixels, int pixels_is_bf16, int B, int n_run,
+                                  void* emb_tokens_split, float* x_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- SURVEY section 8(f), "next" rows: the steps on either side of the grounding path ------------------------------------- */
 
 /* F2a -- visual-token resample handed to the LLM (model/llava_walkgpt/model/llava_arch.py:252-259):

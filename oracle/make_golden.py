@@ -250,8 +250,49 @@ def make_sam_encoder():
     save("sam_encoder_small", {"cfg": cfg, "seed": 31, "pixels_seed": 611, "out": ref(x), "ln_eps": 1e-6})
 
 
+def sam_encoder_full_geometry_cfg():
+    return dict(img_size=1024, patch=16, embed=640, depth=2, heads=8, window_size=14, global_attn_indexes=(1,), out_chans=256)
+
+
+@torch.no_grad()
+def make_sam_encoder_full_geometry():
+    """The reference ImageEncoderViT at SAM's REAL geometry -- 1024-pixel input, 64 x 64 map, head_dim 80, 14 x 14 windows padded 64 -> 70,
+    one windowed and one global block, relative-position tables of 27 / 127 rows, neck -- at a reduced width (8 heads) so that the file
+    stays small.  Weights are rounded to bf16 (what the CUDA path stores) before the reference runs in fp32.  Saves the output subsampled
+    by 4 in both map axes plus whole-map statistics, and the attention of the two block kinds in isolation (qkv -> softmax(qk + rel) v,
+    before proj) for the kernel-level test.  Writes tests/golden/sam_encoder_1024.pt:  python -m oracle.make_golden sam_encoder_1024"""
+    from model.segment_anything.modeling.image_encoder import ImageEncoderViT, add_decomposed_rel_pos
+
+    cfg = sam_encoder_full_geometry_cfg()
+    ref = ImageEncoderViT(img_size=cfg["img_size"], patch_size=cfg["patch"], embed_dim=cfg["embed"], depth=cfg["depth"], num_heads=cfg["heads"],
+                          out_chans=cfg["out_chans"], use_rel_pos=True, window_size=cfg["window_size"],
+                          global_attn_indexes=cfg["global_attn_indexes"], norm_layer=lambda d: nn.LayerNorm(d, eps=1e-6)).eval()
+    spec = specs.sam_image_encoder_spec(cfg["img_size"], cfg["patch"], cfg["embed"], cfg["depth"], cfg["heads"], 4.0, cfg["out_chans"],
+                                        cfg["window_size"], cfg["global_attn_indexes"])
+    sd = {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v) for k, v in specs.make_state_dict(spec, seed=33).items()}
+    ref.load_state_dict(sd, strict=True)
+    x = rnd((1, 3, cfg["img_size"], cfg["img_size"]), 613).to(torch.bfloat16).float()
+    out = ref(x)
+    # attention of each block kind in isolation, on seeded bf16-representable q / k / v (the reference's own arithmetic, Attention.forward
+    # lines 231-247 without the qkv / proj linears)
+    att = {}
+    for tag, n, side, blk in (("window", 3, 14, 0), ("global", 1, 64, 1)):
+        a = ref.blocks[blk].attn
+        heads, d = 2, 80
+        q, k, v = (rnd((n * heads, side * side, d), 700 + i + 10 * blk).to(torch.bfloat16).float() for i in range(3))
+        s = (q * a.scale) @ k.transpose(-2, -1)
+        s = add_decomposed_rel_pos(s, q, a.rel_pos_h, a.rel_pos_w, (side, side), (side, side))
+        o = s.softmax(dim=-1) @ v
+        att[tag] = {"n": n, "heads": heads, "seeds": [700 + i + 10 * blk for i in range(3)], "out_sub": o[:, ::7].clone(), "out_absmax": o.abs().max(),
+                    "block": blk}
+    save("sam_encoder_1024", {"cfg": cfg, "seed": 33, "pixels_seed": 613, "out_sub": out[:, :, ::4, ::4].clone(), "out_mean": out.mean(), "out_std": out.std(),
+                              "out_absmax": out.abs().max(), "attention": att, "ln_eps": 1e-6})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "two_level":
+    if len(sys.argv) > 1 and sys.argv[1] == "sam_encoder_1024":
+        make_sam_encoder_full_geometry()
+    elif len(sys.argv) > 1 and sys.argv[1] == "two_level":
         make_decoder_two_level()
     elif len(sys.argv) > 1 and sys.argv[1] == "match":
         make_match_cost()
@@ -262,3 +303,4 @@ if __name__ == "__main__":
         make_decoder_two_level()
         make_match_cost()
         make_sam_encoder()
+        make_sam_encoder_full_geometry()

@@ -1,6 +1,6 @@
 """fp32 CPU restatement of the SAM ViT image encoder, the pixel encoder of the released WalkGPT wiring (Path B).
-TEST INFRASTRUCTURE ONLY.  No CUDA path exists for this row yet: this file and tests/golden/sam_encoder_small.pt are the
-oracle-first groundwork.  Works on a flat state_dict with the reference parameter names; every function cites the reference lines
+TEST INFRASTRUCTURE ONLY.  Pinned by tests/golden/sam_encoder_small.pt and sam_encoder_1024.pt, both produced by the reference
+ImageEncoderViT (oracle/make_golden.py); the CUDA path is walkgpt_b200/csrc/sam_encoder.cu + sam_attention.cu.  Works on a flat state_dict with the reference parameter names; every function cites the reference lines
 (segment_anything/modeling/image_encoder.py) it follows.
 """
 from __future__ import annotations
@@ -23,6 +23,19 @@ def rel_pos_table(q_size: int, k_size: int, rel_pos: torch.Tensor) -> torch.Tens
     ks = torch.arange(k_size)[None, :] * max(q_size / k_size, 1.0)
     idx = (qs - ks) + (k_size - 1) * max(q_size / k_size, 1.0)
     return rel_pos[idx.long()]
+
+
+def attention_core_rel_pos(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, side: int) -> torch.Tensor:
+    """The attention proper (image_encoder.py:231-241 + add_decomposed_rel_pos :325-361) on given q / k / v [N, side*side, d]:
+    softmax(q d^-0.5 k^T + rel_h + rel_w) v with the position terms from the UNSCALED query."""
+    N, L, d = q.shape
+    s = (q * d ** -0.5) @ k.transpose(-1, -2)
+    Rh, Rw = rel_pos_table(side, side, rel_pos_h), rel_pos_table(side, side, rel_pos_w)
+    qg = q.reshape(N, side, side, d)
+    bias_h = torch.einsum("nhwc,hkc->nhwk", qg, Rh)
+    bias_w = torch.einsum("nhwc,wkc->nhwk", qg, Rw)
+    s = (s.view(N, side, side, side, side) + bias_h[..., :, None] + bias_w[..., None, :]).view(N, L, L)
+    return s.softmax(-1) @ v
 
 
 def attention_rel_pos(sd: SD, p: str, x: torch.Tensor, heads: int) -> torch.Tensor:

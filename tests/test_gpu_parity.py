@@ -146,6 +146,124 @@ def test_attention(B, T, H, masked):
     assert rel_err(ops.attention_d64(qkv, H, 0.125, kv), _attn_ref(qkv, H, 0.125, kv)) < 1e-2
 
 
+# ------------------------------------------------------------------------------------------------ SAM ViT encoder
+def _sam_kernel_qkv(q, k, v, heads):
+    """q / k / v [units, heads, L, 80] -> the kernel's qkv matrix [units * L, 3 * heads * 80] (bf16), columns
+    [Q main | K main | V main | Q rem | K rem | V rem]."""
+    def cols(t, lo, hi):
+        return t[..., lo:hi].permute(0, 2, 1, 3).reshape(t.shape[0] * t.shape[2], heads * (hi - lo))
+    return torch.cat([cols(q, 0, 64), cols(k, 0, 64), cols(v, 0, 64), cols(q, 64, 80), cols(k, 64, 80), cols(v, 64, 80)], dim=1).bfloat16().contiguous()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sam_attention_against_reference_golden_and_oracle(mode):
+    """wg_sam_attention (head_dim 80, decomposed relative position) for both block kinds: against the attention outputs the reference
+    produced for the fixture (windows 0..2 / the one global image), and against the oracle on every window of the padded map
+    (pad tokens act as keys; their rows are dropped)."""
+    from oracle import path_b
+
+    g = load("sam_encoder_1024")
+    cfg = g["cfg"]
+    tag, side = ("window", 14) if mode == 0 else ("global", 64)
+    a = g["attention"][tag]
+    heads, L = a["heads"], side * side
+    spec = specs.sam_image_encoder_spec(cfg["img_size"], cfg["patch"], cfg["embed"], cfg["depth"], cfg["heads"], 4.0, cfg["out_chans"],
+                                        cfg["window_size"], cfg["global_attn_indexes"])
+    sd = {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v) for k, v in specs.make_state_dict(spec, seed=g["seed"]).items()}
+    p = f"blocks.{a['block']}.attn."
+    rel = M.sam_rel_table(sd[p + "rel_pos_h"], sd[p + "rel_pos_w"], side).bfloat16().to(DEV)
+    qf, kf, vf = (rnd((a["n"] * heads, L, 80), s).to(torch.bfloat16).float().view(a["n"], heads, L, 80) for s in a["seeds"])
+    units = 25 if mode == 0 else 1
+    q, k, v = (torch.cat([t, rnd((units - a["n"], heads, L, 80), 900 + i).to(torch.bfloat16).float()], 0) if units > a["n"] else t
+               for i, t in enumerate((qf, kf, vf)))
+    out = ops.sam_attention(_sam_kernel_qkv(q, k, v, heads).to(DEV), rel, 1, mode, heads).float().cpu().view(64, 64, heads, 80)
+    ref = path_b.attention_core_rel_pos(q.reshape(units * heads, L, 80), k.reshape(units * heads, L, 80), v.reshape(units * heads, L, 80),
+                                        sd[p + "rel_pos_h"], sd[p + "rel_pos_w"], side).view(units, heads, side, side, 80)
+    if mode == 0:  # un-partition + crop the oracle's windows (image_encoder.py:273-289)
+        full = ref.view(5, 5, heads, 14, 14, 80).permute(0, 3, 1, 4, 2, 5).reshape(70, 70, heads, 80)[:64, :64]
+        gold = [out[:14, 14 * w:14 * w + 14].permute(2, 0, 1, 3).reshape(heads, L, 80) for w in range(a["n"])]
+        gold = torch.stack(gold).reshape(a["n"] * heads, L, 80)
+    else:
+        full = ref[0].permute(1, 2, 0, 3)
+        gold = out.permute(2, 0, 1, 3).reshape(heads, L, 80)
+    assert (gold[:, ::7] - a["out_sub"]).abs().max().item() < 1e-2 * a["out_absmax"].item()   # the reference's own outputs
+    assert rel_err(out, full) < 1e-2                                                            # every window / the whole map
+
+
+def _sam_encoder_and_oracle_weights(cfg, seed):
+    enc = M.ImageEncoderViT(embed_dim=cfg["embed"], depth=cfg["depth"], num_heads=cfg["heads"], global_attn_indexes=cfg["global_attn_indexes"], seed=seed)
+    _round_weights_to_bf16(enc)
+    return enc.to(DEV), sd_cpu(enc)
+
+
+def test_sam_image_encoder_against_reference_golden_and_oracle():
+    """ImageEncoderViT at SAM's geometry (1024-pixel input, windows padded 64 -> 70, one windowed + one global block, neck), 8 heads wide:
+    against the reference-generated fixture and, block by block, against the oracle."""
+    from oracle import path_b
+
+    g = load("sam_encoder_1024")
+    cfg = g["cfg"]
+    enc, sd = _sam_encoder_and_oracle_weights(cfg, g["seed"])
+    x = rnd((1, 3, 1024, 1024), g["pixels_seed"]).to(torch.bfloat16)
+    out = enc(x.to(DEV).float())
+    assert out.shape == (1, 256, 64, 64) and out.dtype == torch.float32
+    assert (out.cpu()[:, :, ::4, ::4] - g["out_sub"]).abs().max().item() < 2e-2 * g["out_absmax"].item()
+    ref = path_b.image_encoder_vit(sd, x.float(), cfg["heads"], 14, cfg["global_attn_indexes"])
+    print(f"SAM encoder (2 blocks, 8 heads): image embedding max-abs err {(out.cpu() - ref).abs().max().item():.4f} of abs-max {ref.abs().max().item():.2f}")
+    assert rel_err(out, ref) < 2e-2
+    # residual stream after each block (what Block.forward returns): errors stay at the bf16 level block by block
+    for n in (0, 1, 2):
+        _, xs = enc.run(x.to(DEV), n_run=n, want_emb=False, want_x=True)
+        ref_x = _sam_blocks_oracle(sd, x.float(), cfg, n)
+        assert rel_err(xs.view(1, 64, 64, -1), ref_x) < 1e-2, n
+    # bf16 pixels give the same result as fp32 pixels holding the same values
+    assert torch.equal(enc.run(x.to(DEV))[0], enc.run(x.to(DEV).float())[0])
+
+
+def _sam_blocks_oracle(sd, pixels, cfg, n):
+    """Residual stream after n blocks, from the oracle's pieces (image_encoder.py:107-113)."""
+    from oracle import path_b
+
+    w = sd["patch_embed.proj.weight"]
+    x = F.conv2d(pixels, w, sd["patch_embed.proj.bias"], stride=16).permute(0, 2, 3, 1) + sd["pos_embed"]
+    C_ = x.shape[-1]
+    for i in range(n):
+        b = f"blocks.{i}."
+        h = F.layer_norm(x, (C_,), sd[b + "norm1.weight"], sd[b + "norm1.bias"], 1e-6)
+        if i in cfg["global_attn_indexes"]:
+            h = path_b.attention_rel_pos(sd, b + "attn.", h, cfg["heads"])
+        else:
+            win, pad_hw = path_b.window_partition(h, 14)
+            h = path_b.window_unpartition(path_b.attention_rel_pos(sd, b + "attn.", win, cfg["heads"]), 14, pad_hw, (64, 64))
+        x = x + h
+        h = F.layer_norm(x, (C_,), sd[b + "norm2.weight"], sd[b + "norm2.bias"], 1e-6)
+        x = x + F.linear(F.gelu(F.linear(h, sd[b + "mlp.lin1.weight"], sd[b + "mlp.lin1.bias"])), sd[b + "mlp.lin2.weight"], sd[b + "mlp.lin2.bias"])
+    return x
+
+
+def test_path_b_from_pixels_vit_h_end_to_end_gates():
+    """Path B from the PIXELS with the full SAM ViT-H encoder (32 blocks, 16 heads x 80, global blocks 7 / 15 / 23 / 31): image embedding and
+    the north-star gates on the masks against the fp32 oracle (encoder + path_b_from_embeddings), one image, ragged-free 3 [SEG]."""
+    from oracle import path_b
+
+    enc = _round_weights_to_bf16(M.ImageEncoderViT(seed=5))
+    m = _round_weights_to_bf16(M.GroundingPathB(hidden_size=4096, seed=2, image_encoder=enc)).to(DEV)
+    x = scene_images(1, 77, image=1024)
+    seg = rnd((3, 4096), 78)
+    offs = [0, 3]
+    out = m.forward_from_pixels(x.to(DEV), seg.to(DEV), offs)
+    sd = sd_cpu(m.image_encoder)
+    emb_ref = path_b.image_encoder_vit(sd, x.float(), 16, 14, (7, 15, 23, 31))
+    emb = M.merge_split(out["img_emb_split"]).cpu().permute(0, 2, 1).reshape(1, 256, 64, 64)
+    e_emb = rel_err(emb, emb_ref)
+    w = {"msqp": sd_cpu(m.msqp), "ctp": sd_cpu(m.text_hidden_fcs[0]), "prompt": sd_cpu(m.prompt_encoder), "decoder": sd_cpu(m.mask_decoder)}
+    ref = path_b.path_b_from_embeddings(w, emb_ref, seg, offs)
+    err, iou = _gates(out, ref, tag=f"path B from pixels (ViT-H, 32 blocks; image embedding rel err {e_emb:.2e})")
+    assert e_emb < 3e-2
+    assert err <= LOGIT_TOL and iou.min().item() >= IOU_MIN
+    assert rel_err(out["vis_tokens"], ref["vis_tokens"]) < 3e-2
+
+
 # ------------------------------------------------------------------------------------------------ modules vs golden / oracle
 def test_clip_tower_against_reference_golden():
     g = load("clip_3layer")

@@ -234,3 +234,27 @@ def test_visual_token_resample_restatement():
     assert torch.equal(y, grid.reshape(2, 64, 256).transpose(1, 2).bfloat16())
     with pytest.raises(AssertionError, match="not square"):
         path_a.resample_visual_tokens(torch.zeros(1, 35, 8))
+
+
+def test_sam_image_encoder_oracle_at_full_geometry_against_reference_golden():
+    """SURVEY 8(f) row 1 at SAM's real geometry (1024-pixel input, 64 x 64 map, head_dim 80, 14 x 14 windows padded to 70, 27- and 127-row
+    relative-position tables): the oracle restatement against a fixture produced by the reference ImageEncoderViT, including the attention
+    of both block kinds in isolation (the fixture the CUDA attention kernel is tested against)."""
+    from oracle import path_b
+
+    g = load("sam_encoder_1024")
+    cfg = g["cfg"]
+    spec = specs.sam_image_encoder_spec(cfg["img_size"], cfg["patch"], cfg["embed"], cfg["depth"], cfg["heads"], 4.0, cfg["out_chans"],
+                                        cfg["window_size"], cfg["global_attn_indexes"])
+    sd = {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v) for k, v in specs.make_state_dict(spec, seed=g["seed"]).items()}
+    x = rnd((1, 3, cfg["img_size"], cfg["img_size"]), g["pixels_seed"]).to(torch.bfloat16).float()
+    out = path_b.image_encoder_vit(sd, x, cfg["heads"], cfg["window_size"], cfg["global_attn_indexes"], ln_eps=g["ln_eps"])
+    assert out.shape == (1, 256, 64, 64)
+    assert (out[:, :, ::4, ::4] - g["out_sub"]).abs().max().item() < 2e-4 * g["out_absmax"].item()
+    assert abs(out.std().item() - g["out_std"].item()) < 1e-4
+    for tag, side in (("window", 14), ("global", 64)):
+        a = g["attention"][tag]
+        q, k, v = (rnd((a["n"] * a["heads"], side * side, 80), s).to(torch.bfloat16).float() for s in a["seeds"])
+        p = f"blocks.{a['block']}.attn."
+        o = path_b.attention_core_rel_pos(q, k, v, sd[p + "rel_pos_h"], sd[p + "rel_pos_w"], side)
+        assert (o[:, ::7] - a["out_sub"]).abs().max().item() < 2e-5 * a["out_absmax"].item()

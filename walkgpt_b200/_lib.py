@@ -50,7 +50,7 @@ def _parse_header(path: str) -> None:
                 fields.append((am.group(2), STRUCTS[am.group(1)] * int(am.group(3))))
                 continue
             parts = decl.split(" ", 1)
-            ctype = _SCALARS[parts[0]]
+            ctype = STRUCTS[parts[0]] if parts[0] in STRUCTS else _SCALARS[parts[0]]  # nested struct by value, or a scalar
             for fname in parts[1].split(","):
                 fields.append((fname.strip(), ctype))
         STRUCTS[name] = type(name, (C.Structure,), {"_fields_": fields})
@@ -88,6 +88,8 @@ CtpWeights = STRUCTS["wg_ctp_weights"]
 ProjNeckWeights = STRUCTS["wg_proj_neck_weights"]
 TwoWayLayer = STRUCTS["wg_twoway_layer"]
 MaskDecoderWeights = STRUCTS["wg_mask_decoder_weights"]
+SamBlock = STRUCTS["wg_sam_block"]
+SamEncoderWeights = STRUCTS["wg_sam_encoder_weights"]
 
 _lib: Optional[C.CDLL] = None
 

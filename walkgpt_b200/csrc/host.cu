@@ -41,6 +41,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tensor_map(CUtensorMap* out, const void* gptr, int elem_bytes, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box) {
+    return make_tensor_map_sw(out, gptr, elem_bytes, rank, dims, strides_bytes, box, 128);
+}
+
+int make_tensor_map_sw(CUtensorMap* out, const void* gptr, int elem_bytes, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return WG_ERR_CUDA;
     cuuint64_t gdim[5];
@@ -54,8 +59,10 @@ int make_tensor_map(CUtensorMap* out, const void* gptr, int elem_bytes, int rank
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank=%d dims=%llu,%llu stride0=%llu box=%u,%u ptr=%p)", (int)r,
                   rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),

@@ -58,6 +58,10 @@ void set_error(const char* fmt, ...);  // thread-local message for wg_last_error
 int make_tensor_map(CUtensorMap* out, const void* gptr, int elem_bytes, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
 
+// same with an explicit swizzle span (bytes: 128, 64, 32, or 0 = none); the box's innermost extent must not exceed the span
+int make_tensor_map_sw(CUtensorMap* out, const void* gptr, int elem_bytes, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
 inline int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                              uint32_t box_rows, uint32_t box_cols) {
     uint64_t dims[2] = {cols, rows};

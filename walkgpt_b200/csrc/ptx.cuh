@@ -212,6 +212,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
           "r"(v[30]), "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 // store 4 consecutive 32-bit columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -288,6 +296,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO: 8 rows * 128 B
     d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
     d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+    return d;
+}
+// Generic form of the same descriptor: layout_type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (PTX ISA, tcgen05 shared-memory
+// descriptor).  Canonical layouts of densely packed TMA tiles: K-major rows are one swizzle span wide (32 / 64 / 128 bytes) and
+// SBO = 8 rows * span; MN-major tiles hold one k index per span-wide row, SBO = 8 * span again; LBO (distance between swizzle atoms
+// along the leading dimension) only matters when the operand is wider than one atom.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t layout_type, uint32_t sbo_bytes, uint32_t lbo_bytes = 16) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
 }
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32, M x N tile.

@@ -1028,6 +1028,113 @@ class DepthHead(_SpecModule):
         return out
 
 
+# --------------------------------------------------------------------------------------------------
+# SAM ViT image encoder (Path B's pixel encoder)
+# --------------------------------------------------------------------------------------------------
+def sam_qkv_row_order(heads: int, head_dim: int = 80, main: int = 64) -> torch.Tensor:
+    """Row permutation of the reference's ``attn.qkv`` weight ([3, heads, head_dim] rows) into the column order wg_sam_attention
+    reads: [Q main | K main | V main | Q rem | K rem | V rem], main = the first 64 channels of every head, rem = the other 16."""
+    hidden = heads * head_dim
+    idx = []
+    for lo, hi in ((0, main), (main, head_dim)):
+        for part in range(3):
+            for h in range(heads):
+                idx.append(torch.arange(part * hidden + h * head_dim + lo, part * hidden + h * head_dim + hi))
+    return torch.cat(idx)
+
+
+def sam_rel_table(rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, side: int) -> torch.Tensor:
+    """[rel_pos_h ; rel_pos_w] stacked for the attention kernel's prologue MMA: windows (side 14) -> [64, 80] with the two tables at rows 0
+    and 32, global (side 64) -> [256, 80] with them at rows 0 and 128.  The reference interpolates tables of another length
+    (get_rel_pos, image_encoder.py:292-322); the released checkpoints never need that and it is not built."""
+    n = 2 * side - 1
+    if rel_pos_h.shape[0] != n or rel_pos_w.shape[0] != n:
+        raise NotImplementedError(f"rel_pos tables must have 2 * {side} - 1 rows (got {rel_pos_h.shape[0]} / {rel_pos_w.shape[0]}): interpolated tables are not built")
+    half = 32 if side == 14 else 128
+    t = torch.zeros(2 * half, rel_pos_h.shape[1], dtype=torch.float32, device=rel_pos_h.device)
+    t[:n] = rel_pos_h.float()
+    t[half:half + n] = rel_pos_w.float()
+    return t
+
+
+class ImageEncoderViT(_SpecModule):
+    """Drop-in for SAM's ``ImageEncoderViT`` (segment_anything/modeling/image_encoder.py:17-126; ViT-H as built by build_sam.py:15-22 is the
+    default).  The CUDA path is built for the released geometry: 1024-pixel input, 16-pixel patches (64 x 64 map), head_dim 80, 14 x 14
+    windows, relative position tables of 2 * side - 1 rows; embed_dim / depth / heads / global_attn_indexes are free."""
+
+    def __init__(self, img_size: int = 1024, patch_size: int = 16, in_chans: int = 3, embed_dim: int = 1280, depth: int = 32, num_heads: int = 16,
+                 mlp_ratio: float = 4.0, out_chans: int = 256, qkv_bias: bool = True, norm_layer=None, act_layer=None, use_abs_pos: bool = True,
+                 use_rel_pos: bool = True, rel_pos_zero_init: bool = True, window_size: int = 14, global_attn_indexes: Sequence[int] = (7, 15, 23, 31),
+                 *, seed=0):
+        super().__init__()
+        if (img_size, patch_size, in_chans, window_size, out_chans) != (1024, 16, 3, 14, 256) or not (qkv_bias and use_abs_pos and use_rel_pos):
+            raise ValueError("ImageEncoderViT: the CUDA path is built for SAM's geometry (1024 / 16 / 3 channels / window 14 / 256 out, qkv bias, "
+                             "absolute + relative position)")
+        if embed_dim != num_heads * 80 or embed_dim % 128:
+            raise ValueError("ImageEncoderViT: embed_dim must be num_heads * 80 and a multiple of 128 (ViT-H: 1280 = 16 x 80)")
+        self.img_size, self.embed_dim, self.depth, self.num_heads = img_size, embed_dim, depth, num_heads
+        self.mlp_dim = int(embed_dim * mlp_ratio)
+        self.global_attn_indexes = tuple(global_attn_indexes)
+        self._build(specs.sam_image_encoder_spec(img_size, patch_size, embed_dim, depth, num_heads, mlp_ratio, out_chans, window_size, self.global_attn_indexes), seed)
+        self._ws = _Workspace()
+
+    def _pack(self):
+        sd, hold = self._sd(), _Holder()
+        D, heads = self.embed_dim, self.num_heads
+        order = sam_qkv_row_order(heads).to(sd["pos_embed"].device)
+        blocks = (_lib.SamBlock * self.depth)()
+        for i in range(self.depth):
+            p, bk = f"blocks.{i}.", blocks[i]
+            glob = i in self.global_attn_indexes
+            bk.ln1_g, bk.ln1_b = hold.f32(sd[p + "norm1.weight"]), hold.f32(sd[p + "norm1.bias"])
+            bk.w_qkv, bk.b_qkv = hold.bf16(sd[p + "attn.qkv.weight"][order]), hold.f32(sd[p + "attn.qkv.bias"][order])
+            bk.rel_table = hold.bf16(sam_rel_table(sd[p + "attn.rel_pos_h"], sd[p + "attn.rel_pos_w"], 64 if glob else 14))
+            bk.w_proj, bk.b_proj = hold.bf16(sd[p + "attn.proj.weight"]), hold.f32(sd[p + "attn.proj.bias"])
+            bk.ln2_g, bk.ln2_b = hold.f32(sd[p + "norm2.weight"]), hold.f32(sd[p + "norm2.bias"])
+            bk.w_fc1, bk.b_fc1 = hold.bf16(sd[p + "mlp.lin1.weight"]), hold.f32(sd[p + "mlp.lin1.bias"])
+            bk.w_fc2, bk.b_fc2 = hold.bf16(sd[p + "mlp.lin2.weight"]), hold.f32(sd[p + "mlp.lin2.bias"])
+            bk.is_global = int(glob)
+        w = _lib.SamEncoderWeights()
+        w.hidden, w.heads, w.mlp, w.image, w.patch, w.depth, w.out_chans = D, heads, self.mlp_dim, 1024, 16, self.depth, 256
+        w.patch_w = hold.bf16(sd["patch_embed.proj.weight"].reshape(D, -1))
+        w.pos_bias = hold.f32(sd["pos_embed"].reshape(-1, D).float() + sd["patch_embed.proj.bias"].float()[None])
+        w.blocks = C.cast(blocks, C.c_void_p)
+        w1 = sd["neck.0.weight"].reshape(256, D)
+        w3 = pack_conv3x3(sd["neck.2.weight"])
+        terms = split_terms_needed([w1, w3])
+        w.neck.mm_hidden, w.neck.hidden, w.neck.out_chans, w.neck.split_terms = D, D, 256, terms
+        w.neck.w_conv1 = hold(split_weight(w1, terms))
+        w.neck.ln1_g, w.neck.ln1_b = hold.f32(sd["neck.1.weight"]), hold.f32(sd["neck.1.bias"])
+        w.neck.w_conv3 = hold(split_weight(w3, terms))
+        w.neck.ln2_g, w.neck.ln2_b = hold.f32(sd["neck.3.weight"]), hold.f32(sd["neck.3.bias"])
+        self._packed = (w, blocks, hold)
+        return self._packed
+
+    def run(self, pixels: torch.Tensor, n_run: Optional[int] = None, want_emb: bool = True, want_x: bool = False):
+        """pixels [B,3,1024,1024] fp32/bf16 contiguous -> (image embedding TOKENS split-bf16 [B, 4096, 512] | None, residual stream after
+        ``n_run`` blocks fp32 [B, 4096, embed_dim] | None)."""
+        B = pixels.shape[0]
+        w, _, _ = self._packed or self._pack()
+        n_run = self.depth if n_run is None else n_run
+        dev = pixels.device
+        emb = torch.empty(B, 4096, 512, device=dev, dtype=torch.bfloat16) if want_emb else None
+        x = torch.empty(B, 4096, self.embed_dim, device=dev, dtype=torch.float32) if want_x else None
+        ws = self._ws.get(_lib.lib().wg_sam_encoder_workspace_bytes(C.byref(w), B), dev)
+        _lib.check(_lib.lib().wg_sam_encoder_forward(C.byref(w), pixels.data_ptr(), int(pixels.dtype == torch.bfloat16), B, n_run,
+                                                     None if emb is None else emb.data_ptr(), None if x is None else x.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), _stream()), "wg_sam_encoder_forward")
+        return emb, x
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B,3,1024,1024] -> image embeddings [B,256,64,64] in x's dtype (image_encoder.py:107-116)."""
+        _need_cuda(x, "ImageEncoderViT.forward")
+        assert tuple(x.shape[1:]) == (3, 1024, 1024), f"expected [B,3,1024,1024], got {tuple(x.shape)}"
+        with torch.cuda.device(x.device):
+            emb, _ = self.run(_as_kernel_input(x))
+            return tokens_to_nchw(emb, 64, 64, x.dtype, split=True)
+
+
 class _PromptIndex:
     """Per-image [SEG] offsets -> (offsets int32 [B+1] on the device, prompt -> image index int32 [P], P, max prompts per image).
 
@@ -1150,9 +1257,10 @@ class GroundingPathB(nn.Module):
     MaskDecoder -> Sam.postprocess_masks (1024^2 -> crop -> original) / threshold / score, batched over all images and prompts.
     The SAM ViT-H image encoder that produces the embeddings is not built yet: the caller passes its output."""
 
-    def __init__(self, hidden_size: int = 4096, grid: int = 64, image: int = 1024, seed: int = 0):
+    def __init__(self, hidden_size: int = 4096, grid: int = 64, image: int = 1024, seed: int = 0, image_encoder: Optional[nn.Module] = None):
         super().__init__()
         self.grid, self.image, self.hidden_size = grid, image, hidden_size
+        self.image_encoder = image_encoder  # ImageEncoderViT: forward_from_pixels() then starts at the pixels
         self.msqp = MultiScaleQFormerProjector(sam_dim=256, llama_dim=hidden_size, pad_to_square=True, target_square_side=6, seed=seed)
         self.text_hidden_fcs = nn.ModuleList([CalibratedTextProjector(hidden_size, 256, widen=2, use_residual=False, seed=seed)])
         self.prompt_encoder = PromptEncoder(256, (grid, grid), (image, image), 16, seed=seed)
@@ -1160,10 +1268,26 @@ class GroundingPathB(nn.Module):
         self._prompts = _PromptIndex()
 
     @torch.no_grad()
-    def forward(self, image_embeddings: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, input_size: Optional[Tuple[int, int]] = None,
-                original_size: Optional[Tuple[int, int]] = None, want_vis_tokens: bool = True):
+    def forward_from_pixels(self, images: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, input_size: Optional[Tuple[int, int]] = None,
+                            original_size: Optional[Tuple[int, int]] = None, want_vis_tokens: bool = True):
+        """images [B,3,1024,1024] (SAM-preprocessed pixels, model/walkgpt.py:241-260) -> SAM ViT encoder -> the rest of Path B.  The image
+        embedding stays in its split-bf16 token layout between the encoder's neck and the mask decoder (no NCHW round trip)."""
+        if self.image_encoder is None:
+            raise _lib.WalkGPTB200Error("GroundingPathB was built without an image_encoder")
+        _need_cuda(images, "GroundingPathB.forward_from_pixels")
+        with torch.cuda.device(images.device):
+            emb_split, _ = self.image_encoder.run(_as_kernel_input(images))
+        return self.forward(None, seg_hidden, seg_offsets, input_size, original_size, want_vis_tokens, _emb_split=emb_split)
+
+    @torch.no_grad()
+    def forward(self, image_embeddings: Optional[torch.Tensor], seg_hidden: torch.Tensor, seg_offsets, input_size: Optional[Tuple[int, int]] = None,
+                original_size: Optional[Tuple[int, int]] = None, want_vis_tokens: bool = True, _emb_split: Optional[torch.Tensor] = None):
         """image_embeddings [B, 256, g, g] (output of the SAM image encoder, model/walkgpt.py:713-743); seg_hidden [sum S, H];
         seg_offsets int sequence [B+1].  Returns a dict of device tensors (low_res [P, 1, 4g, 4g], logits at original_size, ...)."""
+        if _emb_split is not None:  # tokens straight from ImageEncoderViT.run: split-bf16 [B, hw, 512]
+            B, Cc, h, wd = _emb_split.shape[0], 256, self.grid, self.grid
+            dev = _emb_split.device
+            image_embeddings = merge_split(_emb_split).permute(0, 2, 1).reshape(B, Cc, h, wd)  # view for MSQP's bf16 tokens below
         _need_cuda(image_embeddings, "GroundingPathB.forward")
         dev = image_embeddings.device
         B, Cc, h, wd = image_embeddings.shape
@@ -1181,8 +1305,9 @@ class GroundingPathB(nn.Module):
             _, pe_tok = self.prompt_encoder.dense_pe_tokens()
             self.mask_decoder._packed or self.mask_decoder._pack()
             self.mask_decoder.bind_prompt_constants(pe_tok, self.prompt_encoder.no_mask_embed.weight, (h, wd))
-            low, iou, _ = self.mask_decoder.run(to_split(tokens), txt, prompt_img, False)
+            low, iou, _ = self.mask_decoder.run(_emb_split if _emb_split is not None else to_split(tokens), txt, prompt_img, False)
             out["low_res"], out["iou"] = low, iou
+            out["img_emb_split"] = _emb_split
             logits, mask, score = postprocess_masks_fused(low[:, 0], input_size, original_size, target_size=self.image)
             out["logits"], out["masks"], out["scores"] = logits, mask, score
         return out

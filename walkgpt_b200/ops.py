@@ -76,6 +76,21 @@ def layernorm(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[tor
     return out
 
 
+def sam_attention(qkv: torch.Tensor, rel_table: torch.Tensor, n_images: int, mode: int, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SAM ViT attention with decomposed relative position (image_encoder.py:222-247, 325-361), head_dim 80.  qkv bf16 [rows, 3*heads*80] in
+    the kernel's column order (modules.sam_qkv_row_order): mode 0 = window-major rows [n_images * 25 * 196], mode 1 = image-major
+    [n_images * 4096]; rel_table bf16 (modules.sam_rel_table).  Returns bf16 [n_images * 4096, heads * 80], image-major."""
+    _need_cuda(qkv, rel_table, out)
+    rows = n_images * (25 * 196 if mode == 0 else 4096)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and tuple(qkv.shape) == (rows, 3 * heads * 80)
+    assert rel_table.dtype == torch.bfloat16 and rel_table.is_contiguous() and tuple(rel_table.shape) == (64 if mode == 0 else 256, 80)
+    if out is None:
+        out = torch.empty(n_images * 4096, heads * 80, device=qkv.device, dtype=torch.bfloat16)
+    assert out.is_contiguous() and out.dtype == torch.bfloat16
+    _lib.check(_lib.lib().wg_sam_attention(qkv.data_ptr(), rel_table.data_ptr(), out.data_ptr(), n_images, mode, heads, _stream()), "wg_sam_attention")
+    return out
+
+
 def attention_d64(qkv: torch.Tensor, heads: int, scale: float, key_valid: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv bf16 [B,T,3*heads*64] -> bf16 [B,T,heads*64]; key_valid uint8 [B,T] (0 = padded key)."""
