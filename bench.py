@@ -191,6 +191,120 @@ class LlmPrefill:
         return rows, img_off
 
 
+# algorithmic FLOPs per image of Path B: patch embed 8.05 + 32 blocks x 161.06 (linear layers over 4096 tokens) + 28 x 4.92
+# (windowed attention, 25 windows of 196 tokens incl. the pad keys) + 4 x 85.90 (global attention) + neck 7.52 GF = 5650.8 GF for the
+# encoder; MSQP(sam_dim 256, 4096 tokens) 50.8 GF; SAM mask decoder 3.61 GF per [SEG]
+FLOPS_SAM_ENCODER = 5650.8e9
+FLOPS_PATH_B_REST = 50.8e9
+
+
+def run_path_b(args):
+    """Path B from the pixels on ONE GPU: not BASELINE.json's headline (that is --path a), reported for SURVEY 8(f) row 1."""
+    import ctypes
+
+    import torch
+    from walkgpt_b200 import _lib
+    from walkgpt_b200.modules import GroundingPathB, ImageEncoderViT
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    _lib.require_device(local)
+    lib = _lib.lib()
+    peaks = load_peaks()
+    B, S, H = args.batch or 16, 3, 4096
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    model = GroundingPathB(hidden_size=H, seed=0, image_encoder=ImageEncoderViT(seed=0)).to(dev)
+    gen = torch.Generator().manual_seed(1234)
+    NBUF = 3
+    host_px = [torch.randn(B, 3, 1024, 1024, generator=gen).to(torch.bfloat16).pin_memory() for _ in range(NBUF)]
+    host_seg = [torch.randn(B * S, H, generator=gen).to(torch.bfloat16).pin_memory() for _ in range(NBUF)]
+    dev_px, dev_seg = [t.to(dev) for t in host_px], [t.to(dev) for t in host_seg]
+    offs = list(range(0, B * S + 1, S))
+
+    def step(i):
+        return model.forward_from_pixels(dev_px[i % NBUF], dev_seg[i % NBUF], offs)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    lib.wg_launch_count(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.wg_launch_count(0)
+    clocks = sampler.stop()
+    value = B * K / (ms_total / 1e3)
+    # end to end with host buffers (single-buffered: H2D of the step's pixels + [SEG] states, D2H of its masks / scores / IoU)
+    h_masks = torch.empty(B * S, 1024, 1024, dtype=torch.uint8).pin_memory()
+    h_scores = torch.empty(B * S, dtype=torch.float32).pin_memory()
+    h_iou = torch.empty(B * S, 1, dtype=torch.float32).pin_memory()
+    d_px, d_seg = torch.empty_like(dev_px[0]), torch.empty_like(dev_seg[0])
+
+    def step_e2e(i):
+        d_px.copy_(host_px[i % NBUF], non_blocking=True)
+        d_seg.copy_(host_seg[i % NBUF], non_blocking=True)
+        out = model.forward_from_pixels(d_px, d_seg, offs)
+        h_masks.copy_(out["masks"], non_blocking=True)
+        h_scores.copy_(out["scores"], non_blocking=True)
+        h_iou.copy_(out["iou"], non_blocking=True)
+
+    step_e2e(0)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        step_e2e(i)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    lib.wg_profile_enable(1)
+    PK = min(K, 2)
+    for i in range(PK):
+        step(i)
+    torch.cuda.synchronize()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.wg_profile_collect(buf, len(buf))
+    lib.wg_profile_enable(0)
+    kern = {}
+    for ln in buf.value.decode().splitlines():
+        name, n, tms, fl, by = ln.split()
+        kern[name] = {"launches": int(n) // PK, "ms_per_step": float(tms) / PK, "flops_per_step": float(fl) / PK, "bytes_per_step": float(by) / PK}
+    tot_ms = sum(k["ms_per_step"] for k in kern.values()) or 1.0
+    gemm = [k for n, k in kern.items() if n.startswith("gemm_") or n.startswith("gemm2_")]
+    g_ms, g_fl, g_n = sum(k["ms_per_step"] for k in gemm), sum(k["flops_per_step"] for k in gemm), sum(k["launches"] for k in gemm)
+    peak = peaks["bf16_sustained"]
+    flops_img = FLOPS_SAM_ENCODER + FLOPS_PATH_B_REST + S * 3.61e9
+    step_tf = flops_img * B / (ms_total / K * 1e-3) / 1e12
+    extra = {}
+    for name in ("sam_attention_window", "sam_attention_global"):
+        if name in kern:
+            k = kern[name]
+            extra[name] = {"tflops": k["flops_per_step"] / (k["ms_per_step"] * 1e-3) / 1e12, "ms_per_step": k["ms_per_step"], "share_of_step": k["ms_per_step"] / tot_ms}
+    extra["kernel_ms_per_step"] = {n: round(k["ms_per_step"], 4) for n, k in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+    emit({"metric": "grounding_images_per_sec_1024px_path_b", "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+          "config": {"workload": f"Path B (released SAM-1024 wiring) from the pixels: SAM ViT-H encoder (32 blocks, 1280 wide, 14 x 14 windows + 4 global blocks) + "
+                                 f"MSQP(256) + CTP + SAM mask decoder + postprocess to 1024^2, batch {B}/GPU, {S} [SEG]/image, H={H}",
+                     "batch_per_gpu": B, "seg_per_image": S, "hidden": H, "weights": "random-init, bf16", "flops_per_image": flops_img,
+                     "l2": f"{NBUF} input batches rotated; per-step activations (GBs) exceed the 126 MB L2"},
+          "clocks": clocks, "e2e": {"value": B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": d_px.numel() * 2 + d_seg.numel() * 2,
+                                    "d2h_bytes_per_step": h_masks.numel() + 8 * h_scores.numel(), "ms_per_step": e2e_ms / K, "loop": "single-buffered"},
+          "gpu_launches": int(launches),
+          "roofline": {"kernel": "tcgen05 GEMM family (gemm2_bf16_kernel / gemm_bf16_kernel)", "bound": "tensor", "achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms else 0.0,
+                       "peak": peak, "unit": "TFLOP/s", "frac": (g_fl / (g_ms * 1e-3) / 1e12 / peak) if g_ms else 0.0, "traffic": None,
+                       "peak_source": peaks["source"] + ", sustained figure", "launches_per_step": g_n, "share_of_step": g_ms / tot_ms,
+                       "step_tflops": step_tf, "step_frac_of_peak": step_tf / peak},
+          "kernels": extra})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,11 +314,16 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config number (2 = the headline; 3; 5)")
     ap.add_argument("--seg", type=int, default=None, help="override the [SEG] tokens per image of the chosen config")
     ap.add_argument("--llm-depth", type=int, default=2, help="config 5: decoder layers of the stand-in LLM prefill")
+    ap.add_argument("--path", default="a", choices=["a", "b"], help="a = the benchmarked CLIP-448 composition (BASELINE.json); b = the released "
+                    "SAM-1024 wiring from the pixels (SAM ViT-H encoder + MSQP + CTP + SAM mask decoder), SURVEY 8(f) row 1")
+    ap.add_argument("--batch", type=int, default=None, help="--path b: images per step (default 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.path == "b":
+        return run_path_b(args)
 
     import torch
     import torch.distributed as dist
