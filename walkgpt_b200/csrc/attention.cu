@@ -155,7 +155,10 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, int gblk,
     float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
 #ifndef ATT_DBG_NOMAX  // debug builds (wrong results): knock one phase out to measure what it costs
 #pragma unroll
-    for (int i = 0; i < NCH * 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv(i)));
+    for (int i = 0; i < NCH * 32; i += 8) {  // 3-input maxima (FMNMX3): 4 chains, two new values per instruction
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(fmaxf(mx4[c], __uint_as_float(sv(i + 2 * c))), __uint_as_float(sv(i + 2 * c + 1)));
+    }
 #else
     mx4[0] = 0.f;
 #endif
@@ -539,19 +542,16 @@ struct AttnItem {
     int qt, head, img;
 };
 __device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int w) {
+    // Items of one (image, head) are CONSECUTIVE -- its full tiles, then its partial last tile -- so that the ~300 CTAs running at
+    // any moment work on a few dozen (image, head) pairs whose K / V (262 KB each at the CLIP length) stay in L2.  (Round 1 put every
+    // partial tile at the end of the schedule: each of them re-read its K / V from DRAM long after its siblings had finished --
+    // 1.5x the algorithmic DRAM traffic in the ncu capture.)
     AttnItem it;
-    const int full = p.batch * p.heads * p.n_full_tiles;
-    if (w < full) {
-        it.qt = w % p.n_full_tiles;
-        const int r = w / p.n_full_tiles;
-        it.head = r % p.heads;
-        it.img = r / p.heads;
-    } else {  // the partial last tile of every (image, head) comes after all full tiles: short items fill the end of the schedule
-        const int r = w - full;
-        it.qt = p.n_full_tiles;
-        it.head = r % p.heads;
-        it.img = r / p.heads;
-    }
+    const int per = p.n_full_tiles + ((p.T % ATT_BQ) != 0 ? 1 : 0);
+    it.qt = w % per;
+    const int r = w / per;
+    it.head = r % p.heads;
+    it.img = r / p.heads;
     return it;
 }
 

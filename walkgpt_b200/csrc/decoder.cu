@@ -242,9 +242,129 @@ __device__ void tok_t2i_attention(const float* Qt, const float* __restrict__ kv,
     }
 }
 
+// token -> image attention as its own kernel, split over KEYS: one CTA per (128-key chunk, prompt) handles all 8 heads, so every
+// global read is a whole 512-byte K or V row (the eight serial heads inside the one-CTA-per-prompt token kernel took 227 us per layer
+// at 192 prompts; a (head, prompt) grid read 64-byte slices at a 1.5 KB stride and reached 1.3 TB/s).  Each chunk emits flash-style
+// partials -- per (token, head) the chunk maximum m, the sum l of exp(s - m) and the un-normalised o[16] -- which the token kernel's
+// next part combines in a fixed chunk order (deterministic).  Qt [P][NT][128]; K / V = columns [k_off, +128) / [v_off, +128) of the
+// fp32 image-side projections kv [P*hw][ldkv].
+constexpr int T2I_THREADS = 256;
+constexpr int T2I_CHUNK = 128;                 // keys per CTA
+constexpr int T2I_ROWS = NT * 8;               // (token, head) score rows
+constexpr int T2I_LD = T2I_CHUNK + 1;
+__global__ void __launch_bounds__(T2I_THREADS) t2i_partial_kernel(const float* __restrict__ Qt, const float* __restrict__ kvall, int ldkv, int k_off,
+                                                                   int v_off, int hw, float* __restrict__ Pm, float* __restrict__ Pl,
+                                                                   float* __restrict__ Po) {
+    __shared__ float qs[NT * CI];
+    __shared__ float sc[T2I_ROWS * T2I_LD];
+    __shared__ float oh[NT * CI];
+    const int chunk = blockIdx.x, nchunk = gridDim.x, p = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k0 = chunk * T2I_CHUNK;
+    const float* kv = kvall + ((size_t)p * hw + k0) * ldkv;
+    for (int i = tid; i < NT * CI; i += T2I_THREADS) qs[i] = Qt[(size_t)p * NT * CI + i];
+    __syncthreads();
+    {   // scores: thread = (key, group of 4 heads): 256 contiguous bytes of the key's K row
+        const int key = tid & (T2I_CHUNK - 1), hg = tid >> 7;
+        const bool valid = k0 + key < hw;
+        float kf[64];
+        if (valid) {
+            const float4* kr = reinterpret_cast<const float4*>(kv + (size_t)key * ldkv + k_off + hg * 64);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float4 u = __ldg(kr + c);
+                kf[c * 4] = u.x; kf[c * 4 + 1] = u.y; kf[c * 4 + 2] = u.z; kf[c * 4 + 3] = u.w;
+            }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+            const int h = hg * 4 + hh;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float d = 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) d = fmaf(qs[t * CI + h * 16 + e], kf[hh * 16 + e], d);
+                sc[(t * 8 + h) * T2I_LD + key] = valid ? d * 0.25f : -INFINITY;  // 1/sqrt(16)
+            }
+        }
+    }
+    __syncthreads();
+    for (int row = warp; row < T2I_ROWS; row += T2I_THREADS / 32) {  // chunk-local softmax numerators
+        float* r = sc + row * T2I_LD;
+        float v[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = r[lane + 32 * i];
+            mx = fmaxf(mx, v[i]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float e = __expf(v[i] - mx);  // -inf (keys past hw) -> 0; a chunk always holds at least one real key
+            r[lane + 32 * i] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            Pm[((size_t)p * nchunk + chunk) * T2I_ROWS + row] = mx;
+            Pl[((size_t)p * nchunk + chunk) * T2I_ROWS + row] = sum;
+        }
+    }
+    __syncthreads();
+    {   // o[t][c] = sum_key p[t][head(c)][key] * V[key][c]: thread = (V column, half of the chunk's keys); V rows read whole
+        const int c = tid & (CI - 1), half = tid >> 7, h = c >> 4;
+        float o[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) o[t] = 0.f;
+        const int kend = min(T2I_CHUNK, hw - k0);
+        const float* vp = kv + v_off + c;
+#pragma unroll 4
+        for (int key = half * 64; key < half * 64 + 64; ++key) {
+            if (key < kend) {
+                const float v = __ldg(vp + (size_t)key * ldkv);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) o[t] = fmaf(sc[(t * 8 + h) * T2I_LD + key], v, o[t]);
+            }
+        }
+        if (half == 1) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) oh[t * CI + c] = o[t];
+        }
+        __syncthreads();
+        if (half == 0) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) Po[(((size_t)p * nchunk + chunk) * NT + t) * CI + c] = o[t] + oh[t * CI + c];
+        }
+    }
+}
+
+// combine the chunk partials of t2i_partial_kernel for prompt p into A [NT][128] (shared memory), fixed chunk order
+__device__ void tok_t2i_combine(const float* __restrict__ Pm, const float* __restrict__ Pl, const float* __restrict__ Po, int p, int nchunk, float* A) {
+    for (int i = threadIdx.x; i < NT * CI; i += TK_THREADS) {
+        const int t = i / CI, c = i - t * CI, row = t * 8 + (c >> 4);
+        const float* pm = Pm + (size_t)p * nchunk * T2I_ROWS + row;
+        const float* pl = Pl + (size_t)p * nchunk * T2I_ROWS + row;
+        float M = -INFINITY;
+        for (int ch = 0; ch < nchunk; ++ch) M = fmaxf(M, pm[ch * T2I_ROWS]);
+        float num = 0.f, den = 0.f;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const float w = __expf(pm[ch * T2I_ROWS] - M);
+            num = fmaf(Po[(((size_t)p * nchunk + ch) * NT + t) * CI + c], w, num);
+            den = fmaf(pl[ch * T2I_ROWS], w, den);
+        }
+        A[i] = num / den;
+    }
+    __syncthreads();
+}
+
 struct TokArgs {
     int phase, hw, n_mask_tokens;
-    int part;                            // phases 0/1: 0 = whole layer, 1 = up to norm2 (then the MLP runs as GEMMs), 2 = from norm3 on
+    int part;                            // phases 0/1: 0 = whole layer, 1 = up to norm2 (then the MLP runs as GEMMs), 2 = from norm3 on;
+                                         // 3 = up to the token->image query projection (Qt; the attention then runs as its own kernel over
+                                         // (head, prompt)), 4 = from the attention output At on (out-proj, norm2, hand-over to the MLP GEMMs);
+                                         // final phase: 3 = query projection only, 4 = from At on
     int part_floats;                     // split-K buffer of tok_linear: TK_THREADS * NT * 2 or * 4 floats
     wg_twoway_layer L;                   // weights of this layer (phases 0/1)
     // final-phase weights
@@ -260,6 +380,8 @@ struct TokArgs {
     __nv_bfloat16* Xs;         // part 1: the queries after norm2 once more as split-bf16 [P*NT][512] (A operand of the MLP GEMMs)
     float* Tpe;                // [P][NT][256] token positional term (= initial tokens)
     float* KT; float* VT;      // [P][NT][128] token-side K/V for image->token attention
+    float* Qt;                 // [P][NT][128] token->image queries (part 3)
+    const float *Pm, *Pl, *Po; int nchunk;  // chunk partials of t2i_partial_kernel (part 4 combines them)
     float* hyper;              // [P][n_mask][32]
     float* iou;                // [P][n_mask]
 };
@@ -280,7 +402,7 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
     const float* kv = a.kv + (size_t)p * a.hw * a.ldkv;
     const float* W;
 
-    if (a.phase == 0 && a.part != 2) {
+    if (a.phase == 0 && a.part != 2 && a.part != 4) {
         for (int i = tid; i < NT * C; i += TK_THREADS) {
             const int t = i / C, c = i % C;
             float v = (t < NT - 1) ? a.out_tokens[t * C + c] : a.txt[(size_t)p * C + c] + (a.sparse_add ? a.sparse_add[c] : 0.f);
@@ -299,6 +421,7 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
     if (a.phase < 2) {
         const wg_twoway_layer& L = a.L;
         if (a.part != 2) {
+        if (a.part != 4) {
         // ---- (1) self attention on the tokens
         if (a.phase == 0) {
             for (int i = tid; i < NT * C; i += TK_THREADS) b3[i] = q[i];
@@ -319,10 +442,18 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
         // ---- (2) tokens attend to the image
         tok_add(b3, q, qpe, NT * C);
         tok_linear(b3, C, C, (const float*)L.t2i_wq_t, L.t2i_bq, b0, CI, CI, false, false, part);
+        if (a.part == 3) {  // hand the queries over: the attention runs as t2i_attention_kernel over (head, prompt)
+            for (int i = tid; i < NT * CI; i += TK_THREADS) a.Qt[(size_t)p * NT * CI + i] = b0[i];
+            for (int i = tid; i < NT * C; i += TK_THREADS) a.Tq[(size_t)p * NT * C + i] = q[i];
+            return;
+        }
         tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part.buf);
+        } else {  // part 4: resume with the attention output (combined from the key-chunk partials)
+            tok_t2i_combine(a.Pm, a.Pl, a.Po, p, a.nchunk, b1);
+        }
         tok_linear(b1, CI, CI, (const float*)L.t2i_wo_t, L.t2i_bo, q, C, C, true, false, part);
         tok_layernorm(q, L.n2_g, L.n2_b, 1e-5f);
-        if (a.part == 1) {
+        if (a.part == 1 || a.part == 4) {
             // the MLP runs as two GEMMs over all prompts' token rows: hand the queries over in fp32 (residual) and split-bf16 (operand)
             for (int i = tid; i < NT * C; i += TK_THREADS) {
                 const float v = q[i];
@@ -350,9 +481,17 @@ __global__ void __launch_bounds__(TK_THREADS) decoder_token_kernel(const TokArgs
         for (int i = tid; i < NT * C; i += TK_THREADS) a.Tq[(size_t)p * NT * C + i] = q[i];
     } else {
         // ---- final token->image attention, LayerNorm, hypernetworks, IoU head
-        tok_add(b3, q, qpe, NT * C);
-        tok_linear(b3, C, C, (const float*)a.fin_wq_t, a.fin_bq, b0, CI, CI, false, false, part);
-        tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part.buf);
+        if (a.part != 4) {
+            tok_add(b3, q, qpe, NT * C);
+            tok_linear(b3, C, C, (const float*)a.fin_wq_t, a.fin_bq, b0, CI, CI, false, false, part);
+            if (a.part == 3) {
+                for (int i = tid; i < NT * CI; i += TK_THREADS) a.Qt[(size_t)p * NT * CI + i] = b0[i];
+                return;
+            }
+            tok_t2i_attention(b0, kv, a.ldkv, 0, CI, a.hw, b1, sc, part.buf);
+        } else {
+            tok_t2i_combine(a.Pm, a.Pl, a.Po, p, a.nchunk, b1);
+        }
         tok_linear(b1, CI, CI, (const float*)a.fin_wo_t, a.fin_bo, q, C, C, true, false, part);
         tok_layernorm(q, a.nf_g, a.nf_b, 1e-5f);
         for (int i = tid; i < NT * C; i += TK_THREADS) a.Tq[(size_t)p * NT * C + i] = q[i];
@@ -661,7 +800,7 @@ __global__ void __launch_bounds__(256) upscale_mask2_kernel(const float* __restr
 
 struct DecBuffers {
     __nv_bfloat16 *keysA, *keysB, *a2;   // split-bf16: [rows, 512], [rows, 512], [rows, 256]
-    float *kvq, *U, *Tq, *Tpe, *KT, *VT, *hyper, *iou_all;
+    float *kvq, *U, *Tq, *Tpe, *KT, *VT, *Qt, *Pm, *Pl, *Po, *hyper, *iou_all;
     __nv_bfloat16 *Xs, *Hs;  // token rows of all prompts as split-bf16: MLP input [P*NT, 512], hidden [P*NT, 4096]
 };
 
@@ -682,6 +821,11 @@ bool carve(Workspace& ws, int P, int hw, int up_stages, DecBuffers& d) {
     d.Tpe = (float*)take((size_t)P * NT * C * 4);
     d.KT = (float*)take((size_t)P * NT * CI * 4);
     d.VT = (float*)take((size_t)P * NT * CI * 4);
+    d.Qt = (float*)take((size_t)P * NT * CI * 4);
+    const size_t nchunk = ((size_t)hw + T2I_CHUNK - 1) / T2I_CHUNK;
+    d.Pm = (float*)take((size_t)P * nchunk * T2I_ROWS * 4);
+    d.Pl = (float*)take((size_t)P * nchunk * T2I_ROWS * 4);
+    d.Po = (float*)take((size_t)P * nchunk * NT * CI * 4);
     d.hyper = (float*)take((size_t)P * 4 * 32 * 4);
     d.iou_all = (float*)take((size_t)P * 4 * 4);
     d.Xs = (__nv_bfloat16*)take((size_t)P * NT * 2 * C * 2);
@@ -792,6 +936,11 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     WG_SMEM_OPT_IN(decoder_token_kernel, 227 * 1024);
     WG_REQUIRE(tk_smem <= 227 * 1024, "wg_mask_decoder_forward: token kernel shared memory %zu too large", tk_smem);
 
+    // token->image attention as its own (head, prompt) kernel whenever P fits a grid dimension (WG_DEC_T2I_SPLIT=0: inside the token kernel)
+    static const bool t2i_split_enabled = [] { const char* e = getenv("WG_DEC_T2I_SPLIT"); return e == nullptr || atoi(e) != 0; }();
+    const int t2i_chunks = (hw + T2I_CHUNK - 1) / T2I_CHUNK;
+    const bool split_t2i = t2i_split_enabled && P <= 65535;
+
     TokArgs ta = {};
     ta.hw = hw;
     ta.part_floats = tk_part;
@@ -803,7 +952,7 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     ta.iou_w0_t = w->iou_w0_t; ta.iou_w1_t = w->iou_w1_t; ta.iou_w2_t = w->iou_w2_t;
     ta.iou_b0 = w->iou_b0; ta.iou_b1 = w->iou_b1; ta.iou_b2 = w->iou_b2;
     ta.out_tokens = w->out_tokens; ta.sparse_add = w->sparse_add; ta.txt = txt_emb;
-    ta.Tq = d.Tq; ta.Tpe = d.Tpe; ta.KT = d.KT; ta.VT = d.VT; ta.hyper = d.hyper; ta.iou = d.iou_all;
+    ta.Tq = d.Tq; ta.Tpe = d.Tpe; ta.KT = d.KT; ta.VT = d.VT; ta.Qt = d.Qt; ta.Pm = d.Pm; ta.Pl = d.Pl; ta.Po = d.Po; ta.nchunk = t2i_chunks; ta.hyper = d.hyper; ta.iou = d.iou_all;
 
     // bring-up aid, compiled out of release builds (-DWG_DEBUG): WG_DEBUG_DECODER_STOP=<n> stops after the n-th launch group so
     // intermediates can be inspected; the call then reports WG_ERR_INVALID because the outputs were not produced
@@ -838,8 +987,23 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
         if (L.mlp_w1_split != nullptr && L.mlp_w2_split != nullptr) {
             // token MLP as two GEMMs over the P * NT token rows (hidden = relu(x W1^T + b1) in split-bf16; queries += hidden W2^T + b2
             // in place in fp32), between the two halves of the token kernel
-            ta.part = 1;
-            {
+            if (split_t2i) {
+                ta.part = 3;
+                {
+                    Prof prof("dec_token", s, (double)P * 2.0 * 2.3e6, (double)P * 1.0e6);
+                    decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+                }
+                {
+                    Prof prof("dec_t2i_attention", s, (double)P * 2.0 * 2.0 * NT * CI * hw, (double)P * hw * 1024.0);
+                    t2i_partial_kernel<<<dim3(t2i_chunks, P), T2I_THREADS, 0, s>>>(d.Qt, d.kvq, 384, 0, CI, hw, d.Pm, d.Pl, d.Po);
+                }
+                ta.part = 4;
+                {
+                    Prof prof("dec_token", s, (double)P * 2.0 * 0.3e6, (double)P * 0.2e6);
+                    decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+                }
+            } else {
+                ta.part = 1;
                 Prof prof("dec_token", s, (double)P * 2.0 * 3.0e6, (double)P * (hw * 512.0 + 1.0e6));
                 decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
             }
@@ -892,7 +1056,24 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
         WG_TRY(wg_gemm(&a, s));
     }
     ta.phase = 2; ta.kv = d.kvq; ta.ldkv = 256;
-    {
+    if (split_t2i) {
+        ta.part = 3;
+        {
+            Prof prof("dec_token", s, (double)P * 2.0 * 0.2e6, (double)P * 0.2e6);
+            decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+        }
+        {
+            Prof prof("dec_t2i_attention", s, (double)P * 2.0 * 2.0 * NT * CI * hw, (double)P * hw * 1024.0);
+            t2i_partial_kernel<<<dim3(t2i_chunks, P), T2I_THREADS, 0, s>>>(d.Qt, d.kvq, 256, 0, CI, hw, d.Pm, d.Pl, d.Po);
+        }
+        ta.part = 4;
+        {
+            Prof prof("dec_token", s, (double)P * 2.0 * 2.8e6, (double)P * 1.5e6);
+            decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
+        }
+        ta.part = 0;
+    } else {
+        ta.part = 0;
         Prof prof("dec_token", s, (double)P * 2.0 * 3.0e6, (double)P * (hw * 512.0 + 1.5e6));
         decoder_token_kernel<<<P, TK_THREADS, tk_smem, s>>>(ta);
     }

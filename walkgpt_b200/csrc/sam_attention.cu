@@ -489,6 +489,288 @@ sam_attention_kernel(const __grid_constant__ CUtensorMap tmMain, const __grid_co
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Windowed blocks, second kernel: a window has only 196 keys, so the whole score row fits tensor memory and nothing needs to be
+// "flash": S [128 x 208] = Q K^T in ONE MMA pass (N = 208, 4 + 1 k-steps), a plain two-pass softmax over the row (pass 1: maximum,
+// pass 2: exponentials; both re-read S from tensor memory in 32-column chunks, so a thread never holds more than a chunk), P written
+// IN PLACE over the S columns it came from (P chunk c = columns [16c, 16c+16) only covers S columns that are already consumed), then
+// O = P V (13 k-steps, N = 64 + 16) into columns [112, 192) of the same region, dead by then.  208 columns in all: two CTAs per SM.
+// No ring, no online rescale, no per-block hand-offs: Q, K, V and the position tables are each loaded once, K / V while the prologue
+// MMA (T = Q [R_h ; R_w]^T, see above) and the bias gather run.  First kernel (MODE 0 of sam_attention_kernel, four 64-key blocks):
+// 13 us per CTA, 139 TFLOP/s at the ViT-H bench shape.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int SW_KROWS = 208;                              // 196 keys rounded up to 16
+constexpr int SW_OFF_QM = 0;                               // [128 x 64] SW128                      16384
+constexpr int SW_OFF_KM = 16384;                           // [208 x 64] SW128                      26624
+constexpr int SW_OFF_VM = SW_OFF_KM + SW_KROWS * 128;      // 43008 (1024-aligned)                  26624
+constexpr int SW_OFF_TM = SW_OFF_VM + SW_KROWS * 128;      // 69632: tables main [64 x 64]           8192
+constexpr int SW_OFF_QR = SW_OFF_TM + 8192;                // 77824: [128 x 16] SW32                 4096
+constexpr int SW_OFF_KR = SW_OFF_QR + 4096;                // 81920: [208 x 16] SW32                 6656
+constexpr int SW_OFF_VR = SW_OFF_KR + SW_KROWS * 32;       // 88576 (256-aligned)                    6656
+constexpr int SW_OFF_TR = SW_OFF_VR + SW_KROWS * 32;       // 95232: tables rem [64 x 16]            2048
+constexpr int SW_OFF_BAR = SW_OFF_TR + 2048;               // 97280
+constexpr int SW_NUM_BARS = 9;
+constexpr int SW_SMEM_BYTES = SW_OFF_BAR + SW_NUM_BARS * 8 + 16;
+constexpr uint32_t SW_TM_O = 112, SW_TM_OR = 176;
+
+// t_i (log2 units) of the NCH columns of chunk CH held in a[]: scale * s + rel_h[k_h] + rel_w[k_w]; keys >= 196 give -inf
+template <int CH, int NCH>
+__device__ __forceinline__ void sw_chunk_logits(const uint32_t (&a)[NCH], float (&t)[NCH], float sc, const float (&bh)[SA_WS], const float (&bw)[SA_WS]) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int key = CH * 32 + i;  // compile-time after unrolling
+        t[i] = key < SA_WTOK ? fmaf(__uint_as_float(a[i]), sc, bh[key / SA_WS]) + bw[key % SA_WS] : -INFINITY;
+    }
+}
+
+__global__ void __launch_bounds__(192, 2)
+sam_window_attention_kernel(const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmKVm,
+                            const __grid_constant__ CUtensorMap tmKVr, const __grid_constant__ CUtensorMap tmTabMain,
+                            const __grid_constant__ CUtensorMap tmTabRem, const SamAttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SW_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* tab_full = bars + 1;
+    uint64_t* k_full = bars + 2;
+    uint64_t* v_full = bars + 3;
+    uint64_t* t_full = bars + 4;
+    uint64_t* t_cons = bars + 5;
+    uint64_t* s_full = bars + 6;
+    uint64_t* p_ready = bars + 7;
+    uint64_t* o_full = bars + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + SW_NUM_BARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, unit = blockIdx.z;
+    const int heads = p.heads;
+    const int row0 = unit * SA_WTOK;
+    const int cQm = head * 64, cKm = heads * 64 + head * 64, cVm = 2 * heads * 64 + head * 64;
+    const int cQr = 3 * heads * 64 + head * 16, cKr = cQr + heads * 16, cVr = cKr + heads * 16;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQm);
+        tma_prefetch_desc(&tmKVm);
+        mbar_init(q_full, 1);
+        mbar_init(tab_full, 1);
+        mbar_init(k_full, 1);
+        mbar_init(v_full, 1);
+        mbar_init(t_full, 1);
+        mbar_init(t_cons, 128);
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<SA_TMEM_COLS>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer: everything is loaded exactly once
+            mbar_arrive_expect_tx(q_full, 16384 + 4096);
+            tma_load_2d(smem + SW_OFF_QM, &tmQm, q_full, cQm, row0 + qt * SA_BQ);
+            tma_load_2d(smem + SW_OFF_QR, &tmQr, q_full, cQr, row0 + qt * SA_BQ);
+            mbar_arrive_expect_tx(tab_full, 8192 + 2048);
+            tma_load_2d(smem + SW_OFF_TM, &tmTabMain, tab_full, 0, 0);
+            tma_load_2d(smem + SW_OFF_TR, &tmTabRem, tab_full, 64, 0);
+            mbar_arrive_expect_tx(k_full, SW_KROWS * 160);
+            tma_load_2d(smem + SW_OFF_KM, &tmKVm, k_full, cKm, row0);
+            tma_load_2d(smem + SW_OFF_KR, &tmKVr, k_full, cKr, row0);
+            mbar_arrive_expect_tx(v_full, SW_KROWS * 160);
+            tma_load_2d(smem + SW_OFF_VM, &tmKVm, v_full, cVm, row0);
+            tma_load_2d(smem + SW_OFF_VR, &tmKVr, v_full, cVr, row0);
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        constexpr uint32_t IDESC_T = umma_idesc_bf16(128, 64, false, false);
+        constexpr uint32_t IDESC_S = umma_idesc_bf16(128, SW_KROWS, false, false);
+        constexpr uint32_t IDESC_OM = umma_idesc_bf16(128, 64, false, true);
+        constexpr uint32_t IDESC_OR = umma_idesc_bf16(128, 16, false, true);
+        const uint64_t qm = umma_desc(smem_u32(smem + SW_OFF_QM), LT_SW128, 1024), qr = umma_desc(smem_u32(smem + SW_OFF_QR), LT_SW32, 256);
+        const uint64_t km = umma_desc(smem_u32(smem + SW_OFF_KM), LT_SW128, 1024), kr = umma_desc(smem_u32(smem + SW_OFF_KR), LT_SW32, 256);
+        const uint64_t vm = umma_desc(smem_u32(smem + SW_OFF_VM), LT_SW128, 1024), vr = umma_desc(smem_u32(smem + SW_OFF_VR), LT_SW32, 256);
+        const uint64_t tm = umma_desc(smem_u32(smem + SW_OFF_TM), LT_SW128, 1024), tr = umma_desc(smem_u32(smem + SW_OFF_TR), LT_SW32, 256);
+        mbar_wait(q_full, 0);
+        mbar_wait(tab_full, 0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, qm + k * 2, tm + k * 2, IDESC_T, k != 0);
+            umma_f16_ss(tmem_base, qr, tr, IDESC_T, 1);
+            umma_commit(t_full);
+        }
+        __syncwarp();
+        mbar_wait(t_cons, 0);
+        mbar_wait(k_full, 0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, qm + k * 2, km + k * 2, IDESC_S, k != 0);
+            umma_f16_ss(tmem_base, qr, kr, IDESC_S, 1);
+            umma_commit(s_full);
+        }
+        __syncwarp();
+        mbar_wait(p_ready, 0);
+        mbar_wait(v_full, 0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < SW_KROWS / 16; ++k) {
+                umma_f16_ts(tmem_base + SW_TM_O, tmem_base + k * 8, vm + k * (2048 >> 4), IDESC_OM, k != 0);
+                umma_f16_ts(tmem_base + SW_TM_OR, tmem_base + k * 8, vr + k * (512 >> 4), IDESC_OR, k != 0);
+            }
+            umma_commit(o_full);
+        }
+        __syncwarp();
+    } else {
+        // ---- softmax warps: one thread per query row
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t trow = tmem_base + lane_off;
+        const int tok = qt * SA_BQ + r;
+        const float sc = p.scale_log2;
+        float bw[SA_WS], bh[SA_WS];
+        mbar_wait(t_full, 0);
+        tc_fence_after();
+        {
+            float t[64];  // dynamically indexed below: lives in local memory (L1)
+            uint32_t a[32];
+            tmem_ld_32x32b_x32(trow, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(a[i]);
+            tmem_ld_32x32b_x32(trow + 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[32 + i] = __uint_as_float(a[i]);
+            const int qh = tok / SA_WS, qw = tok - qh * SA_WS;
+#pragma unroll
+            for (int k = 0; k < SA_WS; ++k) {
+                bh[k] = t[(qh + SA_WS - 1 - k) & 31] * SA_LOG2E;  // rows past the window (never stored) stay in range
+                bw[k] = t[32 + qw + SA_WS - 1 - k] * SA_LOG2E;
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(t_cons);
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        // pass 1: row maximum
+        float mx = -INFINITY;
+#define SW_PASS1(CH)                                       \
+    do {                                                   \
+        uint32_t a[32];                                    \
+        float t[32];                                       \
+        tmem_ld_32x32b_x32(trow + (CH) * 32, a);           \
+        tmem_ld_wait();                                    \
+        sw_chunk_logits<CH, 32>(a, t, sc, bh, bw);         \
+        float m4[4] = {t[0], t[1], t[2], t[3]};            \
+        _Pragma("unroll") for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], t[i]); \
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]))); \
+    } while (0)
+        SW_PASS1(0); SW_PASS1(1); SW_PASS1(2); SW_PASS1(3); SW_PASS1(4); SW_PASS1(5);
+#undef SW_PASS1
+        {
+            uint32_t a[16];
+            float t[16];
+            tmem_ld_32x32b_x16(trow + 192, a);
+            tmem_ld_wait();
+            sw_chunk_logits<6, 16>(a, t, sc, bh, bw);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, t[i]);
+        }
+        // pass 2: exponentials, row sum, P (bf16 pairs) written over the consumed S columns
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#define SW_PASS2(CH)                                                                  \
+    do {                                                                              \
+        uint32_t a[32];                                                               \
+        float t[32];                                                                  \
+        tmem_ld_32x32b_x32(trow + (CH) * 32, a);                                      \
+        tmem_ld_wait();                                                               \
+        sw_chunk_logits<CH, 32>(a, t, sc, bh, bw);                                    \
+        uint32_t pk[16];                                                              \
+        _Pragma("unroll") for (int i = 0; i < 32; i += 2) {                           \
+            const float e0 = ex2f(t[i] - mx), e1 = ex2f(t[i + 1] - mx);               \
+            rs[(i >> 1) & 3] += e0 + e1;                                              \
+            pk[i >> 1] = pack_bf16x2(e0, e1);                                         \
+        }                                                                             \
+        tmem_st_32x32b_x16(trow + (CH) * 16, pk);                                     \
+    } while (0)
+        SW_PASS2(0); SW_PASS2(1); SW_PASS2(2); SW_PASS2(3); SW_PASS2(4); SW_PASS2(5);
+#undef SW_PASS2
+        {
+            uint32_t a[16];
+            float t[16];
+            tmem_ld_32x32b_x16(trow + 192, a);
+            tmem_ld_wait();
+            sw_chunk_logits<6, 16>(a, t, sc, bh, bw);
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const float e0 = ex2f(t[i] - mx), e1 = ex2f(t[i + 1] - mx);  // masked keys: 2^-inf = 0
+                rs[(i >> 1) & 3] += e0 + e1;
+                pk[i >> 1] = pack_bf16x2(e0, e1);
+            }
+            tmem_st_32x32b_x4(trow + 96, pk[0], pk[1], pk[2], pk[3]);
+            tmem_st_32x32b_x4(trow + 100, pk[4], pk[5], pk[6], pk[7]);
+        }
+        const float l_run = (rs[0] + rs[1]) + (rs[2] + rs[3]);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+        // ---- epilogue
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        long long orow = -1;
+        if (tok < SA_WTOK) {
+            const int img = unit / 25, win = unit - img * 25;
+            const int iy = (win / 5) * SA_WS + tok / SA_WS, ix = (win % 5) * SA_WS + tok % SA_WS;
+            if (iy < SA_G && ix < SA_G) orow = (long long)img * (SA_G * SA_G) + iy * SA_G + ix;
+        }
+        const bool live = orow >= 0;  // tcgen05.ld is warp-collective: every lane loads, only the stores are predicated
+        const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (live ? orow : 0) * ((long long)heads * SA_D) + head * SA_D);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(trow + SW_TM_O + cc * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 0]) * inv_l, __uint_as_float(ov[g4 * 8 + 1]) * inv_l);
+                u.y = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 2]) * inv_l, __uint_as_float(ov[g4 * 8 + 3]) * inv_l);
+                u.z = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 4]) * inv_l, __uint_as_float(ov[g4 * 8 + 5]) * inv_l);
+                u.w = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 6]) * inv_l, __uint_as_float(ov[g4 * 8 + 7]) * inv_l);
+                if (live) dst[cc * 4 + g4] = u;
+            }
+        }
+        uint32_t orr[16];
+        tmem_ld_32x32b_x16(trow + SW_TM_OR, orr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g4 = 0; g4 < 2; ++g4) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 0]) * inv_l, __uint_as_float(orr[g4 * 8 + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 2]) * inv_l, __uint_as_float(orr[g4 * 8 + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 4]) * inv_l, __uint_as_float(orr[g4 * 8 + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 6]) * inv_l, __uint_as_float(orr[g4 * 8 + 7]) * inv_l);
+            if (live) dst[8 + g4] = u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<SA_TMEM_COLS>(tmem_base);
+    }
+}
+
 }  // namespace
 }  // namespace wg
 
@@ -533,7 +815,20 @@ extern "C" int wg_sam_attention(const void* qkv, const void* rel_table, void* ou
     const double units = (double)n_images * (mode == 0 ? 25 : 1);
     Prof prof(mode == 0 ? "sam_attention_window" : "sam_attention_global", stream, 4.0 * units * heads * keys * keys * SA_D,
               2.0 * 4.0 * units * keys * heads * SA_D);
-    if (mode == 0) {
+    static const bool window_flash = [] { const char* e = getenv("WG_SAM_WINDOW_FLASH"); return e != nullptr && atoi(e) != 0; }();
+    if (mode == 0 && !window_flash) {
+        // one-pass window kernel: Q tile / whole-window K, V boxes
+        CUtensorMap tmQm, tmQr, tmKVm, tmKVr;
+        uint64_t dims[2] = {ncols, rows};
+        uint64_t strides[1] = {ncols * 2};
+        uint32_t bq[2] = {64, 128}, bqr[2] = {16, 128}, bk[2] = {64, SW_KROWS}, bkr[2] = {16, SW_KROWS};
+        WG_TRY(make_tensor_map_sw(&tmQm, qkv, 2, 2, dims, strides, bq, 128));
+        WG_TRY(make_tensor_map_sw(&tmQr, qkv, 2, 2, dims, strides, bqr, 32));
+        WG_TRY(make_tensor_map_sw(&tmKVm, qkv, 2, 2, dims, strides, bk, 128));
+        WG_TRY(make_tensor_map_sw(&tmKVr, qkv, 2, 2, dims, strides, bkr, 32));
+        WG_SMEM_OPT_IN(sam_window_attention_kernel, SW_SMEM_BYTES);
+        sam_window_attention_kernel<<<dim3(2, heads, n_images * 25), 192, SW_SMEM_BYTES, stream>>>(tmQm, tmQr, tmKVm, tmKVr, tmTabMain, tmTabRem, p);
+    } else if (mode == 0) {
         WG_SMEM_OPT_IN(sam_attention_kernel<0>, SA_SMEM_BYTES);
         sam_attention_kernel<0><<<dim3(2, heads, n_images * 25), 192, SA_SMEM_BYTES, stream>>>(tmMain, tmRem, tmTabMain, tmTabRem, p);
     } else {

@@ -143,6 +143,122 @@ __global__ void __launch_bounds__(BIL_THREADS) bilinear_kernel(const float* __re
     }
 }
 
+// Eight pixels per thread, for row widths that are a multiple of 8 (every size the path produces): round 1's four-pixel kernel was
+// ISSUE-bound, not write-bound (ncu, 192 masks of random logits: issue slots 80 % busy, ALU pipe 69 %, 2.6-3.0 TB/s) -- about 110
+// instructions per thread and output row for four pixels, half of them per-row bookkeeping every thread repeated (source-row index
+// arithmetic with float <-> int conversions, votes, pointer math).  Here the row table (source rows + weight) is computed once per
+// CTA into shared memory, a thread amortises the rest over eight pixels (two 16-byte logit stores, one 8-byte mask store), the
+// positive-pixel count comes from a population count of the mask bytes and the score sum from predicated adds.  Same arithmetic per
+// pixel as bilinear_kernel (bit-identical logits).
+constexpr int BIL8_THREADS = 64;
+constexpr int BIL8_MAX_ROWS = 64;
+template <bool SCORE>
+__global__ void __launch_bounds__(BIL8_THREADS) bilinear8_kernel(const float* __restrict__ src, int sh, int sw, float* __restrict__ dst, int dh, int dw,
+                                                                  float scale_y, float scale_x, uint8_t* __restrict__ mask, float* __restrict__ accum,
+                                                                  int rows_per_band) {
+    __shared__ int4 rowtab[BIL8_MAX_ROWS];  // {y0 * sw, y1 * sw, bits of ly, unused}
+    const int n = blockIdx.z;
+    const int ya = blockIdx.y * rows_per_band;
+    const int yb = min(dh, ya + rows_per_band);
+    if (threadIdx.x < yb - ya) {
+        int y0, y1;
+        float ly;
+        src_index(ya + threadIdx.x, scale_y, sh, y0, y1, ly);
+        rowtab[threadIdx.x] = make_int4(y0 * sw, y1 * sw, __float_as_int(ly), 0);
+    }
+    __syncthreads();
+    const int x0 = (blockIdx.x * BIL8_THREADS + threadIdx.x) * 8;
+    float ssum = 0.f;
+    int scnt = 0;
+    const unsigned row_lanes = __ballot_sync(0xffffffffu, x0 < dw);
+    if (x0 < dw) {
+        int xa[8], xb[8];
+        float lx[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) src_index(x0 + v, scale_x, sw, xa[v], xb[v], lx[v]);
+        const float* sbase = src + (size_t)n * sh * sw;
+        float h0[8], h1[8];
+        int cur0 = -1, cur1 = -1;
+        float* drow = dst + ((size_t)n * dh + ya) * dw + x0;
+        uint8_t* mrow = mask + ((size_t)n * dh + ya) * dw + x0;  // only dereferenced when mask != nullptr
+        for (int y = ya; y < yb; ++y) {
+            const int4 rt = rowtab[y - ya];
+            const float ly = __int_as_float(rt.z);
+            if (rt.x != cur0 || rt.y != cur1) {
+                if (rt.x == cur1) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) h0[v] = h1[v];
+                } else {
+                    const float* r0 = sbase + rt.x;
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) h0[v] = (1.f - lx[v]) * __ldg(r0 + xa[v]) + lx[v] * __ldg(r0 + xb[v]);
+                }
+                if (rt.y == rt.x) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) h1[v] = h0[v];
+                } else {
+                    const float* r1 = sbase + rt.y;
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) h1[v] = (1.f - lx[v]) * __ldg(r1 + xa[v]) + lx[v] * __ldg(r1 + xb[v]);
+                }
+                cur0 = rt.x;
+                cur1 = rt.y;
+            }
+            float o[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) o[v] = (1.f - ly) * h0[v] + ly * h1[v];
+            __stcs(reinterpret_cast<float4*>(drow), make_float4(o[0], o[1], o[2], o[3]));
+            __stcs(reinterpret_cast<float4*>(drow) + 1, make_float4(o[4], o[5], o[6], o[7]));
+            drow += dw;
+            if (SCORE) {
+                uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    m0 |= (o[v] > 0.f ? 1u : 0u) << (8 * v);
+                    m1 |= (o[4 + v] > 0.f ? 1u : 0u) << (8 * v);
+                }
+                if (mask) {
+                    __stcs(reinterpret_cast<uint2*>(mrow), make_uint2(m0, m1));
+                    mrow += dw;
+                }
+                if (accum != nullptr && __any_sync(row_lanes, (m0 | m1) != 0)) {
+                    scnt += __popc(m0) + __popc(m1);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        // sigmoid = 1 / (1 + 2^(-o log2 e)): MUFU.EX2 + MUFU.RCP; ex2.approx.ftz flushes 2^(< -126) to 0 -> 1 / 1
+                        float e, sg;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(o[v] * -1.4426950408889634f));
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + e));
+                        if (o[v] > 0.f) ssum += sg;
+                    }
+                }
+            }
+        }
+    }
+    if (SCORE && accum != nullptr) {
+        __shared__ float red[2][BIL8_THREADS / 32];
+        ssum = warp_sum(ssum);
+        const float cnt = warp_sum((float)scnt);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) {
+            red[0][warp] = ssum;
+            red[1][warp] = cnt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f;
+            for (int i = 0; i < BIL8_THREADS / 32; ++i) {
+                a += red[0][i];
+                b += red[1][i];
+            }
+            if (b > 0.f) {
+                atomicAdd(accum + 2 * n, a);
+                atomicAdd(accum + 2 * n + 1, b);
+            }
+        }
+    }
+}
+
 __global__ void finalize_score_kernel(const float* __restrict__ accum, float* __restrict__ score, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) score[i] = accum[2 * i] / (accum[2 * i + 1] + 1e-6f);
@@ -212,6 +328,21 @@ int launch_bilinear(const float* src, int n, int sh, int sw, float* dst, int dh,
               (double)n * ((double)sh * sw * 4.0 + (double)dh * dw * (SCORE && mask ? 5.0 : 4.0)));
     // bands of rows: ~32 CTAs per SM, i.e. several waves at the 7-12 CTAs an SM holds (with ~9 per SM the scoring variant ran 1.3
     // waves: a second, 30 % full round), at least 8 rows each so the per-thread column set-up is amortised
+    if (dw % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 7) == 0)) {
+        const int groups8 = dw / 8;
+        const int xb8 = (groups8 + BIL8_THREADS - 1) / BIL8_THREADS;
+        int bands8 = (32 * device_sm_count() + n * xb8 - 1) / (n * xb8);
+        if (bands8 < 1) bands8 = 1;
+        int rpb = (dh + bands8 - 1) / bands8;
+        if (rpb < 8) rpb = 8;
+        if (rpb > BIL8_MAX_ROWS) rpb = BIL8_MAX_ROWS;
+        bands8 = (dh + rpb - 1) / rpb;
+        if (bands8 <= 65535) {
+            bilinear8_kernel<SCORE><<<dim3(xb8, bands8, n), BIL8_THREADS, 0, s>>>(src, sh, sw, dst, dh, dw, sy, sx, mask, accum, rpb);
+            WG_CHECK_CUDA(cudaGetLastError());
+            return WG_OK;
+        }
+    }
     const int vec = (dw % 4 == 0) ? 4 : 1;
     const int groups = (dw + vec - 1) / vec;
     const int xblocks = (groups + BIL_THREADS - 1) / BIL_THREADS;
