@@ -251,13 +251,12 @@ __device__ void tok_t2i_attention(const float* Qt, const float* __restrict__ kv,
 constexpr int T2I_THREADS = 256;
 constexpr int T2I_CHUNK = 128;                 // keys per CTA
 constexpr int T2I_ROWS = NT * 8;               // (token, head) score rows
-constexpr int T2I_LD = T2I_CHUNK + 1;
+constexpr int T2I_LD = T2I_CHUNK + 4;          // padded row, still 16-byte aligned: the P V pass reads four keys per LDS.128
 __global__ void __launch_bounds__(T2I_THREADS) t2i_partial_kernel(const float* __restrict__ Qt, const float* __restrict__ kvall, int ldkv, int k_off,
                                                                    int v_off, int hw, float* __restrict__ Pm, float* __restrict__ Pl,
                                                                    float* __restrict__ Po) {
-    __shared__ float qs[NT * CI];
-    __shared__ float sc[T2I_ROWS * T2I_LD];
-    __shared__ float oh[NT * CI];
+    __shared__ __align__(16) float qs[NT * CI];
+    __shared__ __align__(16) float sc[T2I_ROWS * T2I_LD];
     const int chunk = blockIdx.x, nchunk = gridDim.x, p = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k0 = chunk * T2I_CHUNK;
@@ -283,7 +282,13 @@ __global__ void __launch_bounds__(T2I_THREADS) t2i_partial_kernel(const float* _
             for (int t = 0; t < NT; ++t) {
                 float d = 0.f;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) d = fmaf(qs[t * CI + h * 16 + e], kf[hh * 16 + e], d);
+                for (int e = 0; e < 16; e += 4) {  // the query slice as four broadcast LDS.128 (scalar reads made this loop LDS-bound)
+                    const float4 qv = *reinterpret_cast<const float4*>(&qs[t * CI + h * 16 + e]);
+                    d = fmaf(qv.x, kf[hh * 16 + e], d);
+                    d = fmaf(qv.y, kf[hh * 16 + e + 1], d);
+                    d = fmaf(qv.z, kf[hh * 16 + e + 2], d);
+                    d = fmaf(qv.w, kf[hh * 16 + e + 3], d);
+                }
                 sc[(t * 8 + h) * T2I_LD + key] = valid ? d * 0.25f : -INFINITY;  // 1/sqrt(16)
             }
         }
@@ -313,29 +318,38 @@ __global__ void __launch_bounds__(T2I_THREADS) t2i_partial_kernel(const float* _
         }
     }
     __syncthreads();
-    {   // o[t][c] = sum_key p[t][head(c)][key] * V[key][c]: thread = (V column, half of the chunk's keys); V rows read whole
-        const int c = tid & (CI - 1), half = tid >> 7, h = c >> 4;
-        float o[NT];
+    {   // o[t][c] = sum_key p[t][head(c)][key] * V[key][c].  A warp owns every 8th key and reads its whole 512-byte V row with one
+        // LDG.128 per lane (four columns each); four rows in flight per warp keep enough bytes outstanding (one float per lane did not)
+        const int c4 = lane * 4, h = lane >> 2;
+        float o[NT][4];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) o[t] = 0.f;
+        for (int t = 0; t < NT; ++t) o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.f;
         const int kend = min(T2I_CHUNK, hw - k0);
-        const float* vp = kv + v_off + c;
+        const float* vp = kv + v_off + c4;
 #pragma unroll 4
-        for (int key = half * 64; key < half * 64 + 64; ++key) {
+        for (int key = warp; key < T2I_CHUNK; key += T2I_THREADS / 32) {
             if (key < kend) {
-                const float v = __ldg(vp + (size_t)key * ldkv);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(vp + (size_t)key * ldkv));
 #pragma unroll
-                for (int t = 0; t < NT; ++t) o[t] = fmaf(sc[(t * 8 + h) * T2I_LD + key], v, o[t]);
+                for (int t = 0; t < NT; ++t) {
+                    const float pt = sc[(t * 8 + h) * T2I_LD + key];
+                    o[t][0] = fmaf(pt, v.x, o[t][0]);
+                    o[t][1] = fmaf(pt, v.y, o[t][1]);
+                    o[t][2] = fmaf(pt, v.z, o[t][2]);
+                    o[t][3] = fmaf(pt, v.w, o[t][3]);
+                }
             }
         }
-        if (half == 1) {
+        __syncthreads();  // every warp is done with the probabilities: their storage now takes the per-warp partial sums
+        float* part = sc;  // [warps][NT * CI]  (8 * 768 <= 48 * 132 floats)
 #pragma unroll
-            for (int t = 0; t < NT; ++t) oh[t * CI + c] = o[t];
-        }
+        for (int t = 0; t < NT; ++t) *reinterpret_cast<float4*>(&part[warp * (NT * CI) + t * CI + c4]) = make_float4(o[t][0], o[t][1], o[t][2], o[t][3]);
         __syncthreads();
-        if (half == 0) {
+        for (int i = tid; i < NT * CI; i += T2I_THREADS) {  // fixed-order sum over the warps
+            float v = 0.f;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) Po[(((size_t)p * nchunk + chunk) * NT + t) * CI + c] = o[t] + oh[t * CI + c];
+            for (int w8 = 0; w8 < T2I_THREADS / 32; ++w8) v += part[w8 * (NT * CI) + i];
+            Po[((size_t)p * nchunk + chunk) * NT * CI + i] = v;
         }
     }
 }
