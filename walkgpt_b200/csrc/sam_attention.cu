@@ -524,6 +524,142 @@ __device__ __forceinline__ void sw_chunk_logits(const uint32_t (&a)[NCH], float 
     }
 }
 
+// this row's relative-position bias registers from the prologue product T (columns [0,64) of the row's TMEM lane), log2 units
+__device__ __forceinline__ void sw_read_bias(uint32_t trow, int tok, float (&bh)[SA_WS], float (&bw)[SA_WS]) {
+    float t[64];  // dynamically indexed below: lives in local memory (L1)
+    uint32_t a[32];
+    tmem_ld_32x32b_x32(trow, a);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(a[i]);
+    tmem_ld_32x32b_x32(trow + 32, a);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[32 + i] = __uint_as_float(a[i]);
+    const int qh = tok / SA_WS, qw = tok - qh * SA_WS;
+#pragma unroll
+    for (int k = 0; k < SA_WS; ++k) {
+        bh[k] = t[(qh + SA_WS - 1 - k) & 31] * SA_LOG2E;  // rows past the window (never stored) stay in range
+        bw[k] = t[32 + qw + SA_WS - 1 - k] * SA_LOG2E;
+    }
+}
+
+// two-pass softmax of one score row held in tensor memory (208 columns at trow): P (bf16 pairs) replaces S in place; returns the row sum.
+// Pass 1 only takes the maximum of the RAW scores: softmax is shift-invariant, so the shift may be any upper bound of the logits, here
+// scale * max(s) + max(rel_h) + max(rel_w) (at most the spread of the position terms above the true maximum -- harmless in fp32 / bf16
+// floating point), which spares the bias arithmetic of a whole pass.  Both passes load chunk c + 1 from tensor memory while chunk c is
+// processed (tcgen05.wait::ld covers every outstanding load, so the prefetch is issued right after the wait for the current chunk).
+__device__ __forceinline__ float sw_softmax_row(uint32_t trow, float sc, float (&bh)[SA_WS], const float (&bw)[SA_WS]) {
+    uint32_t a[2][32];
+    float smax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    tmem_ld_32x32b_x32(trow, a[0]);
+    tmem_ld_wait();
+#define SW_PASS1(CH)                                                                                  \
+    do {                                                                                              \
+        if ((CH) < 5) tmem_ld_32x32b_x32(trow + ((CH) + 1) * 32, a[((CH) + 1) & 1]);                  \
+        else {                                                                                        \
+            uint32_t(&nx)[16] = *reinterpret_cast<uint32_t(*)[16]>(&a[((CH) + 1) & 1][0]);            \
+            tmem_ld_32x32b_x16(trow + 192, nx);                                                       \
+        }                                                                                             \
+        _Pragma("unroll") for (int i = 0; i < 32; ++i) smax[i & 3] = fmaxf(smax[i & 3], __uint_as_float(a[(CH) & 1][i])); \
+        tmem_ld_wait();                                                                               \
+    } while (0)
+    SW_PASS1(0); SW_PASS1(1); SW_PASS1(2); SW_PASS1(3); SW_PASS1(4); SW_PASS1(5);
+#undef SW_PASS1
+#pragma unroll
+    for (int i = 0; i < 4; ++i) smax[i & 3] = fmaxf(smax[i & 3], __uint_as_float(a[0][i]));  // chunk 6: keys 192..195 (the others are masked)
+    tmem_ld_32x32b_x32(trow, a[0]);  // pass 2 starts: chunk 0 again, in flight while the shift is formed
+    float bmax_h = bh[0], bmax_w = bw[0];
+#pragma unroll
+    for (int k = 1; k < SA_WS; ++k) {
+        bmax_h = fmaxf(bmax_h, bh[k]);
+        bmax_w = fmaxf(bmax_w, bw[k]);
+    }
+    const float mraw = fmaxf(fmaxf(smax[0], smax[1]), fmaxf(smax[2], smax[3]));
+    const float shift = fmaf(mraw, sc, bmax_h + bmax_w);  // sc > 0
+#pragma unroll
+    for (int k = 0; k < SA_WS; ++k) bh[k] -= shift;       // fold the shift into the row term
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    tmem_ld_wait();
+#define SW_PASS2(CH)                                                                                  \
+    do {                                                                                              \
+        if ((CH) < 5) tmem_ld_32x32b_x32(trow + ((CH) + 1) * 32, a[((CH) + 1) & 1]);                  \
+        else {                                                                                        \
+            uint32_t(&nx)[16] = *reinterpret_cast<uint32_t(*)[16]>(&a[((CH) + 1) & 1][0]);            \
+            tmem_ld_32x32b_x16(trow + 192, nx);                                                       \
+        }                                                                                             \
+        float t[32];                                                                                  \
+        sw_chunk_logits<CH, 32>(a[(CH) & 1], t, sc, bh, bw);                                          \
+        uint32_t pk[16];                                                                              \
+        _Pragma("unroll") for (int i = 0; i < 32; i += 2) {                                           \
+            const float e0 = ex2f(t[i]), e1 = ex2f(t[i + 1]);                                         \
+            rs[(i >> 1) & 3] += e0 + e1;                                                              \
+            pk[i >> 1] = pack_bf16x2(e0, e1);                                                         \
+        }                                                                                             \
+        tmem_ld_wait();                                                                               \
+        tmem_st_32x32b_x16(trow + (CH) * 16, pk);                                                     \
+    } while (0)
+    SW_PASS2(0); SW_PASS2(1); SW_PASS2(2); SW_PASS2(3); SW_PASS2(4); SW_PASS2(5);
+#undef SW_PASS2
+    {
+        uint32_t(&a6)[16] = *reinterpret_cast<uint32_t(*)[16]>(&a[0][0]);
+        float t[16];
+        sw_chunk_logits<6, 16>(a6, t, sc, bh, bw);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const float e0 = ex2f(t[i]), e1 = ex2f(t[i + 1]);  // masked keys: 2^-inf = 0
+            rs[(i >> 1) & 3] += e0 + e1;
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+        }
+        tmem_st_32x32b_x4(trow + 96, pk[0], pk[1], pk[2], pk[3]);
+        tmem_st_32x32b_x4(trow + 100, pk[4], pk[5], pk[6], pk[7]);
+    }
+    tmem_st_wait();
+    return (rs[0] + rs[1]) + (rs[2] + rs[3]);
+}
+
+// O / l of one row -> bf16 -> its 160 contiguous output bytes.  tcgen05.ld is warp-collective: every lane loads, only the stores are
+// predicated (a window's pad rows and the rows past it have no output row)
+__device__ __forceinline__ void sw_store_row(uint32_t trow, float l_run, bool live, uint4* dst) {
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(trow + SW_TM_O + cc * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 0]) * inv_l, __uint_as_float(ov[g4 * 8 + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 2]) * inv_l, __uint_as_float(ov[g4 * 8 + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 4]) * inv_l, __uint_as_float(ov[g4 * 8 + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 6]) * inv_l, __uint_as_float(ov[g4 * 8 + 7]) * inv_l);
+            if (live) dst[cc * 4 + g4] = u;
+        }
+    }
+    uint32_t orr[16];
+    tmem_ld_32x32b_x16(trow + SW_TM_OR, orr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g4 = 0; g4 < 2; ++g4) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 0]) * inv_l, __uint_as_float(orr[g4 * 8 + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 2]) * inv_l, __uint_as_float(orr[g4 * 8 + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 4]) * inv_l, __uint_as_float(orr[g4 * 8 + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 6]) * inv_l, __uint_as_float(orr[g4 * 8 + 7]) * inv_l);
+        if (live) dst[8 + g4] = u;
+    }
+}
+
+// image-major output row of token `tok` of window `unit` (-1: a pad token or a row past the window)
+__device__ __forceinline__ long long sw_out_row(int unit, int tok) {
+    if (tok >= SA_WTOK) return -1;
+    const int img = unit / 25, win = unit - img * 25;
+    const int iy = (win / 5) * SA_WS + tok / SA_WS, ix = (win % 5) * SA_WS + tok % SA_WS;
+    return (iy < SA_G && ix < SA_G) ? (long long)img * (SA_G * SA_G) + iy * SA_G + ix : -1;
+}
+
 __global__ void __launch_bounds__(192, 2)
 sam_window_attention_kernel(const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmKVm,
                             const __grid_constant__ CUtensorMap tmKVr, const __grid_constant__ CUtensorMap tmTabMain,
@@ -637,130 +773,18 @@ sam_window_attention_kernel(const __grid_constant__ CUtensorMap tmQm, const __gr
         float bw[SA_WS], bh[SA_WS];
         mbar_wait(t_full, 0);
         tc_fence_after();
-        {
-            float t[64];  // dynamically indexed below: lives in local memory (L1)
-            uint32_t a[32];
-            tmem_ld_32x32b_x32(trow, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(a[i]);
-            tmem_ld_32x32b_x32(trow + 32, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[32 + i] = __uint_as_float(a[i]);
-            const int qh = tok / SA_WS, qw = tok - qh * SA_WS;
-#pragma unroll
-            for (int k = 0; k < SA_WS; ++k) {
-                bh[k] = t[(qh + SA_WS - 1 - k) & 31] * SA_LOG2E;  // rows past the window (never stored) stay in range
-                bw[k] = t[32 + qw + SA_WS - 1 - k] * SA_LOG2E;
-            }
-        }
+        sw_read_bias(trow, tok, bh, bw);
         tc_fence_before();
         mbar_arrive(t_cons);
         mbar_wait(s_full, 0);
         tc_fence_after();
-        // pass 1: row maximum
-        float mx = -INFINITY;
-#define SW_PASS1(CH)                                       \
-    do {                                                   \
-        uint32_t a[32];                                    \
-        float t[32];                                       \
-        tmem_ld_32x32b_x32(trow + (CH) * 32, a);           \
-        tmem_ld_wait();                                    \
-        sw_chunk_logits<CH, 32>(a, t, sc, bh, bw);         \
-        float m4[4] = {t[0], t[1], t[2], t[3]};            \
-        _Pragma("unroll") for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], t[i]); \
-        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]))); \
-    } while (0)
-        SW_PASS1(0); SW_PASS1(1); SW_PASS1(2); SW_PASS1(3); SW_PASS1(4); SW_PASS1(5);
-#undef SW_PASS1
-        {
-            uint32_t a[16];
-            float t[16];
-            tmem_ld_32x32b_x16(trow + 192, a);
-            tmem_ld_wait();
-            sw_chunk_logits<6, 16>(a, t, sc, bh, bw);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, t[i]);
-        }
-        // pass 2: exponentials, row sum, P (bf16 pairs) written over the consumed S columns
-        float rs[4] = {0.f, 0.f, 0.f, 0.f};
-#define SW_PASS2(CH)                                                                  \
-    do {                                                                              \
-        uint32_t a[32];                                                               \
-        float t[32];                                                                  \
-        tmem_ld_32x32b_x32(trow + (CH) * 32, a);                                      \
-        tmem_ld_wait();                                                               \
-        sw_chunk_logits<CH, 32>(a, t, sc, bh, bw);                                    \
-        uint32_t pk[16];                                                              \
-        _Pragma("unroll") for (int i = 0; i < 32; i += 2) {                           \
-            const float e0 = ex2f(t[i] - mx), e1 = ex2f(t[i + 1] - mx);               \
-            rs[(i >> 1) & 3] += e0 + e1;                                              \
-            pk[i >> 1] = pack_bf16x2(e0, e1);                                         \
-        }                                                                             \
-        tmem_st_32x32b_x16(trow + (CH) * 16, pk);                                     \
-    } while (0)
-        SW_PASS2(0); SW_PASS2(1); SW_PASS2(2); SW_PASS2(3); SW_PASS2(4); SW_PASS2(5);
-#undef SW_PASS2
-        {
-            uint32_t a[16];
-            float t[16];
-            tmem_ld_32x32b_x16(trow + 192, a);
-            tmem_ld_wait();
-            sw_chunk_logits<6, 16>(a, t, sc, bh, bw);
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                const float e0 = ex2f(t[i] - mx), e1 = ex2f(t[i + 1] - mx);  // masked keys: 2^-inf = 0
-                rs[(i >> 1) & 3] += e0 + e1;
-                pk[i >> 1] = pack_bf16x2(e0, e1);
-            }
-            tmem_st_32x32b_x4(trow + 96, pk[0], pk[1], pk[2], pk[3]);
-            tmem_st_32x32b_x4(trow + 100, pk[4], pk[5], pk[6], pk[7]);
-        }
-        const float l_run = (rs[0] + rs[1]) + (rs[2] + rs[3]);
-        tmem_st_wait();
+        const float l_run = sw_softmax_row(trow, sc, bh, bw);
         tc_fence_before();
         mbar_arrive(p_ready);
-        // ---- epilogue
         mbar_wait(o_full, 0);
         tc_fence_after();
-        long long orow = -1;
-        if (tok < SA_WTOK) {
-            const int img = unit / 25, win = unit - img * 25;
-            const int iy = (win / 5) * SA_WS + tok / SA_WS, ix = (win % 5) * SA_WS + tok % SA_WS;
-            if (iy < SA_G && ix < SA_G) orow = (long long)img * (SA_G * SA_G) + iy * SA_G + ix;
-        }
-        const bool live = orow >= 0;  // tcgen05.ld is warp-collective: every lane loads, only the stores are predicated
-        const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (live ? orow : 0) * ((long long)heads * SA_D) + head * SA_D);
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            uint32_t ov[32];
-            tmem_ld_32x32b_x32(trow + SW_TM_O + cc * 32, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 0]) * inv_l, __uint_as_float(ov[g4 * 8 + 1]) * inv_l);
-                u.y = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 2]) * inv_l, __uint_as_float(ov[g4 * 8 + 3]) * inv_l);
-                u.z = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 4]) * inv_l, __uint_as_float(ov[g4 * 8 + 5]) * inv_l);
-                u.w = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 6]) * inv_l, __uint_as_float(ov[g4 * 8 + 7]) * inv_l);
-                if (live) dst[cc * 4 + g4] = u;
-            }
-        }
-        uint32_t orr[16];
-        tmem_ld_32x32b_x16(trow + SW_TM_OR, orr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g4 = 0; g4 < 2; ++g4) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 0]) * inv_l, __uint_as_float(orr[g4 * 8 + 1]) * inv_l);
-            u.y = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 2]) * inv_l, __uint_as_float(orr[g4 * 8 + 3]) * inv_l);
-            u.z = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 4]) * inv_l, __uint_as_float(orr[g4 * 8 + 5]) * inv_l);
-            u.w = pack_bf16x2(__uint_as_float(orr[g4 * 8 + 6]) * inv_l, __uint_as_float(orr[g4 * 8 + 7]) * inv_l);
-            if (live) dst[8 + g4] = u;
-        }
+        const long long orow = sw_out_row(unit, tok);
+        sw_store_row(trow, l_run, orow >= 0, reinterpret_cast<uint4*>(p.out + (orow >= 0 ? orow : 0) * ((long long)heads * SA_D) + head * SA_D));
     }
 
     tc_fence_before();
@@ -768,6 +792,205 @@ sam_window_attention_kernel(const __grid_constant__ CUtensorMap tmQm, const __gr
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<SA_TMEM_COLS>(tmem_base);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Windowed blocks, persistent kernel: ONE CTA per SM walks the (window, head) items; it owns BOTH 128-query tiles of an item (two
+// softmax warpgroups, one tensor-memory region of 208 columns each) so K / V are loaded once per item, and the producer loads the next
+// item's Q / K / V (105 KB, second shared-memory stage) while the current one is computed: allocation, barrier set-up, the position
+// tables and the TMA round trips -- what made the one-CTA-per-tile kernel 11 us per CTA -- are paid once or hidden.
+//   warp 0 producer | warp 1 MMA issuer | warps 2-5 softmax of tile A (tokens 0..127) | warps 6-9 softmax of tile B (tokens 128..195)
+// Per item:  T_A, T_B (prologue products for the position bias)  ->  S_A, S_B  ->  two-pass softmax, P in place  ->  O_A, O_B  -> store.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int SP_STAGE_BYTES = 32768 + 8192 + 2 * (SW_KROWS * 128) + 2 * (SW_KROWS * 32);  // 107520 per (window, head)
+constexpr int SP_OFF_QM = 0, SP_OFF_KM = 32768, SP_OFF_VM = SP_OFF_KM + SW_KROWS * 128, SP_OFF_QR = SP_OFF_VM + SW_KROWS * 128;
+constexpr int SP_OFF_KR = SP_OFF_QR + 8192, SP_OFF_VR = SP_OFF_KR + SW_KROWS * 32;
+static_assert(SP_OFF_VR + SW_KROWS * 32 == SP_STAGE_BYTES && SP_STAGE_BYTES % 1024 == 0, "stage layout");
+constexpr int SP_OFF_TM = 2 * SP_STAGE_BYTES;       // tables main [64 x 64]
+constexpr int SP_OFF_TR = SP_OFF_TM + 8192;         // tables rem  [64 x 16]
+constexpr int SP_OFF_BAR = SP_OFF_TR + 2048;
+constexpr int SP_NUM_BARS = 24;
+constexpr int SP_SMEM_BYTES = SP_OFF_BAR + SP_NUM_BARS * 8 + 16;
+constexpr int SP_THREADS = 320;
+constexpr uint32_t SP_TM_TILE = 256;                // tensor-memory region of tile B starts here
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+sam_window_persist_kernel(const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmKVm,
+                          const __grid_constant__ CUtensorMap tmKVr, const __grid_constant__ CUtensorMap tmTabMain,
+                          const __grid_constant__ CUtensorMap tmTabRem, const SamAttnParams p, int n_items) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_OFF_BAR);
+    uint64_t* q_full = bars + 0;      // [2] per stage
+    uint64_t* k_full = bars + 2;      // [2]
+    uint64_t* v_full = bars + 4;      // [2]
+    uint64_t* stage_free = bars + 6;  // [2] every MMA that reads the stage has completed
+    uint64_t* tab_full = bars + 8;
+    uint64_t* t_full = bars + 9;      // [2] per tile
+    uint64_t* t_cons = bars + 11;     // [2]
+    uint64_t* s_full = bars + 13;     // [2]
+    uint64_t* p_ready = bars + 15;    // [2]
+    uint64_t* o_full = bars + 17;     // [2]
+    uint64_t* o_read = bars + 19;     // [2] the tile's O has been read: its tensor-memory region may take the next item
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + SP_NUM_BARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int heads = p.heads;
+    const int stride = gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQm);
+        tma_prefetch_desc(&tmQr);
+        tma_prefetch_desc(&tmKVm);
+        tma_prefetch_desc(&tmKVr);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&stage_free[i], 1);
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_cons[i], 128);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_ready[i], 128);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_read[i], 128);
+        }
+        mbar_init(tab_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            mbar_arrive_expect_tx(tab_full, 8192 + 2048);
+            tma_load_2d(smem + SP_OFF_TM, &tmTabMain, tab_full, 0, 0);
+            tma_load_2d(smem + SP_OFF_TR, &tmTabRem, tab_full, 64, 0);
+            int it = 0;
+            for (int w = blockIdx.x; w < n_items; w += stride, ++it) {
+                const int s = it & 1;
+                const int head = w % heads, unit = w / heads;
+                const int row0 = unit * SA_WTOK;
+                const int cQm = head * 64, cKm = heads * 64 + head * 64, cVm = 2 * heads * 64 + head * 64;
+                const int cQr = 3 * heads * 64 + head * 16, cKr = cQr + heads * 16, cVr = cKr + heads * 16;
+                uint8_t* st = smem + s * SP_STAGE_BYTES;
+                if (it >= 2) mbar_wait_relaxed(&stage_free[s], ((it >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&q_full[s], 32768 + 8192);
+                tma_load_2d(st + SP_OFF_QM, &tmQm, &q_full[s], cQm, row0);
+                tma_load_2d(st + SP_OFF_QM + 16384, &tmQm, &q_full[s], cQm, row0 + 128);
+                tma_load_2d(st + SP_OFF_QR, &tmQr, &q_full[s], cQr, row0);
+                tma_load_2d(st + SP_OFF_QR + 4096, &tmQr, &q_full[s], cQr, row0 + 128);
+                mbar_arrive_expect_tx(&k_full[s], SW_KROWS * 160);
+                tma_load_2d(st + SP_OFF_KM, &tmKVm, &k_full[s], cKm, row0);
+                tma_load_2d(st + SP_OFF_KR, &tmKVr, &k_full[s], cKr, row0);
+                mbar_arrive_expect_tx(&v_full[s], SW_KROWS * 160);
+                tma_load_2d(st + SP_OFF_VM, &tmKVm, &v_full[s], cVm, row0);
+                tma_load_2d(st + SP_OFF_VR, &tmKVr, &v_full[s], cVr, row0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t IDESC_T = umma_idesc_bf16(128, 64, false, false);
+        constexpr uint32_t IDESC_S = umma_idesc_bf16(128, SW_KROWS, false, false);
+        constexpr uint32_t IDESC_OM = umma_idesc_bf16(128, 64, false, true);
+        constexpr uint32_t IDESC_OR = umma_idesc_bf16(128, 16, false, true);
+        const uint64_t tm = umma_desc(smem_u32(smem + SP_OFF_TM), LT_SW128, 1024), tr = umma_desc(smem_u32(smem + SP_OFF_TR), LT_SW32, 256);
+        mbar_wait(tab_full, 0);
+        int it = 0;
+        for (int w = blockIdx.x; w < n_items; w += stride, ++it) {
+            const int s = it & 1, ph = it & 1, sp = (it >> 1) & 1;
+            const uint32_t sb = smem_u32(smem + s * SP_STAGE_BYTES);
+            const uint64_t km = umma_desc(sb + SP_OFF_KM, LT_SW128, 1024), kr = umma_desc(sb + SP_OFF_KR, LT_SW32, 256);
+            const uint64_t vm = umma_desc(sb + SP_OFF_VM, LT_SW128, 1024), vr = umma_desc(sb + SP_OFF_VR, LT_SW32, 256);
+            mbar_wait(&q_full[s], sp);
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {  // prologue products T_x = Q_x [R_h ; R_w]^T
+                const uint64_t qm = umma_desc(sb + SP_OFF_QM + x * 16384, LT_SW128, 1024), qr = umma_desc(sb + SP_OFF_QR + x * 4096, LT_SW32, 256);
+                if (it > 0) mbar_wait(&o_read[x], (it - 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + x * SP_TM_TILE, qm + k * 2, tm + k * 2, IDESC_T, k != 0);
+                    umma_f16_ss(tmem_base + x * SP_TM_TILE, qr, tr, IDESC_T, 1);
+                    umma_commit(&t_full[x]);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&k_full[s], sp);
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {  // S_x = Q_x K^T, all 208 key columns at once
+                const uint64_t qm = umma_desc(sb + SP_OFF_QM + x * 16384, LT_SW128, 1024), qr = umma_desc(sb + SP_OFF_QR + x * 4096, LT_SW32, 256);
+                mbar_wait(&t_cons[x], ph);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + x * SP_TM_TILE, qm + k * 2, km + k * 2, IDESC_S, k != 0);
+                    umma_f16_ss(tmem_base + x * SP_TM_TILE, qr, kr, IDESC_S, 1);
+                    umma_commit(&s_full[x]);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&v_full[s], sp);
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {  // O_x = P_x V
+                mbar_wait(&p_ready[x], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t tb = tmem_base + x * SP_TM_TILE;
+#pragma unroll
+                    for (int k = 0; k < SW_KROWS / 16; ++k) {
+                        umma_f16_ts(tb + SW_TM_O, tb + k * 8, vm + k * (2048 >> 4), IDESC_OM, k != 0);
+                        umma_f16_ts(tb + SW_TM_OR, tb + k * 8, vr + k * (512 >> 4), IDESC_OR, k != 0);
+                    }
+                    umma_commit(&o_full[x]);
+                    if (x == 1) umma_commit(&stage_free[s]);  // every MMA reading this stage has been issued before this commit
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== softmax warpgroups: tile x, one thread per query row =====================
+        const int x = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t trow = tmem_base + x * SP_TM_TILE + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int tok = x * SA_BQ + r;
+        const float sc = p.scale_log2;
+        int it = 0;
+        for (int w = blockIdx.x; w < n_items; w += stride, ++it) {
+            const int ph = it & 1;
+            const int head = w % heads, unit = w / heads;
+            float bw[SA_WS], bh[SA_WS];
+            mbar_wait(&t_full[x], ph);
+            tc_fence_after();
+            sw_read_bias(trow, tok, bh, bw);
+            tc_fence_before();
+            mbar_arrive(&t_cons[x]);
+            mbar_wait(&s_full[x], ph);
+            tc_fence_after();
+            const float l_run = sw_softmax_row(trow, sc, bh, bw);
+            tc_fence_before();
+            mbar_arrive(&p_ready[x]);
+            mbar_wait(&o_full[x], ph);
+            tc_fence_after();
+            const long long orow = sw_out_row(unit, tok);
+            sw_store_row(trow, l_run, orow >= 0, reinterpret_cast<uint4*>(p.out + (orow >= 0 ? orow : 0) * ((long long)heads * SA_D) + head * SA_D));
+            tc_fence_before();
+            mbar_arrive(&o_read[x]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -815,8 +1038,9 @@ extern "C" int wg_sam_attention(const void* qkv, const void* rel_table, void* ou
     const double units = (double)n_images * (mode == 0 ? 25 : 1);
     Prof prof(mode == 0 ? "sam_attention_window" : "sam_attention_global", stream, 4.0 * units * heads * keys * keys * SA_D,
               2.0 * 4.0 * units * keys * heads * SA_D);
-    static const bool window_flash = [] { const char* e = getenv("WG_SAM_WINDOW_FLASH"); return e != nullptr && atoi(e) != 0; }();
-    if (mode == 0 && !window_flash) {
+    // windowed blocks: 0 = persistent two-tile kernel (default), 1 = one CTA per query tile, 2 = the first version (four 64-key flash blocks)
+    static const int window_kernel = [] { const char* e = getenv("WG_SAM_WINDOW_KERNEL"); return e ? atoi(e) : 0; }();
+    if (mode == 0 && window_kernel != 2) {
         // one-pass window kernel: Q tile / whole-window K, V boxes
         CUtensorMap tmQm, tmQr, tmKVm, tmKVr;
         uint64_t dims[2] = {ncols, rows};
@@ -826,8 +1050,16 @@ extern "C" int wg_sam_attention(const void* qkv, const void* rel_table, void* ou
         WG_TRY(make_tensor_map_sw(&tmQr, qkv, 2, 2, dims, strides, bqr, 32));
         WG_TRY(make_tensor_map_sw(&tmKVm, qkv, 2, 2, dims, strides, bk, 128));
         WG_TRY(make_tensor_map_sw(&tmKVr, qkv, 2, 2, dims, strides, bkr, 32));
-        WG_SMEM_OPT_IN(sam_window_attention_kernel, SW_SMEM_BYTES);
-        sam_window_attention_kernel<<<dim3(2, heads, n_images * 25), 192, SW_SMEM_BYTES, stream>>>(tmQm, tmQr, tmKVm, tmKVr, tmTabMain, tmTabRem, p);
+        if (window_kernel == 0) {
+            const int n_items = n_images * 25 * heads;
+            const int sms = device_sm_count();
+            WG_SMEM_OPT_IN(sam_window_persist_kernel, SP_SMEM_BYTES);
+            sam_window_persist_kernel<<<n_items < sms ? n_items : sms, SP_THREADS, SP_SMEM_BYTES, stream>>>(tmQm, tmQr, tmKVm, tmKVr, tmTabMain, tmTabRem, p,
+                                                                                                         n_items);
+        } else {
+            WG_SMEM_OPT_IN(sam_window_attention_kernel, SW_SMEM_BYTES);
+            sam_window_attention_kernel<<<dim3(2, heads, n_images * 25), 192, SW_SMEM_BYTES, stream>>>(tmQm, tmQr, tmKVm, tmKVr, tmTabMain, tmTabRem, p);
+        }
     } else if (mode == 0) {
         WG_SMEM_OPT_IN(sam_attention_kernel<0>, SA_SMEM_BYTES);
         sam_attention_kernel<0><<<dim3(2, heads, n_images * 25), 192, SA_SMEM_BYTES, stream>>>(tmMain, tmRem, tmTabMain, tmTabRem, p);
