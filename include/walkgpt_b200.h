@@ -158,6 +158,11 @@ WG_API size_t wg_clip_workspace_bytes(const wg_clip_weights* w, int B);
 WG_API int wg_clip_forward(const wg_clip_weights* w, const void* pixels, int pixels_is_bf16, const uint8_t* key_valid, int B,
                     int n_run, int mid_index, void* out_last, void* out_mid, int out_is_bf16, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* The same with feature_select's "cls_patch" (clip_encoder.py:61-69): keep_cls != 0 keeps the CLS row, outputs are then
+ * [B, 1 + g*g, hidden]; keep_cls == 0 is wg_clip_forward ("patch"). */
+WG_API int wg_clip_forward_ex(const wg_clip_weights* w, const void* pixels, int pixels_is_bf16, const uint8_t* key_valid, int B,
+                       int n_run, int mid_index, void* out_last, void* out_mid, int out_is_bf16, int keep_cls, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* A2 -- Multi-Scale Query Projector.  Replaces MultiScaleQFormerProjector.forward (utils/utils_walkgpt.py:259-300). */
 typedef struct wg_msqp_block {                 /* one CrossAttnBlock (utils_walkgpt.py:163-185) */

@@ -502,11 +502,12 @@ def depth_head(sd: SD, low_res_logits: torch.Tensor, upscaled: torch.Tensor, pre
 # --------------------------------------------------------------------------------------------------
 def path_a_forward(weights: Dict[str, SD], pixels: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets: Sequence[int],
                    key_valid=None, select_layer: int = -2, num: Numerics = FP32, clip_layers: int = 24,
-                   input_size=(448, 448), original_size=(448, 448)):
+                   input_size=(448, 448), original_size=(448, 448), f_last: Optional[torch.Tensor] = None):
     """weights: {"clip","msqp","proj","neck","ctp","prompt","decoder"} state dicts (module-local names).
-    Returns dict of every stage output."""
+    Returns dict of every stage output.  f_last: the tower's output computed elsewhere (bench.py's CPU arm runs HF CLIP itself)."""
     out = {}
-    f_last, f_mid = clip_tower(weights["clip"], pixels, key_valid, select_layer, num=num, total_layers=clip_layers)
+    if f_last is None:
+        f_last, f_mid = clip_tower(weights["clip"], pixels, key_valid, select_layer, num=num, total_layers=clip_layers)
     out["f_last"] = f_last
     B, L, _ = f_last.shape
     g = int(math.sqrt(L))

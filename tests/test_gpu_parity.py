@@ -725,6 +725,82 @@ def test_full_batch_properties(path_model):
     assert torch.equal(out2["logits"][S:], logits[S:]) and not torch.equal(out2["logits"][:S], logits[:S])
 
 
+def test_clip_tower_cls_patch_select_feature():
+    """feature_select 'cls_patch' (clip_encoder.py:61-69): the CLS row is kept; the patch rows are the 'patch' result bit for bit."""
+    def tower(feature):
+        a = M._ClipArgs()
+        a.mm_vision_select_feature = feature
+        return _round_weights_to_bf16(M.CLIPVisionTower(None, a, layers=3, seed=9)).to(DEV)
+    t_cls, t_patch = tower("cls_patch"), tower("patch")
+    px = rnd((2, 3, 448, 448), 91).to(DEV)
+    (last_c, (mid_c,)), (last_p, (mid_p,)) = t_cls(px), t_patch(px)
+    assert last_c.shape == (2, 1025, 1024) and last_p.shape == (2, 1024, 1024)
+    assert torch.equal(last_c[:, 1:], last_p) and torch.equal(mid_c[:, 1:], mid_p)
+    hs = path_a.clip_hidden_states(sd_cpu(t_cls), px.cpu())
+    assert rel_err(last_c, hs[t_cls.hidden_state_indices()[0]]) < 1e-2
+
+
+def test_device_seg_offsets_and_their_validation(path_model):
+    """seg_offsets as a DEVICE tensor (wg_prompt_index: no host synchronisation) gives what the host list gives; inconsistent device
+    offsets are clamped (no out-of-bounds access), inconsistent host offsets raise."""
+    B, H = 3, 4096
+    offs = [0, 2, 2, 5]
+    px = rnd((B, 3, 448, 448), 61).bfloat16().to(DEV)
+    seg = rnd((5, H), 62).to(DEV)
+    a = path_model(px, seg, offs)
+    for dt in (torch.int32, torch.int64):
+        b = path_model(px, seg, torch.tensor(offs, dtype=dt, device=DEV))
+        assert torch.equal(a["logits"], b["logits"]) and torch.equal(a["depth"], b["depth"]) and torch.equal(a["iou"], b["iou"])
+    bad = path_model(px, seg, torch.tensor([0, 9, 1, 5], dtype=torch.int32, device=DEV))  # clamped, must simply not fault
+    torch.cuda.synchronize()
+    assert bad["logits"].shape == a["logits"].shape
+    idx = torch.empty(5, dtype=torch.int32, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for o, want in (([0, 2, 2, 5], 0), ([0, 9, 1, 5], 1), ([1, 2, 2, 5], 1), ([0, 2, 2, 4], 1)):
+        od = torch.tensor(o, dtype=torch.int32, device=DEV)
+        _lib.check(_lib.lib().wg_prompt_index(od.data_ptr(), 3, 5, idx.data_ptr(), status.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        assert status.item() == want and 0 <= idx.min().item() and idx.max().item() <= 2
+    with pytest.raises(ValueError):
+        path_model(px, seg, [0, 3, 2, 5])
+
+
+def test_two_streams_and_cuda_graph_replay(path_model):
+    """Scratch buffers are per (device, stream): two calls in flight on two streams do not disturb each other; and a captured CUDA graph
+    of the whole path replays to the eager result bit for bit."""
+    B, S, H = 2, 3, 4096
+    offs = [0, S, 2 * S]
+    px = [rnd((B, 3, 448, 448), 70 + i).bfloat16().to(DEV) for i in range(2)]
+    seg = [rnd((B * S, H), 80 + i).to(DEV) for i in range(2)]
+    want = [path_model(px[i], seg[i], offs)["logits"].clone() for i in range(2)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    for rep in range(3):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                got[i] = path_model(px[i], seg[i], offs)["logits"]
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    g = M.GraphedGroundingPath(path_model, px[0], seg[0], offs)
+    before = _lib.lib().wg_launch_count(0)
+    out = g(px[1], seg[1])
+    torch.cuda.synchronize()
+    assert _lib.lib().wg_launch_count(0) == before  # replay: no host-side launches at all
+    assert torch.equal(out["logits"], want[1])
+    assert torch.equal(g(px[0], seg[0])["logits"], want[0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_second_device_runs_the_large_shared_memory_kernels():
+    """The > 48 KB dynamic shared memory opt-in is per (kernel, device): the same kernels on cuda:1 after cuda:0."""
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(dev):
+            a, w = rnd((300, 1024), 1).bfloat16().to(dev), rnd((384, 1024), 2).bfloat16().to(dev)
+            assert rel_err(ops.gemm(a, w), a.float().cpu() @ w.float().cpu().t()) < 1e-2
+            qkv = torch.randn(1, 300, 3 * 2 * 64, device=dev).bfloat16()
+            assert rel_err(ops.attention_d64(qkv, 2, 0.125), _attn_ref(qkv.cpu(), 2, 0.125)) < 1e-2
+
+
 # ------------------------------------------------------------------------------------------------ SURVEY 8(f) "next" rows
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
 def test_visual_token_resample_is_bit_exact(dt):

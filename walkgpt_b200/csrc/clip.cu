@@ -42,6 +42,13 @@ extern "C" size_t wg_clip_workspace_bytes(const wg_clip_weights* w, int B) {
 extern "C" int wg_clip_forward(const wg_clip_weights* w, const void* pixels, int pixels_is_bf16, const uint8_t* key_valid, int B, int n_run,
                                int mid_index, void* out_last, void* out_mid, int out_is_bf16, void* workspace, size_t workspace_bytes,
                                void* stream_) {
+    return wg_clip_forward_ex(w, pixels, pixels_is_bf16, key_valid, B, n_run, mid_index, out_last, out_mid, out_is_bf16, 0, workspace, workspace_bytes,
+                              stream_);
+}
+
+extern "C" int wg_clip_forward_ex(const wg_clip_weights* w, const void* pixels, int pixels_is_bf16, const uint8_t* key_valid, int B, int n_run,
+                                  int mid_index, void* out_last, void* out_mid, int out_is_bf16, int keep_cls, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
     using namespace wg;
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     WG_REQUIRE(w && pixels && out_last && workspace, "wg_clip_forward: null pointer");
@@ -67,7 +74,7 @@ extern "C" int wg_clip_forward(const wg_clip_weights* w, const void* pixels, int
     WG_TRY(launch_im2col_patch(pixels, pixels_is_bf16, b.patches, B, w->image, w->patch, w->kpad, s));
     WG_TRY(gemm_f32_out(b.patches, w->kpad, w->patch_w, B * L, D, w->kpad, nullptr, WG_ACT_NONE, b.patch_emb, D, nullptr, s));
     WG_TRY(launch_embed_ln(b.patch_emb, w->cls_emb, w->pos_emb, w->pre_ln_g, w->pre_ln_b, 1e-5f, b.x, B, T, D, s));
-    if (out_mid && mid_index == 0) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s));
+    if (out_mid && mid_index == 0) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s, keep_cls));
 
     for (int i = 0; i < n_run; ++i) {
         const wg_clip_layer& ly = w->layers[i];
@@ -78,8 +85,8 @@ extern "C" int wg_clip_forward(const wg_clip_weights* w, const void* pixels, int
         WG_TRY(wg_layernorm(b.x, 0, D, ly.ln2_g, ly.ln2_b, 1e-5f, b.ln, D, M, D, s));
         WG_TRY(gemm_bf16_out(b.ln, D, ly.w_fc1, M, w->mlp, D, ly.b_fc1, WG_ACT_QUICK_GELU, b.h1, w->mlp, s));
         WG_TRY(gemm_f32_out(b.h1, w->mlp, ly.w_fc2, M, D, w->mlp, ly.b_fc2, WG_ACT_NONE, b.x, D, b.x, s));
-        if (out_mid && mid_index == i + 1) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s));
+        if (out_mid && mid_index == i + 1) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s, keep_cls));
     }
-    WG_TRY(launch_drop_cls_cast(b.x, out_last, out_is_bf16, B, T, D, s));
+    WG_TRY(launch_drop_cls_cast(b.x, out_last, out_is_bf16, B, T, D, s, keep_cls));
     return WG_OK;
 }

@@ -7,7 +7,7 @@ namespace wg {
 int launch_im2col_patch(const void* pixels, int is_bf16, void* out_bf16, int B, int IMG, int P, int KPAD, cudaStream_t s);
 int launch_embed_ln(const float* patch_emb, const float* cls, const float* pos, const float* gamma, const float* beta, float eps, float* x,
                     int B, int T, int D, cudaStream_t s);
-int launch_drop_cls_cast(const float* x, void* out, int out_is_bf16, int B, int T, int D, cudaStream_t s);
+int launch_drop_cls_cast(const float* x, void* out, int out_is_bf16, int B, int T, int D, cudaStream_t s, int keep_cls = 0);
 
 // Bump allocator over a caller-provided workspace (256-byte aligned slices).
 struct Workspace {

@@ -211,15 +211,16 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const float* __restrict__
     }
 }
 
-// out[b, i, :] = x[b, 1+i, :]   (drop CLS), fp32 -> fp32 or bf16
+// out[b, i, :] = x[b, skip + i, :]   (skip = 1 drops CLS: select_feature "patch"; skip = 0 keeps it: "cls_patch"), fp32 -> fp32 or bf16
 template <typename TOut>
-__global__ void __launch_bounds__(256) drop_cls_cast_kernel(const float* __restrict__ x, TOut* __restrict__ out, int B, int T, int D) {
-    const long long n4 = (long long)B * (T - 1) * (D / 4);
+__global__ void __launch_bounds__(256) drop_cls_cast_kernel(const float* __restrict__ x, TOut* __restrict__ out, int B, int T, int D, int skip) {
+    const int To = T - skip;
+    const long long n4 = (long long)B * To * (D / 4);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const int d4 = (int)(i % (D / 4));
         const long long tok = i / (D / 4);
-        const int b = (int)(tok / (T - 1)), t = (int)(tok % (T - 1));
-        float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * T + t + 1) * D) + d4 * 4);
+        const int b = (int)(tok / To), t = (int)(tok % To);
+        float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * T + t + skip) * D) + d4 * 4);
         if constexpr (sizeof(TOut) == 4) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + tok * D + d4 * 4) = v;
         } else {
@@ -267,15 +268,16 @@ int launch_embed_ln(const float* patch_emb, const float* cls, const float* pos, 
     return WG_OK;
 }
 
-int launch_drop_cls_cast(const float* x, void* out, int out_is_bf16, int B, int T, int D, cudaStream_t s) {
-    const long long n4 = (long long)B * (T - 1) * (D / 4);
+int launch_drop_cls_cast(const float* x, void* out, int out_is_bf16, int B, int T, int D, cudaStream_t s, int keep_cls) {
+    const int skip = keep_cls ? 0 : 1;
+    const long long n4 = (long long)B * (T - skip) * (D / 4);
     long long blocks = (n4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     Prof prof("drop_cls_cast", s, 0.0, (double)n4 * 4 * (out_is_bf16 ? 6.0 : 8.0));
     if (out_is_bf16)
-        drop_cls_cast_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out), B, T, D);
+        drop_cls_cast_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out), B, T, D, skip);
     else
-        drop_cls_cast_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(x, static_cast<float*>(out), B, T, D);
+        drop_cls_cast_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(x, static_cast<float*>(out), B, T, D, skip);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
 }

@@ -141,8 +141,8 @@ class CLIPVisionTower(_SpecModule):
         self.vision_tower_name = vision_tower
         self.select_layer = getattr(args, "mm_vision_select_layer", -2)
         self.select_feature = getattr(args, "mm_vision_select_feature", "patch")
-        if self.select_feature != "patch":
-            raise ValueError(f"Unexpected select feature: {self.select_feature}")  # cls_patch is not on the hot path
+        if self.select_feature not in ("patch", "cls_patch"):
+            raise ValueError(f"Unexpected select feature: {self.select_feature}")  # clip_encoder.py:61-69
         if getattr(args, "resize_vision_tower", False):
             image = getattr(args, "resize_vision_tower_size", image)
         self.geom = dict(hidden=hidden, mlp=mlp, layers=layers, heads=heads, image=image, patch=patch)
@@ -256,8 +256,9 @@ class CLIPVisionTower(_SpecModule):
             idx_mid = idx_last
         n_run = max(idx_last, idx_mid)
         L = self.num_patches
+        keep_cls = int(self.select_feature == "cls_patch")
         kernel_dtype = torch.bfloat16 if out_dtype == torch.bfloat16 else torch.float32
-        out_hi = torch.empty(B, L, g["hidden"], device=images.device, dtype=kernel_dtype)
+        out_hi = torch.empty(B, L + keep_cls, g["hidden"], device=images.device, dtype=kernel_dtype)
         out_lo = torch.empty_like(out_hi) if idx_last != idx_mid else None
         kv = None
         if attention_mask is not None:
@@ -266,10 +267,10 @@ class CLIPVisionTower(_SpecModule):
         nbytes = _lib.lib().wg_clip_workspace_bytes(C.byref(w), B)
         ws = self._ws.get(nbytes, images.device)
         with torch.cuda.device(images.device):
-            _lib.check(_lib.lib().wg_clip_forward(
+            _lib.check(_lib.lib().wg_clip_forward_ex(
                 C.byref(w), images.data_ptr(), int(images.dtype == torch.bfloat16), None if kv is None else kv.data_ptr(), B,
                 n_run, min(idx_last, idx_mid), out_hi.data_ptr(), None if out_lo is None else out_lo.data_ptr(),
-                int(kernel_dtype == torch.bfloat16), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+                int(kernel_dtype == torch.bfloat16), keep_cls, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
                 "wg_clip_forward")
         if out_lo is None:
             last = mid = out_hi
@@ -1249,6 +1250,38 @@ class GroundingPath(nn.Module):
         out = self.encode_images(images_clip, attention_mask, want_vis_tokens)
         out.update(self.ground(out["img_emb_split"], seg_hidden, seg_offsets, input_size, original_size))
         return out
+
+
+class GraphedGroundingPath:
+    """One batch shape of ``GroundingPath.forward`` (or ``GroundingPathB.forward_from_pixels``) captured as a CUDA graph: ~275 kernel
+    launches become one ``cudaGraphLaunch``, which matters for small batches where the step is launch-bound (at batch 64 it is not).
+    Inputs are copied into the graph's static buffers; the returned dict holds the graph's static outputs (valid until the next call).
+
+        g = GraphedGroundingPath(path, images, seg_hidden, seg_offsets)     # seg_offsets: host list (fixed [SEG] layout per graph)
+        out = g(images2, seg_hidden2)
+    """
+
+    def __init__(self, path: nn.Module, images: torch.Tensor, seg_hidden: torch.Tensor, seg_offsets, from_pixels_b: bool = False, **kw):
+        _need_cuda(images, "GraphedGroundingPath")
+        self.images, self.seg = images.clone(), seg_hidden.clone()
+        fn = path.forward_from_pixels if from_pixels_b else path
+        offs = [int(v) for v in seg_offsets]
+        cur = torch.cuda.current_stream(images.device)
+        side = torch.cuda.Stream(images.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up outside the capture: packs weights, caches offsets / PE tables, opts kernels in
+            for _ in range(2):
+                fn(self.images, self.seg, offs, **kw)
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(self.images, self.seg, offs, **kw)
+
+    def __call__(self, images: torch.Tensor, seg_hidden: torch.Tensor):
+        self.images.copy_(images)
+        self.seg.copy_(seg_hidden)
+        self.graph.replay()
+        return self.out
 
 
 class GroundingPathB(nn.Module):
