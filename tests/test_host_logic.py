@@ -153,3 +153,47 @@ def test_prompt_index_validates_host_offsets_and_caches_by_value():
     pi.index([0, 1, 2, 5], 3, 5, "cpu")
     pi.index([0, 0, 0, 5], 3, 5, "cpu")
     assert len(pi.cache) == 2  # bounded
+
+
+def test_sam_encoder_host_side_packing():
+    """ImageEncoderViT drop-in: reference parameter names / shapes, the qkv row permutation (head slices of 64 + 16 channels) and the
+    relative-position tables the attention kernel's prologue MMA reads."""
+    enc = M.ImageEncoderViT(embed_dim=640, depth=2, num_heads=8, global_attn_indexes=(1,))
+    sd = enc.state_dict()
+    assert sd["pos_embed"].shape == (1, 64, 64, 640) and sd["blocks.0.attn.rel_pos_h"].shape == (27, 80) and sd["blocks.1.attn.rel_pos_w"].shape == (127, 80)
+    assert sd["blocks.0.attn.qkv.weight"].shape == (1920, 640) and sd["neck.2.weight"].shape == (256, 256, 3, 3)
+    order = M.sam_qkv_row_order(8)
+    assert sorted(order.tolist()) == list(range(1920))                       # a permutation
+    # head 3 of K: main slice then rem slice
+    k3 = 640 + 3 * 80
+    assert order[8 * 64 + 3 * 64: 8 * 64 + 4 * 64].tolist() == list(range(k3, k3 + 64))
+    assert order[3 * 8 * 64 + 8 * 16 + 3 * 16: 3 * 8 * 64 + 8 * 16 + 4 * 16].tolist() == list(range(k3 + 64, k3 + 80))
+    # a linear layer with permuted rows gives permuted outputs: the attention kernel sees q_h = [main | rem] of the reference's q_h
+    x = torch.randn(5, 640)
+    W, b = sd["blocks.0.attn.qkv.weight"], sd["blocks.0.attn.qkv.bias"]
+    ref = F.linear(x, W, b).view(5, 3, 8, 80)
+    got = F.linear(x, W[order], b[order])
+    main, rem = got[:, :3 * 8 * 64].view(5, 3, 8, 64), got[:, 3 * 8 * 64:].view(5, 3, 8, 16)
+    assert torch.equal(torch.cat([main, rem], dim=-1), ref)
+    t = M.sam_rel_table(sd["blocks.0.attn.rel_pos_h"], sd["blocks.0.attn.rel_pos_w"], 14)
+    assert t.shape == (64, 80) and torch.equal(t[:27], sd["blocks.0.attn.rel_pos_h"]) and torch.equal(t[32:59], sd["blocks.0.attn.rel_pos_w"])
+    assert t[27:32].abs().sum() == 0 and t[59:].abs().sum() == 0
+    t = M.sam_rel_table(sd["blocks.1.attn.rel_pos_h"], sd["blocks.1.attn.rel_pos_w"], 64)
+    assert t.shape == (256, 80) and torch.equal(t[128:255], sd["blocks.1.attn.rel_pos_w"])
+    with pytest.raises(NotImplementedError):
+        M.sam_rel_table(torch.zeros(13, 80), torch.zeros(13, 80), 14)         # tables that would need get_rel_pos's interpolation
+    with pytest.raises(ValueError):
+        M.ImageEncoderViT(img_size=512)
+    with pytest.raises(ValueError):
+        M.ImageEncoderViT(embed_dim=768, num_heads=12)                        # head_dim 64: ViT-B is not SAM ViT-H's geometry
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (build container only)")
+def test_reference_image_encoder_loads_our_state_dict_strictly():
+    import sys
+    import torch.nn as nn
+    sys.path.insert(0, REF)
+    from model.segment_anything.modeling.image_encoder import ImageEncoderViT
+    ref = ImageEncoderViT(img_size=1024, patch_size=16, embed_dim=640, depth=2, num_heads=8, out_chans=256, use_rel_pos=True, window_size=14,
+                          global_attn_indexes=(1,), norm_layer=lambda d: nn.LayerNorm(d, eps=1e-6))
+    ref.load_state_dict(M.ImageEncoderViT(embed_dim=640, depth=2, num_heads=8, global_attn_indexes=(1,)).state_dict(), strict=True)
