@@ -110,11 +110,17 @@ struct AttnParams {
     float scale_log2;
     const uint8_t* key_valid;  // [B, T] or null
     int n_items, n_full_tiles, batch;  // persistent kernel: work items = (image, head, query tile), full tiles first
+    // T = 128 k + 1 (the CLIP tower: 1024 patches + CLS) in the persistent kernel: the key blocks cover the first 128 k keys and the
+    // LAST key is scored once per tile on CUDA cores by the row's own softmax thread (extra_key = 1); it enters the initial maximum
+    // and is folded into O and l in the epilogue, so the tile runs k instead of k + 1 softmax steps
+    int extra_key;
+    const __nv_bfloat16* qkv;
 };
 
 struct SoftmaxState {
     float m_ref;  // the maximum the current scale refers to
     float l_run;  // running row sum in that scale
+    float x_acc;  // persistent kernel, extra_key: the last key's score, accumulated two 16-byte chunks per key block (blocks 0..3)
 };
 
 // One key block for one query row (= one thread): S row (NCH x 32 columns) from TMEM -> registers, hand S back, online softmax
@@ -127,7 +133,8 @@ struct SoftmaxState {
 // columns are packed into registers before it, so that the tensor core's latency is covered by exponentials, not by a stall.
 template <int NCH, int POLY, int SPLIT>
 __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, int gblk, const AttnParams& p, const uint32_t* kmask, uint32_t tmem_S, uint32_t tmem_O,
-                                              uint32_t tmem_P, uint32_t lane_off, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready, int tr, int half, int r, float* xch) {
+                                              uint32_t tmem_P, uint32_t lane_off, uint64_t* s_free, uint64_t* p_free, uint64_t* p_ready, int tr, int half, int r, float* xch,
+                                              const uint8_t* xq = nullptr, const uint8_t* xk = nullptr) {
     // j = key block within the current query tile; gblk = key blocks this CTA has processed before it (barrier phases; == j in
     // the one-tile-per-CTA kernel, a running count in the persistent one)
     // NCH = number of 32-column chunks THIS thread handles (SPLIT = 2: the thread owns columns [64 half, 64 half + 32 NCH))
@@ -138,6 +145,24 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& st, int j, int gblk,
 #define sv(i) sv2[(i) >> 5][(i) & 31]
 #pragma unroll
     for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tmem_S + lane_off + half * 64 + c * 32, sv2[c]);
+    if (xq != nullptr && j < 4) {
+        // extra_key: a quarter of the dot product q_row . k_last in the shadow of the tensor-memory loads (xq: this row of the swizzled
+        // Q tile, xk: the K row, both in shared memory; chunk `pos` of the Q row holds the row's 16-byte chunk pos ^ (r & 7))
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const int pos = j * 2 + pp;
+            const uint4 qa = *reinterpret_cast<const uint4*>(xq + pos * 16);
+            const uint4 ka = *reinterpret_cast<const uint4*>(xk + ((pos ^ (r & 7)) * 16));
+            const uint32_t qw[4] = {qa.x, qa.y, qa.z, qa.w}, kw[4] = {ka.x, ka.y, ka.z, ka.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a0 = fmaf(__uint_as_float(qw[e] << 16), __uint_as_float(kw[e] << 16), a0);
+                a1 = fmaf(__uint_as_float(qw[e] & 0xffff0000u), __uint_as_float(kw[e] & 0xffff0000u), a1);
+            }
+        }
+        st.x_acc += a0 + a1;
+    }
     if (NCH > 0) tmem_ld_wait();
     TR(0, j, 2);
     tc_fence_before();
@@ -444,7 +469,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         // warps whose 32 query rows all lie past T (last query tile: only the 1025th token is real) skip the arithmetic and only
         // keep the barrier protocol alive; their P / O rows are never stored (the TMA store clips at T).
         const bool warp_active = qt * ATT_BQ + quarter * 32 < p.T;
-        SoftmaxState st{0.f, 0.f};
+        SoftmaxState st{0.f, 0.f, 0.f};
         for (int j = 0; j < nkb; ++j) {
             TR(0, j, 0);
             mbar_wait(s_full, j & 1);
@@ -536,7 +561,8 @@ constexpr int PQ_OFF_V = PQ_OFF_K + 2 * TILE_BYTES;      // 2 stages
 constexpr int PQ_OFF_BAR = PQ_OFF_V + 2 * TILE_BYTES;
 constexpr int PQ_NUM_BARS = 16;
 constexpr int PQ_OFF_KMASK = PQ_OFF_BAR + PQ_NUM_BARS * 8 + 16;
-constexpr int PQ_SMEM_BYTES = PQ_OFF_KMASK + (ATT_MAX_T / 32) * 4;
+constexpr int PQ_OFF_XKV = PQ_OFF_KMASK + (ATT_MAX_T / 32) * 4;  // extra_key: [2 Q buffers][K row | V row] of the last key, 128 B each
+constexpr int PQ_SMEM_BYTES = PQ_OFF_XKV + 2 * 256;
 
 struct AttnItem {
     int qt, head, img;
@@ -616,8 +642,13 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
                 const bool has_next = w + stride < p.n_items;
                 const AttnItem nxt = has_next ? attn_item(p, w + stride) : cur;
                 if (it == 0) {
-                    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
+                    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES + (p.extra_key ? 256 : 0));
                     tma_load_3d(smem + PQ_OFF_Q, &tmQKV, &q_full[0], cur.head * ATT_D, cur.qt * ATT_BQ, cur.img);
+                    if (p.extra_key) {
+                        const __nv_bfloat16* xrow = p.qkv + ((size_t)cur.img * p.T + (p.T - 1)) * (3 * HD) + cur.head * ATT_D;
+                        bulk_load_1d(smem + PQ_OFF_XKV, xrow + HD, 128, &q_full[0]);
+                        bulk_load_1d(smem + PQ_OFF_XKV + 128, xrow + 2 * HD, 128, &q_full[0]);
+                    }
                     mbar_arrive_expect_tx(&k_full[0], TILE_BYTES);
                     tma_load_3d(smem + PQ_OFF_K, &tmQKV, &k_full[0], HD + cur.head * ATT_D, 0, cur.img);
                 }
@@ -639,8 +670,13 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
                         // Q of the next item into the other buffer; from the third item on that buffer last staged an O tile
                         const int qb = (it + 1) & 1;
                         if (it + 1 >= 2) mbar_wait_relaxed(&q_free[qb], (((it + 1) >> 1) - 1) & 1);
-                        mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES);
+                        mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES + (p.extra_key ? 256 : 0));
                         tma_load_3d(smem + PQ_OFF_Q + qb * TILE_BYTES, &tmQKV, &q_full[qb], nxt.head * ATT_D, nxt.qt * ATT_BQ, nxt.img);
+                        if (p.extra_key) {  // the last key's K and V rows travel with the Q tile
+                            const __nv_bfloat16* xrow = p.qkv + ((size_t)nxt.img * p.T + (p.T - 1)) * (3 * HD) + nxt.head * ATT_D;
+                            bulk_load_1d(smem + PQ_OFF_XKV + qb * 256, xrow + HD, 128, &q_full[qb]);
+                            bulk_load_1d(smem + PQ_OFF_XKV + qb * 256 + 128, xrow + 2 * HD, 128, &q_full[qb]);
+                        }
                     }
                 }
             }
@@ -713,7 +749,7 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
         const int r = quarter * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
         uint32_t* words = reinterpret_cast<uint32_t*>(smem + PQ_OFF_KMASK);
-        const bool need_mask = p.key_valid != nullptr || (p.T % ATT_BKV) != 0;
+        const bool need_mask = p.key_valid != nullptr || ((p.T % ATT_BKV) != 0 && !p.extra_key);
         int g = 0, it = 0, mask_img = -1;
         for (int w = blockIdx.x; w < p.n_items; w += stride, ++it) {
             const AttnItem cur = attn_item(p, w);
@@ -735,7 +771,18 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
                 kmask = words;
             }
             const bool warp_active = cur.qt * ATT_BQ + quarter * 32 < p.T;
-            SoftmaxState st{0.f, 0.f};
+            SoftmaxState st{0.f, 0.f, 0.f};
+            // extra_key: the last key's K row | V row arrived with the Q tile; its score is accumulated inside blocks 0..3
+            const uint8_t* xkv = smem + PQ_OFF_XKV + (it & 1) * 256;
+            const uint8_t* xq = nullptr;
+            bool x_valid = false;
+            if (p.extra_key && warp_active) {
+                x_valid = p.key_valid == nullptr || p.key_valid[(size_t)cur.img * p.T + (p.T - 1)] != 0;
+                if (x_valid) {
+                    mbar_wait(&q_full[it & 1], (it >> 1) & 1);  // long complete (S_0 of this item is already being computed)
+                    xq = smem + PQ_OFF_Q + (it & 1) * TILE_BYTES + r * 128;
+                }
+            }
             for (int j = 0; j < nkb; ++j, ++g) {
                 mbar_wait(s_full, g & 1);
                 tc_fence_after();
@@ -748,7 +795,7 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
                     const int ncols = (j + 1 == nkb) ? p.n_last : ATT_BKV;
                     const uint32_t* km = (p.key_valid != nullptr || j + 1 == nkb) ? kmask : nullptr;
                     const int nch = (ncols + 31) >> 5;
-#define WG_SM_ARGS st, j, g, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr, 0, r, nullptr
+#define WG_SM_ARGS st, j, g, p, km, tmem_S, tmem_O, tmem_P, lane_off, s_free, p_free, p_ready, tr, 0, r, nullptr, xq, xkv
                     if (nch == 4) softmax_block<4, POLY, 1>(WG_SM_ARGS);
                     else if (nch == 3) softmax_block<3, POLY, 1>(WG_SM_ARGS);
                     else if (nch == 2) softmax_block<2, POLY, 1>(WG_SM_ARGS);
@@ -764,7 +811,22 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
             // ---- epilogue: O / l, bf16, staged in this item's (finished) Q buffer, bulk store left in flight
             mbar_wait(p_free, (g - 1) & 1);
             tc_fence_after();
-            const float inv_l = st.l_run > 0.f ? 1.0f / st.l_run : 0.f;
+            // the extra key joins here: common maximum m_fin, O and l brought to it (a_x = 1 unless the last key's score exceeds the
+            // running reference), weight p_x <= 1
+            float a_x = 1.f, p_x = 0.f;
+            if (x_valid) {
+                const float d = (st.x_acc - st.m_ref) * p.scale_log2;
+                if (st.l_run > 0.f) {
+                    a_x = d > 0.f ? ex2_approx(-d) : 1.f;
+                    p_x = d > 0.f ? 1.f : ex2_approx(d);
+                } else {  // every key of the blocks is masked: the extra key is the whole row
+                    a_x = 0.f;
+                    p_x = 1.f;
+                }
+            }
+            const float l_fin = st.l_run * a_x + p_x;
+            const float inv0 = l_fin > 0.f ? 1.0f / l_fin : 0.f;
+            const float inv_l = inv0 * a_x, w_x = inv0 * p_x;
             uint8_t* o_tile = smem + PQ_OFF_Q + (it & 1) * TILE_BYTES;
             uint8_t* o_row = o_tile + r * 128;
             if (warp_active) {
@@ -773,13 +835,27 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
                     uint32_t ov[32];
                     tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
                     tmem_ld_wait();
+                    const float fin = x_valid ? 1.f : inv_l;
+                    if (x_valid) {  // O * inv_l + w_x * V[last key] here; the packing below then scales by 1
+                        const uint4* v16 = reinterpret_cast<const uint4*>(xkv + 128) + c * 4;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const uint4 va = v16[q4];
+                            const uint32_t vw[4] = {va.x, va.y, va.z, va.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                ov[q4 * 8 + 2 * e] = __float_as_uint(fmaf(w_x, __uint_as_float(vw[e] << 16), __uint_as_float(ov[q4 * 8 + 2 * e]) * inv_l));
+                                ov[q4 * 8 + 2 * e + 1] = __float_as_uint(fmaf(w_x, __uint_as_float(vw[e] & 0xffff0000u), __uint_as_float(ov[q4 * 8 + 2 * e + 1]) * inv_l));
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         uint4 u;
-                        u.x = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 0]) * inv_l, __uint_as_float(ov[q4 * 8 + 1]) * inv_l);
-                        u.y = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 2]) * inv_l, __uint_as_float(ov[q4 * 8 + 3]) * inv_l);
-                        u.z = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 4]) * inv_l, __uint_as_float(ov[q4 * 8 + 5]) * inv_l);
-                        u.w = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 6]) * inv_l, __uint_as_float(ov[q4 * 8 + 7]) * inv_l);
+                        u.x = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 0]) * fin, __uint_as_float(ov[q4 * 8 + 1]) * fin);
+                        u.y = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 2]) * fin, __uint_as_float(ov[q4 * 8 + 3]) * fin);
+                        u.z = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 4]) * fin, __uint_as_float(ov[q4 * 8 + 5]) * fin);
+                        u.w = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 6]) * fin, __uint_as_float(ov[q4 * 8 + 7]) * fin);
                         *reinterpret_cast<uint4*>(o_row + (((c * 4 + q4) ^ (r & 7)) * 16)) = u;
                     }
                 }
@@ -839,9 +915,11 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     p.n_last = ((T - (p.num_kv_blocks - 1) * ATT_BKV) + 15) / 16 * 16;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.key_valid = key_valid;
+    p.extra_key = 0;
+    p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     // tuning knobs (defaults measured on B200): WG_ATTN_POLY = exponentials per 8 evaluated on the FMA pipe,
     // WG_ATTN_SPLIT = softmax threads per query row
-    struct Knobs { int poly, split, smem_pad, persist; };
+    struct Knobs { int poly, split, smem_pad, persist, extra; };
     static const Knobs knobs = [] {  // read once (C++11 guarantees a thread-safe initialisation)
         Knobs k;
         const char* pad = getenv("WG_ATTN_SMEM_PAD");  // debug: extra dynamic smem (forces one CTA per SM when large)
@@ -854,6 +932,8 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
         if (k.split != 1 && k.split != 2) k.split = ATT_SPLIT_DEFAULT;
         e = getenv("WG_ATTN_PERSIST");
         k.persist = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+        e = getenv("WG_ATTN_EXTRA_KEY");  // 0: the 1025th key gets its own (narrow) key block, as in round 1
+        k.extra = (e == nullptr || atoi(e) != 0) ? 1 : 0;
         return k;
     }();
     const int poly = knobs.poly, split = knobs.split, smem_pad = knobs.smem_pad, persist = knobs.persist;
@@ -867,6 +947,11 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     // CTA per (tile, head, image)
     const long long n_items = (long long)B * heads * ((T + ATT_BQ - 1) / ATT_BQ);
     if (persist && split == 1 && p.num_kv_blocks >= 4 && n_items < (1ll << 30)) {
+        if (knobs.extra && T % ATT_BKV == 1 && T / ATT_BKV >= 4) {  // T = 128 k + 1: k full key blocks + the last key on CUDA cores
+            p.extra_key = 1;
+            p.num_kv_blocks = T / ATT_BKV;
+            p.n_last = ATT_BKV;
+        }
         p.n_full_tiles = T / ATT_BQ;
         p.batch = B;
         p.n_items = (int)n_items;
