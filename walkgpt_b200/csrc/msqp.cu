@@ -276,6 +276,269 @@ __global__ void __launch_bounds__(256) msqp_attention_kernel(const __nv_bfloat16
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same cross attention on the tensor cores (tcgen05 / TMEM / TMA).  One CTA per (image, head, split of <= 1024 keys), two per SM;
+// with more than one split (the 4096-token scale of Path B) every CTA leaves an unnormalised partial (m, l, O) and
+// msqp_merge_splits_kernel combines them.
+// With <= 12 queries the natural orientation is the TRANSPOSED score tile: keys on the MMA's M dimension.
+//   warp 0   : TMA producer: Q [16 x 128] once, then the K tiles and the V tiles ([128 keys x 128 dims] = two 64-wide 128B-swizzled
+//              boxes, 32 KB) of this head through ONE 3-stage ring -- each K / V byte crosses L2 -> SM exactly once
+//   warp 1   : TMEM allocation + MMA issue.  Phase 1: S^T_kb [128 keys x 16 queries] = K_kb Q^T (M = 128, N = 16, 8 k-steps) for every
+//              key block into its own 16 tensor-memory columns -- the whole score matrix (<= 8 x 16 columns) stays in TMEM, so the
+//              softmax is an exact two-pass one with no running rescale.  Phase 2: O [16 (of 128) x 128] += P_kb V_kb, P as a K-major
+//              shared-memory operand, V as the MN-major operand straight from its TMA tile (two N = 64 halves)
+//   warps 2-5: softmax, ONE THREAD PER KEY (TMEM lane == key): pass A row maxima per query (16 registers, then shuffles + one shared
+//              exchange), pass B exponentials, per-thread partial sums, P^T written as bf16 into the 16 real rows of the P operand.
+//              The MMA's M is 128 but only rows < nq mean anything: rows 16..127 of the P operand are never initialised -- the
+//              descriptor walks into whatever follows (the K/V ring) and the garbage lands in O lanes that nobody reads.
+// Keys past Nkv in the last block (Nkv = 256 / 64 / 1 for the pooled and global scales) are masked to -inf; their V rows are other
+// images' rows or TMA zero fill and meet P = 0.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int TC_MAX_NKV = 1024;
+constexpr int TC_PART_PITCH = 132;                // floats per partial row: 128 O values, m, l, 2 pad (16-byte rows)
+constexpr int TC_OFF_Q = 0;                       // 2 boxes [16 x 64] bf16, 2 KB each
+constexpr int TC_OFF_P = 4096;                    // 2 buffers x 2 boxes [16 real rows x 64 keys], 2 KB each
+constexpr int TC_OFF_KV = 12288;                  // 3 stages x 32 KB
+constexpr int TC_STAGES = 3;
+constexpr int TC_STAGE_BYTES = 32768;
+constexpr int TC_OFF_BAR = TC_OFF_KV + TC_STAGES * TC_STAGE_BYTES;
+constexpr int TC_NUM_BARS = 14;
+constexpr int TC_OFF_RED = TC_OFF_BAR + TC_NUM_BARS * 8 + 16;   // [4 warps][16] floats
+constexpr int TC_SMEM_BYTES = TC_OFF_RED + 4 * 16 * 4;
+
+__global__ void __launch_bounds__(192, 2)
+msqp_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int k_off, int v_off,
+                         __nv_bfloat16* __restrict__ out, int nq, int Nkv_all, int nsplit, float* __restrict__ part) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;    // [3]
+    uint64_t* kv_empty = bars + 4;   // [3]
+    uint64_t* s_done = bars + 7;
+    uint64_t* o_done = bars + 8;
+    uint64_t* p_ready = bars + 9;    // [2]
+    uint64_t* p_free = bars + 11;    // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + TC_NUM_BARS);
+    float* red = reinterpret_cast<float*>(smem + TC_OFF_RED);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sp = blockIdx.x % nsplit, bh = blockIdx.x / nsplit;
+    const int b = bh >> 3, h = bh & 7;
+    const int key0 = sp * TC_MAX_NKV;                                     // this split's first key
+    const int Nkv = min(TC_MAX_NKV, Nkv_all - key0);                       // and its key count
+    const int NB = (Nkv + 127) >> 7;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmKV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < TC_STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_done, 1);
+        mbar_init(o_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&p_ready[i], 128);
+            mbar_init(&p_free[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_S = *tmem_ptr_smem;   // 16 columns per key block
+    const uint32_t tmem_O = tmem_S + 128;     // 128 columns
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 4096);
+            tma_load_2d(smem + TC_OFF_Q, &tmQ, q_full, h * 128, b * nq);
+            tma_load_2d(smem + TC_OFF_Q + 2048, &tmQ, q_full, h * 128 + 64, b * nq);
+            for (int i = 0; i < 2 * NB; ++i) {
+                const int st = i % TC_STAGES, use = i / TC_STAGES;
+                mbar_wait_relaxed(&kv_empty[st], (use & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], TC_STAGE_BYTES);
+                const int col = (i < NB ? k_off : v_off) + h * 128;
+                const int row = b * Nkv_all + key0 + (i < NB ? i : i - NB) * 128;
+                uint8_t* dst = smem + TC_OFF_KV + st * TC_STAGE_BYTES;
+                tma_load_2d(dst, &tmKV, &kv_full[st], col, row);
+                tma_load_2d(dst + 16384, &tmKV, &kv_full[st], col + 64, row);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 16, false, false);
+        constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 64, false, true);
+        const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + TC_OFF_Q));
+        const uint64_t p_desc = umma_desc_sw128(smem_u32(smem + TC_OFF_P));
+        const uint64_t kv_desc = umma_desc_sw128(smem_u32(smem + TC_OFF_KV));
+        mbar_wait(q_full, 0);
+        for (int kb = 0; kb < NB; ++kb) {
+            const int st = kb % TC_STAGES;
+            mbar_wait(&kv_full[st], (kb / TC_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t kd = kv_desc + st * (TC_STAGE_BYTES >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)  // 128 dims = 2 boxes x 4 k-steps of 16
+                    umma_f16_ss(tmem_S + kb * 16, kd + (ks >> 2) * (16384 >> 4) + (ks & 3) * 2, q_desc + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2, IDESC_S,
+                                ks != 0);
+                umma_commit(&kv_empty[st]);
+                if (kb + 1 == NB) umma_commit(s_done);
+            }
+            __syncwarp();
+        }
+        for (int kb = 0; kb < NB; ++kb) {
+            const int i = NB + kb, st = i % TC_STAGES, buf = kb & 1;
+            mbar_wait(&kv_full[st], (i / TC_STAGES) & 1);
+            mbar_wait(&p_ready[buf], (kb >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t vd = kv_desc + st * (TC_STAGE_BYTES >> 4);
+                const uint64_t pd = p_desc + buf * (4096 >> 4);
+#pragma unroll
+                for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)  // 128 keys = 8 k-steps; P: 2 boxes x 4 k-steps, V: 2048 B per k-step inside its box
+                        umma_f16_ss(tmem_O + nh * 64, pd + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2, vd + nh * (16384 >> 4) + ks * (2048 >> 4), IDESC_O,
+                                    (kb | ks) != 0);
+                umma_commit(&kv_empty[st]);
+                umma_commit(&p_free[buf]);
+                if (kb + 1 == NB) umma_commit(o_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int t = quarter * 32 + lane;  // key within a block == TMEM lane
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const float c = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
+        mbar_wait(s_done, 0);
+        tc_fence_after();
+        // ---- pass A: maxima
+        float mx[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) mx[q] = -INFINITY;
+        for (int kb = 0; kb < NB; ++kb) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_S + lane_off + kb * 16, v);
+            tmem_ld_wait();
+            if (kb * 128 + t < Nkv) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(v[q]));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) mx[q] = warp_max(mx[q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) red[quarter * 16 + q] = mx[q];
+        }
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) mx[q] = fmaxf(fmaxf(red[q], red[16 + q]), fmaxf(red[32 + q], red[48 + q])) * c;  // key 0 is always valid: finite
+        named_bar_sync(1, 128);  // red is reused for the sums
+        // ---- pass B: exponentials, partial sums, P^T -> the operand tile (row q, key t)
+        float sum[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sum[q] = 0.f;
+        const uint32_t p_elem = static_cast<uint32_t>((t >> 6) * 2048 + (t & 7) * 2);
+        const uint32_t p_chunk = static_cast<uint32_t>((t & 63) >> 3);
+        for (int kb = 0; kb < NB; ++kb) {
+            const int buf = kb & 1;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_S + lane_off + kb * 16, v);
+            tmem_ld_wait();
+            const bool valid = kb * 128 + t < Nkv;
+            float pr[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                pr[q] = valid ? exp2f(fmaf(__uint_as_float(v[q]), c, -mx[q])) : 0.f;
+                sum[q] += pr[q];
+            }
+            if (kb >= 2) mbar_wait(&p_free[buf], ((kb >> 1) - 1) & 1);
+            uint8_t* pb = smem + TC_OFF_P + buf * 4096 + p_elem;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (q < nq) *reinterpret_cast<__nv_bfloat16*>(pb + q * 128 + ((p_chunk ^ (q & 7)) << 4)) = __float2bfloat16(pr[q]);
+            fence_proxy_async_smem();
+            mbar_arrive(&p_ready[buf]);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sum[q] = warp_sum(sum[q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) red[quarter * 16 + q] = sum[q];
+        }
+        named_bar_sync(1, 128);
+        // ---- epilogue: the warp that owns TMEM lanes 0..31 holds the query rows
+        if (quarter == 0) {
+            mbar_wait(o_done, 0);
+            tc_fence_after();
+            const float l_row = red[lane & 15] + red[16 + (lane & 15)] + red[32 + (lane & 15)] + red[48 + (lane & 15)];
+            const float inv = 1.0f / l_row;
+            __nv_bfloat16* orow = out + ((size_t)b * nq + lane) * D + h * 128;
+            // several splits: partial record [16 rows][128 O values | m | l] per (image, head, split), unnormalised, m in log2 units
+            float* prow = part != nullptr ? part + (((size_t)bh * nsplit + sp) * 16 + lane) * TC_PART_PITCH : nullptr;
+            if (prow != nullptr && lane < nq) {
+                float m_row = mx[0];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) m_row = (lane == q) ? mx[q] : m_row;
+                prow[128] = m_row;
+                prow[129] = l_row;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(tmem_O + cc * 32, ov);  // warp-collective: every lane loads, only real query rows store
+                tmem_ld_wait();
+                if (prow != nullptr) {
+                    if (lane < nq) {
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            *reinterpret_cast<uint4*>(prow + cc * 32 + g4 * 4) = make_uint4(ov[g4 * 4], ov[g4 * 4 + 1], ov[g4 * 4 + 2], ov[g4 * 4 + 3]);
+                    }
+                } else if (lane < nq) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 0]) * inv, __uint_as_float(ov[g4 * 8 + 1]) * inv);
+                        u.y = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 2]) * inv, __uint_as_float(ov[g4 * 8 + 3]) * inv);
+                        u.z = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 4]) * inv, __uint_as_float(ov[g4 * 8 + 5]) * inv);
+                        u.w = pack_bf16x2(__uint_as_float(ov[g4 * 8 + 6]) * inv, __uint_as_float(ov[g4 * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + cc * 32 + g4 * 8) = u;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_S);
+    }
+}
+
+// out[b, q, h*128 + d] = sum_s O_s 2^(m_s - M) / sum_s l_s 2^(m_s - M) over the key splits.  grid B*8, 128 threads (d)
+__global__ void __launch_bounds__(128) msqp_merge_splits_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out, int nq, int nsplit) {
+    const int bh = blockIdx.x, b = bh >> 3, h = bh & 7, d = threadIdx.x;
+    for (int q = 0; q < nq; ++q) {
+        float M = -INFINITY;
+        for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, part[(((size_t)bh * nsplit + sp) * 16 + q) * TC_PART_PITCH + 128]);
+        float o = 0.f, l = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) {
+            const float* r = part + (((size_t)bh * nsplit + sp) * 16 + q) * TC_PART_PITCH;
+            const float w = exp2f(r[128] - M);
+            o = fmaf(r[d], w, o);
+            l = fmaf(r[129], w, l);
+        }
+        out[((size_t)b * nq + q) * D + h * 128 + d] = __float2bfloat16(o / l);
+    }
+}
+
 // tokens[b, 0..31] = concat of the four query groups, tokens[b, 32..n_tok) = pad_token   (bf16)
 struct AssembleArgs {
     const float* q[4];
@@ -309,6 +572,7 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(AssembleArgs a, co
 struct MsqpBuffers {
     __nv_bfloat16 *xs, *t, *hg, *kv[4], *qn, *qp, *ao, *f, *f1, *tok;
     float* q[4];
+    float* part;  // key-split partials of the tensor-core cross attention (scales with more than 1024 keys)
     long long rows[4], row_off[4], R;
 };
 
@@ -341,6 +605,7 @@ bool carve(Workspace& ws, const wg_msqp_weights* w, int B, int L, MsqpBuffers& m
     m.f = (__nv_bfloat16*)take(qmax * D * 2);
     m.f1 = (__nv_bfloat16*)take(qmax * 4 * D * 2);
     m.tok = (__nv_bfloat16*)take((size_t)B * w->n_tokens * D * 2);
+    m.part = (float*)take((size_t)B * 8 * ((L + TC_MAX_NKV - 1) / TC_MAX_NKV) * 16 * TC_PART_PITCH * 4);
     return ok;
 }
 
@@ -416,16 +681,31 @@ extern "C" int wg_msqp_forward(const wg_msqp_weights* w, const void* feats_bf16,
         broadcast_queries_kernel<<<grid_for((long long)Mq * (D / 4)), 256, 0, s>>>(S.queries, m.q[sc], B, S.nq);
         }
         WG_CHECK_CUDA(cudaGetLastError());
-        const size_t smem = (size_t)(MAXQ * 128 + (size_t)QPAD * Nkv + 4 * MAXQ * 128) * sizeof(float);
-        WG_REQUIRE(smem <= 227 * 1024, "wg_msqp_forward: %d kv tokens x %d queries exceed shared memory", Nkv, S.nq);
+        const size_t smem = (size_t)(MAXQ * 128 + (size_t)QPAD * Nkv + 4 * MAXQ * 128) * sizeof(float);  // CUDA-core kernel (WG_MSQP_TC=0)
         WG_SMEM_OPT_IN(msqp_attention_kernel, 227 * 1024);
+        WG_SMEM_OPT_IN(msqp_attention_tc_kernel, TC_SMEM_BYTES);
+        // tensor-core kernel (Nkv <= 1024): queries as [16 x 64] boxes of qp, K / V as [128 x 64] boxes of this scale's kv matrix
+        static const bool use_tc = [] { const char* e = getenv("WG_MSQP_TC"); return e == nullptr || atoi(e) != 0; }();
+        CUtensorMap tmQ, tmKV;
+        if (use_tc) {
+            WG_TRY(make_tmap_2d_bf16(&tmQ, m.qp, (uint64_t)Mq, D, D, 16, 64));
+            WG_TRY(make_tmap_2d_bf16(&tmKV, m.kv[sc], (uint64_t)m.rows[sc], 4 * D, 4 * D, 128, 64));
+        }
         for (int l = 0; l < 2; ++l) {
             const wg_msqp_block& Bk = S.blocks[l];
             WG_TRY(wg_layernorm(m.q[sc], 0, D, Bk.qn_g, Bk.qn_b, 1e-5f, m.qn, D, Mq, D, s));
             WG_TRY(gemm_bf16_out(m.qn, D, Bk.w_q, Mq, D, D, Bk.b_q, WG_ACT_NONE, m.qp, D, s));
             {
                 Prof prof("msqp_attention", s, 4.0 * B * 8 * (double)S.nq * Nkv * 128, (double)B * Nkv * 2 * D * 2.0);
-            msqp_attention_kernel<<<dim3(B, 8), 256, smem, s>>>(m.qp, m.kv[sc], 4 * D, l * 2 * D, l * 2 * D + D, m.ao, S.nq, Nkv);
+            if (use_tc) {
+                const int nsplit = (Nkv + TC_MAX_NKV - 1) / TC_MAX_NKV;
+                msqp_attention_tc_kernel<<<B * 8 * nsplit, 192, TC_SMEM_BYTES, s>>>(tmQ, tmKV, l * 2 * D, l * 2 * D + D, m.ao, S.nq, Nkv, nsplit,
+                                                                                   nsplit > 1 ? m.part : nullptr);
+                if (nsplit > 1) msqp_merge_splits_kernel<<<B * 8, 128, 0, s>>>(m.part, m.ao, S.nq, nsplit);
+            } else {
+                WG_REQUIRE(smem <= 227 * 1024, "wg_msqp_forward: %d kv tokens x %d queries exceed shared memory", Nkv, S.nq);
+                msqp_attention_kernel<<<dim3(B, 8), 256, smem, s>>>(m.qp, m.kv[sc], 4 * D, l * 2 * D, l * 2 * D + D, m.ao, S.nq, Nkv);
+            }
             }
             WG_CHECK_CUDA(cudaGetLastError());
             WG_TRY(gemm_f32_out(m.ao, D, Bk.w_o, Mq, D, D, Bk.b_o, WG_ACT_NONE, m.q[sc], D, m.q[sc], s));
