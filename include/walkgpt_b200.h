@@ -164,6 +164,13 @@ WG_API int wg_clip_forward_ex(const wg_clip_weights* w, const void* pixels, int 
                        int n_run, int mid_index, void* out_last, void* out_mid, int out_is_bf16, int keep_cls, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* LayerNorm fused into the GEMM that produces its input (CTA-pair kernel, fp32 residual epilogue): mode 0 = separate LayerNorm
+ * kernels (default; the faster choice under this pool's power cap), 1 = every fc2 GEMM also emits layer_norm1 of
+ * the NEXT encoder layer, 2 = and every out-proj GEMM emits layer_norm2.  The tiles of a 1024-wide row block exchange their row
+ * statistics through global memory inside the persistent kernel.  Returns the previous mode; mode < 0 only queries.  The initial
+ * mode is the environment variable WG_CLIP_FUSE_LN (unset = 0).  Process-wide. */
+WG_API int wg_clip_set_fuse_ln(int mode);
+
 /* A2 -- Multi-Scale Query Projector.  Replaces MultiScaleQFormerProjector.forward (utils/utils_walkgpt.py:259-300). */
 typedef struct wg_msqp_block {                 /* one CrossAttnBlock (utils_walkgpt.py:163-185) */
     const float* qn_g; const float* qn_b;      /* q_norm */

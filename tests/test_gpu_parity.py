@@ -280,6 +280,37 @@ def test_clip_tower_against_reference_golden():
         assert rel_err(lastm[:, 40::41, ::13], g["hs_masked_sub"][idx][:, 1:]) < 1e-2
 
 
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_clip_tower_fused_residual_layernorm_epilogue(mode):
+    """wg_clip_set_fuse_ln: the fc2 (mode 1) and out-proj (mode 2) GEMMs emit the following LayerNorm from their fp32-residual epilogue
+    (row statistics exchanged between the four 256-column tiles of a row block inside the persistent kernel).  Checked against the
+    reference golden (3 layers, masked and unmasked), against the separate-LayerNorm path, and for batch invariance: an image's rows are
+    the same bits alone (20 tiles, below one wave) and inside a batch of 3 whose row blocks straddle image boundaries."""
+    g = load("clip_3layer")
+    sd = specs.make_state_dict(M.clip_param_spec(layers=g["layers"]), seed=g["seed"])
+    px = rnd((2, 3, 448, 448), g["px_seed"])
+    a = M._ClipArgs()
+    a.mm_vision_select_layer = -1
+    tower = load_into(M.CLIPVisionTower(None, a, layers=g["layers"]), sd)
+    lib = _lib.lib()
+    base, _ = tower(px.to(DEV))
+    prev = lib.wg_clip_set_fuse_ln(mode)
+    try:
+        assert lib.wg_clip_set_fuse_ln(-1) == mode
+        last, _ = tower(px.to(DEV))
+        assert rel_err(last[:, 40::41, ::13], g["hs_sub"][3][:, 1:]) < 1e-2
+        assert rel_err(last, base) < 2e-3                       # same arithmetic up to the rounding of the row statistics
+        lastm, _ = tower(px.to(DEV), attention_mask=g["key_valid"].to(DEV))
+        assert rel_err(lastm[:, 40::41, ::13], g["hs_masked_sub"][3][:, 1:]) < 1e-2
+        px3 = torch.cat([px, rnd((1, 3, 448, 448), 99)])
+        batch, _ = tower(px3.to(DEV))
+        solo, _ = tower(px3[2:].to(DEV))
+        assert torch.equal(batch[:2], last) and torch.equal(batch[2:], solo)
+    finally:
+        lib.wg_clip_set_fuse_ln(prev)
+
+
 def test_clip_tower_24_layers_against_oracle():
     tower = M.CLIPVisionTower(layers=24, seed=3).to(DEV)
     px = rnd((2, 3, 448, 448), 7)

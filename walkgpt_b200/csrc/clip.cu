@@ -1,6 +1,7 @@
 // A1: CLIP ViT-L/14@448 tower forward = a fixed sequence of the kernels in gemm.cu / attention.cu / rowwise.cu.
 // Residual stream in fp32 (LayerNorm statistics, residual adds); GEMM operands and attention in bf16.
 #include "internal.h"
+#include <atomic>
 
 namespace wg {
 namespace {
@@ -13,6 +14,9 @@ struct ClipBuffers {
     void* qkv;       // bf16 [B*T, 3D]
     void* attn;      // bf16 [B*T, D]
     void* h1;        // bf16 [B*T, mlp]
+    float* ln_stats;     // fused residual + LayerNorm epilogue (gemm2.cu, WG_OUT_F32_LN): per-tile row statistics
+    unsigned* ln_flags;  // and the tiles' "published" flags (zeroed at the start of every forward)
+    size_t ln_flag_bytes;
 };
 
 bool carve(Workspace& ws, const wg_clip_weights* w, int B, ClipBuffers& b) {
@@ -24,11 +28,26 @@ bool carve(Workspace& ws, const wg_clip_weights* w, int B, ClipBuffers& b) {
     b.qkv = ws.take((size_t)B * T * 3 * D * 2);
     b.attn = ws.take((size_t)B * T * D * 2);
     b.h1 = ws.take((size_t)B * T * w->mlp * 2);
-    return b.patches && b.patch_emb && b.x && b.ln && b.qkv && b.attn && b.h1;
+    const size_t row_blocks = 2 * (((size_t)B * T + 255) / 256), nt = D / 256;  // both CTAs of the last pair tile publish, valid rows or not
+    b.ln_stats = static_cast<float*>(ws.take(row_blocks * nt * 128 * 2 * sizeof(float)));
+    b.ln_flag_bytes = row_blocks * nt * sizeof(unsigned);
+    b.ln_flags = static_cast<unsigned*>(ws.take(b.ln_flag_bytes));
+    return b.patches && b.patch_emb && b.x && b.ln && b.qkv && b.attn && b.h1 && b.ln_stats && b.ln_flags;
+}
+
+std::atomic<int>& fuse_ln_mode() {
+    static std::atomic<int> mode([] { const char* e = getenv("WG_CLIP_FUSE_LN"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : v > 2 ? 2 : v; }());
+    return mode;
 }
 
 }  // namespace
 }  // namespace wg
+
+extern "C" int wg_clip_set_fuse_ln(int mode) {
+    std::atomic<int>& m = wg::fuse_ln_mode();
+    if (mode < 0) return m.load();
+    return m.exchange(mode > 2 ? 2 : mode);
+}
 
 extern "C" size_t wg_clip_workspace_bytes(const wg_clip_weights* w, int B) {
     using namespace wg;
@@ -76,15 +95,35 @@ extern "C" int wg_clip_forward_ex(const wg_clip_weights* w, const void* pixels, 
     WG_TRY(launch_embed_ln(b.patch_emb, w->cls_emb, w->pos_emb, w->pre_ln_g, w->pre_ln_b, 1e-5f, b.x, B, T, D, s));
     if (out_mid && mid_index == 0) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s, keep_cls));
 
+    // LayerNorm fused into the epilogue of the GEMM that produces its input (WG_CLIP_FUSE_LN: 0 = separate LayerNorm kernels, 1 = the
+    // fc2 GEMM also emits ln1 of the NEXT layer, 2 = and the out-proj GEMM emits ln2); needs a full wave of pair tiles
+    const int fuse = gemm_pair_ln_eligible(M, D) ? fuse_ln_mode().load(std::memory_order_relaxed) : 0;
+    unsigned epoch = 0;
+    if (fuse) WG_CHECK_CUDA(cudaMemsetAsync(b.ln_flags, 0, b.ln_flag_bytes, s));
+    auto gemm_resid_ln = [&](const void* A, long long lda, const void* W, int K, const float* bias, const float* g, const float* be) -> int {
+        wg_gemm_args a = {};
+        a.A = A; a.lda = lda; a.W = W; a.ldw = K; a.M = M; a.N = D; a.K = K;
+        a.bias = bias; a.bias_period = 1; a.act = WG_ACT_NONE; a.out_mode = WG_OUT_F32; a.out = b.x; a.ldo = D; a.resid = b.x;
+        GemmLnFuse f = {b.ln, g, be, 1e-5f, b.ln_stats, b.ln_flags, ++epoch};
+        return launch_gemm_pair_ln(&a, &f, s);
+    };
     for (int i = 0; i < n_run; ++i) {
         const wg_clip_layer& ly = w->layers[i];
-        WG_TRY(wg_layernorm(b.x, 0, D, ly.ln1_g, ly.ln1_b, 1e-5f, b.ln, D, M, D, s));
+        if (i == 0 || fuse < 1) WG_TRY(wg_layernorm(b.x, 0, D, ly.ln1_g, ly.ln1_b, 1e-5f, b.ln, D, M, D, s));
         WG_TRY(gemm_bf16_out(b.ln, D, ly.w_qkv, M, 3 * D, D, ly.b_qkv, WG_ACT_NONE, b.qkv, 3 * D, s));
         WG_TRY(wg_attention_d64(b.qkv, b.attn, key_valid, B, T, w->heads, scale, s));
-        WG_TRY(gemm_f32_out(b.attn, D, ly.w_o, M, D, D, ly.b_o, WG_ACT_NONE, b.x, D, b.x, s));
-        WG_TRY(wg_layernorm(b.x, 0, D, ly.ln2_g, ly.ln2_b, 1e-5f, b.ln, D, M, D, s));
+        if (fuse >= 2) {
+            WG_TRY(gemm_resid_ln(b.attn, D, ly.w_o, D, ly.b_o, ly.ln2_g, ly.ln2_b));
+        } else {
+            WG_TRY(gemm_f32_out(b.attn, D, ly.w_o, M, D, D, ly.b_o, WG_ACT_NONE, b.x, D, b.x, s));
+            WG_TRY(wg_layernorm(b.x, 0, D, ly.ln2_g, ly.ln2_b, 1e-5f, b.ln, D, M, D, s));
+        }
         WG_TRY(gemm_bf16_out(b.ln, D, ly.w_fc1, M, w->mlp, D, ly.b_fc1, WG_ACT_QUICK_GELU, b.h1, w->mlp, s));
-        WG_TRY(gemm_f32_out(b.h1, w->mlp, ly.w_fc2, M, D, w->mlp, ly.b_fc2, WG_ACT_NONE, b.x, D, b.x, s));
+        if (fuse >= 1 && i + 1 < n_run) {
+            WG_TRY(gemm_resid_ln(b.h1, w->mlp, ly.w_fc2, w->mlp, ly.b_fc2, w->layers[i + 1].ln1_g, w->layers[i + 1].ln1_b));
+        } else {
+            WG_TRY(gemm_f32_out(b.h1, w->mlp, ly.w_fc2, M, D, w->mlp, ly.b_fc2, WG_ACT_NONE, b.x, D, b.x, s));
+        }
         if (out_mid && mid_index == i + 1) WG_TRY(launch_drop_cls_cast(b.x, out_mid, out_is_bf16, B, T, D, s, keep_cls));
     }
     WG_TRY(launch_drop_cls_cast(b.x, out_last, out_is_bf16, B, T, D, s, keep_cls));

@@ -15,6 +15,7 @@
 //   tmem_empty[a] (L, 2)   : one arrival per CTA, forwarded by its warp 3 once the CTA's 8 epilogue warps arrived on epi_done[a] (local):
 //                            the remote arrive costs ~1100-1800 cycles, which the epilogue warps used to pay once per tile
 #include "gemm_common.cuh"
+#include "internal.h"
 
 namespace wg {
 
@@ -52,6 +53,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using L = SmemLayout2<STAGES>;
+    constexpr bool F32_EPI = EPI == WG_OUT_F32 || EPI == WG_OUT_F32_LN;
     constexpr int TMEM_COLS = 2 * BN2;
     constexpr uint32_t IDESC = umma_idesc_bf16(2 * BM, BN2, false, false);
     constexpr uint32_t STAGE_TX_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
@@ -78,7 +80,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if (EPI != WG_OUT_F32) tma_prefetch_desc(&tmC);
+        if (!F32_EPI) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -193,15 +195,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
 
-            epilogue_tile<BN2, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid);
+            LnRowStats ln;
+            epilogue_tile<BN2, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid, &ln);
             tc_fence_before();
             __syncwarp();
 #ifdef GEMM2_TRACE
             if (tre) TRE(iter, 5);
 #endif
             if (lane == 0) mbar_arrive(&epi_done[acc]);
+            // fused LayerNorm: the accumulator is already back with the MMA warp; the wait for the row block's other tiles and the
+            // normalising pass run beside the next tile's main loop
+            if constexpr (EPI == WG_OUT_F32_LN) ln_pass2<BN2>(p, m0, n0, q, grp, lane, epi_tid, ln);
         }
-        if (EPI != WG_OUT_F32 && epi_tid == 0) tma_store_wait_all<0>();
+        if (!F32_EPI && epi_tid == 0) tma_store_wait_all<0>();
     } else if (warp == 3 && lane == 0) {
         // ===================== forwards "accumulator drained" to the leader's MMA warp =====================
         int iter = 0;
@@ -222,12 +228,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <int STAGES, int EPI>
-int launch2(const wg_gemm_args* a, cudaStream_t stream) {
+int launch2(const wg_gemm_args* a, cudaStream_t stream, const GemmLnFuse* fuse = nullptr) {
     using L = SmemLayout2<STAGES>;
+    constexpr bool F32_EPI = EPI == WG_OUT_F32 || EPI == WG_OUT_F32_LN;
     CUtensorMap tmA, tmB, tmC;
     WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->a_k_wrap > 0 ? a->a_k_wrap : a->K, a->lda, BM, BK));
     WG_TRY(make_tmap_2d_bf16(&tmB, a->W, a->N, a->K, a->ldw, 128, BK));
-    if (EPI != WG_OUT_F32) {
+    if (!F32_EPI) {
         WG_TRY(make_tmap_2d_bf16(&tmC, a->out, a->M, a->split_out ? 2 * a->N : a->N, a->ldo, BM, 64));
     } else {
         tmC = tmA;
@@ -242,22 +249,35 @@ int launch2(const wg_gemm_args* a, cudaStream_t stream) {
     p.bias = a->bias;
     p.bias_period = a->bias_period;
     p.act = a->act;
-    p.out_f32 = (EPI == WG_OUT_F32) ? static_cast<float*>(a->out) : nullptr;
-    p.resid_f32 = (EPI == WG_OUT_F32) ? static_cast<const float*>(a->resid) : nullptr;
+    p.out_f32 = F32_EPI ? static_cast<float*>(a->out) : nullptr;
+    p.resid_f32 = F32_EPI ? static_cast<const float*>(a->resid) : nullptr;
     p.resid_bf16 = (EPI == WG_OUT_BF16_LN) ? static_cast<const __nv_bfloat16*>(a->resid) : nullptr;
     p.ldo = a->ldo;
     p.ln_gamma = a->ln_gamma;
     p.ln_beta = a->ln_beta;
     p.ln_eps = a->ln_eps;
     p.a_k_wrap = a->a_k_wrap;
-    p.split_out = (EPI != WG_OUT_F32) ? a->split_out : 0;
+    p.split_out = !F32_EPI ? a->split_out : 0;
+    p.ln_out = nullptr; p.ln_stats = nullptr; p.ln_flags = nullptr; p.ln_epoch = 0;
+    if (EPI == WG_OUT_F32_LN) {
+        p.ln_out = static_cast<__nv_bfloat16*>(fuse->ln_out);
+        p.ln_stats = fuse->stats;
+        p.ln_flags = fuse->flags;
+        p.ln_epoch = fuse->epoch;
+        p.ln_gamma = fuse->gamma;
+        p.ln_beta = fuse->beta;
+        p.ln_eps = fuse->eps;
+    }
 
     auto kern = gemm2_bf16_kernel<STAGES, EPI>;
     WG_SMEM_OPT_IN(kern, L::DYN_BYTES);  // per instantiation and device
-    const int max_pairs = device_sm_count() / 2;
+    int max_pairs = device_sm_count() / 2;
+    // fused LayerNorm: the n-tiles of a row block must run in the SAME wave (a tile that waits for the next wave's tiles stalls its
+    // pair's epilogue for a whole main loop, and the delay spreads through the groups): a multiple of the n-tile count of pairs
+    if (EPI == WG_OUT_F32_LN) max_pairs = (max_pairs / p.num_n_tiles) * p.num_n_tiles;
     const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
-    static const char* kname = EPI == WG_OUT_BF16 ? "gemm2_bf16" : EPI == WG_OUT_F32 ? "gemm2_f32" : "gemm2_bf16ln";
-    const double out_bytes = (double)a->M * a->N * (EPI == WG_OUT_F32 ? (a->resid ? 8.0 : 4.0) : (a->resid ? 4.0 : 2.0));
+    static const char* kname = EPI == WG_OUT_BF16 ? "gemm2_bf16" : EPI == WG_OUT_F32 ? "gemm2_f32" : EPI == WG_OUT_F32_LN ? "gemm2_f32_ln" : "gemm2_bf16ln";
+    const double out_bytes = (double)a->M * a->N * (F32_EPI ? (a->resid ? 8.0 : 4.0) + (EPI == WG_OUT_F32_LN ? 2.0 : 0.0) : (a->resid ? 4.0 : 2.0));
     // ALGORITHMIC flops: a split-bf16 operand ([hi | lo | hi] against [W_hi | W_hi | W_lo], K = 2C or 3C executed) stands for ONE
     // fp32-accurate product over C = a_k_wrap / 2 columns
     const double k_alg = a->a_k_wrap > 0 ? 0.5 * a->a_k_wrap : (double)a->K;
@@ -268,6 +288,20 @@ int launch2(const wg_gemm_args* a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// fp32 output + fp32 residual (in place) + bf16 LayerNorm of the result over the full row, N % 256 == 0 with 2..8 n-tiles.  The n-tiles
+// of a row block wait for each other inside the kernel, which is safe because the grid is persistent (every pair resident) and pairs
+// take tiles in increasing order with at least as many pairs as n-tiles (no cyclic wait; see ln_pass2).  Used at every M (also below
+// one wave of tiles) so that a row's arithmetic does not depend on the batch it is computed in.
+int launch_gemm_pair_ln(const wg_gemm_args* a, const GemmLnFuse* f, cudaStream_t stream) {
+    const int nt = a->N / BN2;
+    if (a->out_mode != WG_OUT_F32 || a->N % BN2 != 0 || nt < 2 || nt > 8 || device_sm_count() / 2 < 2 * nt ||
+        !f || !f->ln_out || !f->stats || !f->flags || f->epoch == 0 || !f->gamma || !f->beta || a->conv_grid != 0) {
+        set_error("launch_gemm_pair_ln: unsupported problem (M=%d N=%d)", a->M, a->N);
+        return WG_ERR_INVALID;
+    }
+    return launch2<6, WG_OUT_F32_LN>(a, stream, f);
+}
 
 // Used by wg_gemm for N % 256 == 0 problems with at least one full wave of 256 x 256 tiles.
 int launch_gemm_pair(const wg_gemm_args* a, cudaStream_t stream) {

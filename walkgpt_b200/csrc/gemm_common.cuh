@@ -34,7 +34,25 @@ struct GemmParams {
     int conv_g, conv_c;  // implicit 3x3 convolution over a channels-last g x g map with conv_c channels per term (conv_g = 0: off)
     int a_k_wrap;   // A's k coordinate wraps at this many columns (0 = off): A' = [hi | lo | hi] of a split-bf16 operand
     int split_out;  // bf16 outputs are written as split-bf16: hi at column c, lo = bf16(x - hi) at column N + c
+    // WG_OUT_F32_LN (pair kernel only): the fp32 output row block is ALSO emitted as bf16 LayerNorm_N(out) * gamma + beta.  A row
+    // spans N / 256 tiles that different CTA pairs compute at the same time: every CTA publishes its rows' (sum, sum of squares) over
+    // its 256 columns in ln_stats, raises ln_flags[row block][n tile] to ln_epoch, and waits for the other tiles of its row block.
+    __nv_bfloat16* ln_out;   // bf16 [M, N], ld = N
+    float* ln_stats;         // [2 * ceil(M / 256)][N / 256][128][2]
+    unsigned* ln_flags;      // [2 * ceil(M / 256)][N / 256], zeroed before the first launch of a sequence
+    unsigned ln_epoch;       // unique (> 0) per launch since the flags were zeroed
 };
+
+constexpr int WG_OUT_F32_LN = 16;  // internal out mode: WG_OUT_F32 + residual + fused LayerNorm over the full row (launch_gemm_pair_ln)
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -118,13 +136,24 @@ __device__ __forceinline__ void stage_bf16_32(uint8_t* cbuf, int r, int half, co
 
 // Epilogue of one 128 x BN accumulator tile held in this CTA's TMEM at `taddr` (lane quarter q already applied).
 // Called by all 8 epilogue warps (grp = 0/1 take alternate column chunks); m0/n0 = global origin of this CTA's tile.
+// WG_OUT_F32_LN: per-thread row statistics handed from the tile's first pass (epilogue_tile) to ln_pass2 -- a thread of the transposed
+// store layout touches rows q*32 + it*4 + (lane >> 3), it = 0..7, of its warp's 32 rows
+struct LnRowStats {
+    float s1[8], s2[8];
+};
+
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtensorMap& tmC, uint8_t* cbufs, uint32_t taddr, int m0, int n0, int q,
-                                              int grp, int lane, int epi_tid) {
+                                              int grp, int lane, int epi_tid, LnRowStats* ln = nullptr) {
     const int r = q * 32 + lane;
     const int row = m0 + r;
     const bool row_ok = row < p.M;
-    if constexpr (EPI == WG_OUT_F32) {
+    if constexpr (EPI == WG_OUT_F32 || EPI == WG_OUT_F32_LN) {
+        constexpr bool FUSE_LN = EPI == WG_OUT_F32_LN;
+        if constexpr (FUSE_LN) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) ln->s1[it] = ln->s2[it] = 0.f;
+        }
         // fp32 output (+ fp32 residual, in place on the ViT residual stream).  Each thread owns one accumulator row, which
         // would make global accesses 16 B per thread at a 4 KB stride; instead every warp transposes its 32x32 chunk
         // through a padded smem tile so that each quarter-warp touches one full 128-byte line (coalesced LDG/STG.128).
@@ -177,11 +206,52 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
                 if (grow < p.M && gcol < p.N) {
                     if (p.resid_f32) { o[it].x += rsd[it].x; o[it].y += rsd[it].y; o[it].z += rsd[it].z; o[it].w += rsd[it].w; }
                     *reinterpret_cast<float4*>(p.out_f32 + (size_t)grow * p.ldo + gcol) = o[it];
+                    if constexpr (FUSE_LN) {
+                        ln->s1[it] += (o[it].x + o[it].y) + (o[it].z + o[it].w);
+                        ln->s2[it] = fmaf(o[it].x, o[it].x, fmaf(o[it].y, o[it].y, fmaf(o[it].z, o[it].z, fmaf(o[it].w, o[it].w, ln->s2[it]))));
+                    }
                 }
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) rsd[it] = nxt[it];
             __syncwarp();
+        }
+        if constexpr (FUSE_LN) {
+            // (sum, sum of squares) of this CTA's 256 columns per row: reduce over the 8 lanes that share a row, add the other column
+            // group's half through the (now idle) staging tiles, publish for the other n-tiles of the row block
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+                    ln->s1[it] += __shfl_xor_sync(0xffffffffu, ln->s1[it], d);
+                    ln->s2[it] += __shfl_xor_sync(0xffffffffu, ln->s2[it], d);
+                }
+            }
+            float2* mine = reinterpret_cast<float2*>(stg);                                                               // [32 rows]
+            const float2* other = reinterpret_cast<const float2*>(reinterpret_cast<float*>(cbufs) + ((grp ^ 1) * 4 + q) * (32 * 32));
+            if (cj == 0) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) mine[it * 4 + rr0] = make_float2(ln->s1[it], ln->s2[it]);
+            }
+            named_bar_sync(3, 2 * EPI_GROUP_THREADS);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const float2 o2 = other[it * 4 + rr0];
+                ln->s1[it] += o2.x;
+                ln->s2[it] += o2.y;
+            }
+            const int nt = p.num_n_tiles;
+            const size_t slot = (size_t)(m0 >> 7) * nt + (n0 / BN);
+            if (grp == 0 && cj == 0) {
+                float2* dst = reinterpret_cast<float2*>(p.ln_stats) + slot * 128 + q * 32;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) dst[it * 4 + rr0] = make_float2(ln->s1[it], ln->s2[it]);
+            }
+            named_bar_sync(3, 2 * EPI_GROUP_THREADS);  // every staging read and every statistics store of this CTA is done
+            if (epi_tid == 0 && grp == 0) {
+                __threadfence();
+                st_release_gpu(p.ln_flags + slot, p.ln_epoch);
+            }
         }
     } else {
         float mean = 0.f, rstd = 1.f;
@@ -279,6 +349,63 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
             if (epi_tid == 0) {
                 tma_store_2d(&tmC, cbuf, part * p.N + colc, m0);
                 tma_store_commit();
+            }
+        }
+    }
+}
+
+// WG_OUT_F32_LN, second pass of a tile (after its accumulator has been handed back to the MMA warp): wait for the other n-tiles of
+// the row block, complete the row statistics, re-read this CTA's fp32 output tile (just written: L2) in the coalesced store layout,
+// normalise, write bf16.  All 8 epilogue warps call it.
+template <int BN>
+__device__ __forceinline__ void ln_pass2(const GemmParams& p, int m0, int n0, int q, int grp, int lane, int epi_tid, LnRowStats& ln) {
+    const int rr0 = lane >> 3, cj = lane & 7, cc = cj * 4;
+    const int nt = p.num_n_tiles;
+    const int my_n = n0 / BN;
+    const size_t slot0 = (size_t)(m0 >> 7) * nt;
+    if (epi_tid == 0 && grp == 0) {
+        for (int t = 0; t < nt; ++t) {
+            if (t == my_n) continue;
+            while (ld_acquire_gpu(p.ln_flags + slot0 + t) != p.ln_epoch) __nanosleep(64);
+        }
+    }
+    named_bar_sync(3, 2 * EPI_GROUP_THREADS);
+    float a[8], b[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        float s1 = 0.f, s2 = 0.f;  // summed in n-tile order by every tile of the row block: all of them normalise with the same bits
+        for (int t = 0; t < nt; ++t) {
+            float2 v = make_float2(ln.s1[it], ln.s2[it]);
+            if (t != my_n) v = __ldcg(reinterpret_cast<const float2*>(p.ln_stats) + (slot0 + t) * 128 + q * 32 + it * 4 + rr0);
+            s1 += v.x;
+            s2 += v.y;
+        }
+        const float inv_n = 1.0f / (float)p.N;
+        const float mean = s1 * inv_n;
+        const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+        a[it] = rsqrtf(var + p.ln_eps);
+        b[it] = -mean * a[it];
+    }
+#pragma unroll 1
+    for (int c = grp; c < BN / 32; c += 2) {
+        const int gcol = n0 + c * 32 + cc;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + gcol));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + gcol));
+        float4 x[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int grow = m0 + q * 32 + it * 4 + rr0;
+            x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < p.M) x[it] = __ldcg(reinterpret_cast<const float4*>(p.out_f32 + (size_t)grow * p.ldo + gcol));
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int grow = m0 + q * 32 + it * 4 + rr0;
+            if (grow < p.M) {
+                uint2 u;
+                u.x = pack_bf16x2(fmaf(fmaf(x[it].x, a[it], b[it]), ga.x, be.x), fmaf(fmaf(x[it].y, a[it], b[it]), ga.y, be.y));
+                u.y = pack_bf16x2(fmaf(fmaf(x[it].z, a[it], b[it]), ga.z, be.z), fmaf(fmaf(x[it].w, a[it], b[it]), ga.w, be.w));
+                *reinterpret_cast<uint2*>(p.ln_out + (size_t)grow * p.N + gcol) = u;
             }
         }
     }

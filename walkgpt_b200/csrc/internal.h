@@ -40,4 +40,21 @@ inline int gemm_f32_out(const void* A, long long lda, const void* W, int M, int 
     return wg_gemm(&a, s);
 }
 
+// Fused "fp32 residual add + LayerNorm over the full row" epilogue of the CTA-pair GEMM (gemm2.cu, WG_OUT_F32_LN): the fp32 result
+// (out, in place on the residual stream) is also emitted as bf16 LayerNorm(out) * gamma + beta.
+struct GemmLnFuse {
+    void* ln_out;        // bf16 [M, N], ld = N
+    const float* gamma;
+    const float* beta;
+    float eps;
+    float* stats;        // scratch [2 * ceil(M / 256)][N / 256][128][2] floats (both CTAs of every pair tile publish)
+    unsigned* flags;     // scratch [2 * ceil(M / 256)][N / 256], zeroed (stream-ordered) before the first launch that uses them
+    unsigned epoch;      // > 0, unique per launch since the flags were zeroed
+};
+int launch_gemm_pair_ln(const wg_gemm_args* a, const GemmLnFuse* f, cudaStream_t stream);
+inline bool gemm_pair_ln_eligible(int M, int N) {
+    const int nt = N / 256, pairs = device_sm_count() / 2;
+    return M > 0 && N % 256 == 0 && nt >= 2 && nt <= 8 && pairs >= 2 * nt;
+}
+
 }  // namespace wg
