@@ -335,6 +335,13 @@ WG_API int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, const
                                          const int32_t* prompt_img, int P, int multimask_output, const float* prev_masks, int n_prev,
                                          float* low_res_out, float* iou_out, float* depth_pool_out, void* workspace,
                                          size_t workspace_bytes, void* stream);
+/* The same with the number of images behind img_emb_tokens_bf16 (prompt_img values are < n_images): layer 0 of the two-way transformer
+ * sees identical keys for all prompts of an image, so its image-side projections are then computed once per image instead of once per
+ * prompt (n_images <= 0, or previous-level masks: computed per prompt as wg_mask_decoder_forward_level does).  Same results. */
+WG_API int wg_mask_decoder_forward_images(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, int n_images, const float* txt_emb,
+                                   const int32_t* prompt_img, int P, int multimask_output, const float* prev_masks, int n_prev,
+                                   float* low_res_out, float* iou_out, float* depth_pool_out, void* workspace,
+                                   size_t workspace_bytes, void* stream);
 
 /* A6 -- PromptEncoder.get_dense_pe / PositionEmbeddingRandom.forward (prompt_encoder.py:67-76, 216-229).
  * gauss fp32 [2, F]; out_chw fp32 [2F, h, w] (reference layout, nullable); out_tokens fp32 [h*w, 2F] (nullable). */

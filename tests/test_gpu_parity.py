@@ -781,7 +781,7 @@ def test_llm_hidden_states_feed_the_path():
         hidden = llm(inputs_embeds=torch.cat([emb[:, :IMG_SLOT], vis256, emb[:, IMG_SLOT + 1:]], 1), use_cache=False).last_hidden_state.contiguous()
     assert hidden.shape == (B, Lin + 255, H)
     rows, counts, row_off, img_off = ops.seg_gather(hidden, ids, SEG, offset=list(range(B + 1)), shift=255, max_out=5)
-    ref_rows, ref_offs = path_a.gather_seg_rows(hidden.cpu(), ids.cpu(), SEG, list(range(B + 1)), shift=255)
+    ref_rows, _, ref_offs = path_a.gather_seg_rows(hidden.cpu(), ids.cpu(), SEG, list(range(B + 1)), shift=255)
     assert img_off.tolist() == [0, 3, 5] == [int(v) for v in ref_offs] and torch.equal(rows.cpu(), ref_rows)
     out = m.ground(enc["img_emb_split"], rows, img_off)      # device offsets: wg_prompt_index
     ref = path_a.path_a_forward(_oracle_weights(m), px.float(), ref_rows, [0, 3, 5])

@@ -254,13 +254,14 @@ constexpr int T2I_ROWS = NT * 8;               // (token, head) score rows
 constexpr int T2I_LD = T2I_CHUNK + 4;          // padded row, still 16-byte aligned: the P V pass reads four keys per LDS.128
 __global__ void __launch_bounds__(T2I_THREADS) t2i_partial_kernel(const float* __restrict__ Qt, const float* __restrict__ kvall, int ldkv, int k_off,
                                                                    int v_off, int hw, float* __restrict__ Pm, float* __restrict__ Pl,
-                                                                   float* __restrict__ Po) {
+                                                                   float* __restrict__ Po, const int* __restrict__ kv_img) {
     __shared__ __align__(16) float qs[NT * CI];
     __shared__ __align__(16) float sc[T2I_ROWS * T2I_LD];
     const int chunk = blockIdx.x, nchunk = gridDim.x, p = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k0 = chunk * T2I_CHUNK;
-    const float* kv = kvall + ((size_t)p * hw + k0) * ldkv;
+    // kv_img != null (layer 0): the projections exist once per image, kv rows of prompt p are those of image kv_img[p]
+    const float* kv = kvall + ((size_t)(kv_img != nullptr ? kv_img[p] : p) * hw + k0) * ldkv;
     for (int i = tid; i < NT * CI; i += T2I_THREADS) qs[i] = Qt[(size_t)p * NT * CI + i];
     __syncthreads();
     {   // scores: thread = (key, group of 4 heads): 256 contiguous bytes of the key's K row
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(256) expand_keys_kernel(const __nv_bfloat16* _
         const int c8 = (int)(i % (C / 8));
         const long long row = i / (C / 8);
         const int p = (int)(row / hw), pos = (int)(row % hw);
-        const int img = prompt_img[p];
+        const int img = prompt_img != nullptr ? prompt_img[p] : p;  // null: one key set per IMAGE (layer-0 projections shared by its prompts)
         const __nv_bfloat16* src = emb + ((size_t)img * hw + pos) * (2 * C) + c8 * 8;
         float gate = 1.0f;
         if (prev_masks != nullptr) {
@@ -617,7 +618,8 @@ __global__ void __launch_bounds__(256) up2x_ln_gelu_kernel(const float* __restri
 
 // image -> token attention, one thread per image position (6 keys, 8 heads x 16): q fp32 in, out split-bf16 [P*hw][2*128]
 __global__ void __launch_bounds__(256) i2t_attention_kernel(const float* __restrict__ kvq, int ldkv, int q_off, const float* __restrict__ KT,
-                                                            const float* __restrict__ VT, __nv_bfloat16* __restrict__ out, int hw) {
+                                                            const float* __restrict__ VT, __nv_bfloat16* __restrict__ out, int hw,
+                                                            const int* __restrict__ kv_img) {
     __shared__ float kt[NT * CI], vt[NT * CI];
     const int p = blockIdx.y;
     for (int i = threadIdx.x; i < NT * CI; i += 256) {
@@ -628,7 +630,8 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(const float* __restr
     const int pos = blockIdx.x * 256 + threadIdx.x;
     if (pos >= hw) return;
     const size_t row = (size_t)p * hw + pos;
-    const float4* qr = reinterpret_cast<const float4*>(kvq + row * ldkv + q_off);
+    const size_t qrow = (size_t)(kv_img != nullptr ? kv_img[p] : p) * hw + pos;  // layer 0: image-side queries shared by the image's prompts
+    const float4* qr = reinterpret_cast<const float4*>(kvq + qrow * ldkv + q_off);
     __nv_bfloat16* orow = out + row * (2 * CI);
 #pragma unroll 1
     for (int h = 0; h < 8; ++h) {
@@ -906,6 +909,14 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
                                              const int32_t* prompt_img, int P, int multimask_output, const float* prev_masks, int n_prev,
                                              float* low_res_out, float* iou_out, float* depth_pool_out, void* workspace, size_t workspace_bytes,
                                              void* stream_) {
+    return wg_mask_decoder_forward_images(w, img_emb_tokens_bf16, 0, txt_emb, prompt_img, P, multimask_output, prev_masks, n_prev, low_res_out, iou_out,
+                                          depth_pool_out, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int wg_mask_decoder_forward_images(const wg_mask_decoder_weights* w, const void* img_emb_tokens_bf16, int n_images, const float* txt_emb,
+                                              const int32_t* prompt_img, int P, int multimask_output, const float* prev_masks, int n_prev,
+                                              float* low_res_out, float* iou_out, float* depth_pool_out, void* workspace, size_t workspace_bytes,
+                                              void* stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     WG_REQUIRE(prev_masks == nullptr || n_prev > 0, "wg_mask_decoder_forward_level: previous masks need n_prev > 0");
     WG_REQUIRE(w != nullptr, "wg_mask_decoder_forward: null weights");
@@ -954,6 +965,11 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     static const bool t2i_split_enabled = [] { const char* e = getenv("WG_DEC_T2I_SPLIT"); return e == nullptr || atoi(e) != 0; }();
     const int t2i_chunks = (hw + T2I_CHUNK - 1) / T2I_CHUNK;
     const bool split_t2i = t2i_split_enabled && P <= 65535;
+    // Layer 0 of the two-way transformer sees the SAME keys for every prompt of an image (the keys only become prompt-specific after
+    // the first image->token attention, transformer.py:151-242): its image-side projections [K_t2i | V_t2i | Q_i2t] are computed once
+    // per image and indexed through prompt_img by the attention kernels.  Needs the image count (n_images > 0), no previous-level gate.
+    static const bool share_enabled = [] { const char* e = getenv("WG_DEC_SHARE_L0"); return e == nullptr || atoi(e) != 0; }();
+    const bool share0 = share_enabled && n_images > 0 && n_images < P && prev_masks == nullptr && split_t2i;
 
     TokArgs ta = {};
     ta.hw = hw;
@@ -989,9 +1005,18 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
     __nv_bfloat16* keys_next = d.keysB;
     for (int l = 0; l < 2; ++l) {
         const wg_twoway_layer& L = w->layers[l];
+        const bool shared = share0 && l == 0 && L.mlp_w1_split != nullptr && L.mlp_w2_split != nullptr;  // (the all-in-one token kernel indexes kv per prompt)
+        const int32_t* kv_img = shared ? prompt_img : nullptr;
+        if (shared) {  // the images' own key sets (embedding + no-mask term) in the not yet used second key buffer
+            long long blk = ((long long)n_images * hw * (C / 8) + 255) / 256;
+            if (blk > 148 * 32) blk = 148 * 32;
+            Prof prof("dec_expand_keys", s, 0.0, (double)n_images * hw * C * 8.0);
+            expand_keys_kernel<<<(unsigned)blk, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(img_emb_tokens_bf16), nullptr, w->no_mask, keys_next, n_images, hw,
+                                                         nullptr, 0);
+        }
         {   // [K_t2i | V_t2i | Q_i2t] with the positional term as a per-position bias table
             wg_gemm_args a = {};
-            a.A = keys; a.lda = 2 * C; a.W = L.w_img; a.ldw = T * C; a.M = (int)rows; a.N = 384; a.K = T * C;
+            a.A = shared ? keys_next : keys; a.lda = 2 * C; a.W = L.w_img; a.ldw = T * C; a.M = shared ? n_images * hw : (int)rows; a.N = 384; a.K = T * C;
             a.a_k_wrap = T == 3 ? 2 * C : 0;
             a.bias = L.b_img; a.bias_period = hw; a.out_mode = WG_OUT_F32; a.out = d.kvq; a.ldo = 384;
             WG_TRY(wg_gemm(&a, s));
@@ -1009,7 +1034,7 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
                 }
                 {
                     Prof prof("dec_t2i_attention", s, (double)P * 2.0 * 2.0 * NT * CI * hw, (double)P * hw * 1024.0);
-                    t2i_partial_kernel<<<dim3(t2i_chunks, P), T2I_THREADS, 0, s>>>(d.Qt, d.kvq, 384, 0, CI, hw, d.Pm, d.Pl, d.Po);
+                    t2i_partial_kernel<<<dim3(t2i_chunks, P), T2I_THREADS, 0, s>>>(d.Qt, d.kvq, 384, 0, CI, hw, d.Pm, d.Pl, d.Po, kv_img);
                 }
                 ta.part = 4;
                 {
@@ -1047,7 +1072,7 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
         WG_DBG_STEP();
         {
             Prof prof("dec_i2t_attention", s, (double)rows * 8 * 6 * 16 * 4.0, (double)rows * 512.0);
-            i2t_attention_kernel<<<dim3((hw + 255) / 256, P), 256, 0, s>>>(d.kvq, 384, 256, d.KT, d.VT, d.a2, hw);
+            i2t_attention_kernel<<<dim3((hw + 255) / 256, P), 256, 0, s>>>(d.kvq, 384, 256, d.KT, d.VT, d.a2, hw, kv_img);
         }
         WG_CHECK_CUDA(cudaGetLastError());
         WG_DBG_STEP();
@@ -1078,7 +1103,7 @@ extern "C" int wg_mask_decoder_forward_level(const wg_mask_decoder_weights* w, c
         }
         {
             Prof prof("dec_t2i_attention", s, (double)P * 2.0 * 2.0 * NT * CI * hw, (double)P * hw * 1024.0);
-            t2i_partial_kernel<<<dim3(t2i_chunks, P), T2I_THREADS, 0, s>>>(d.Qt, d.kvq, 256, 0, CI, hw, d.Pm, d.Pl, d.Po);
+            t2i_partial_kernel<<<dim3(t2i_chunks, P), T2I_THREADS, 0, s>>>(d.Qt, d.kvq, 256, 0, CI, hw, d.Pm, d.Pl, d.Po, nullptr);
         }
         ta.part = 4;
         {

@@ -847,10 +847,12 @@ class MaskDecoderMultiScale(_SpecModule):
             assert prev_masks.dtype == torch.float32 and prev_masks.is_contiguous() and prev_masks.shape[0] == P
             assert tuple(prev_masks.shape[-2:]) == (w.grid_h, w.grid_w), "previous masks must have this level's grid size"
             n_prev = prev_masks.shape[1]
-        _lib.check(_lib.lib().wg_mask_decoder_forward_level(C.byref(w), emb_tokens_bf16.data_ptr(), txt_emb_f32.data_ptr(), prompt_img_i32.data_ptr(), P,
-                                                            int(multimask_output), None if prev_masks is None else prev_masks.data_ptr(), n_prev,
-                                                            low.data_ptr(), iou.data_ptr(), None if pool is None else pool.data_ptr(),
-                                                            ws.data_ptr(), ws.numel(), _stream()), "wg_mask_decoder_forward_level")
+        n_images = emb_tokens_bf16.numel() // (hw * emb_tokens_bf16.shape[-1])  # layer-0 projections are shared by an image's prompts
+        _lib.check(_lib.lib().wg_mask_decoder_forward_images(C.byref(w), emb_tokens_bf16.data_ptr(), n_images, txt_emb_f32.data_ptr(),
+                                                             prompt_img_i32.data_ptr(), P, int(multimask_output),
+                                                             None if prev_masks is None else prev_masks.data_ptr(), n_prev,
+                                                             low.data_ptr(), iou.data_ptr(), None if pool is None else pool.data_ptr(),
+                                                             ws.data_ptr(), ws.numel(), _stream()), "wg_mask_decoder_forward_images")
         return low, iou, pool
 
     def upsample_embedding(self, emb_tokens_bf16: torch.Tensor, grid: Tuple[int, int]) -> torch.Tensor:
