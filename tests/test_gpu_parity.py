@@ -330,6 +330,18 @@ def test_msqp_against_reference_golden(tag):
     assert y.shape == g["y"].shape and rel_err(y, g["y"]) < 1.5e-2
 
 
+@pytest.mark.parametrize("grid,sam_dim,B", [(4, 256, 3), (12, 256, 2), (36, 256, 2), (64, 256, 1)])
+def test_msqp_tensor_core_cross_attention_at_other_grid_sizes(grid, sam_dim, B):
+    """The tcgen05 cross-attention kernel against the oracle where the key counts are awkward: grid 4 (16 / 4 / 1 / 1 keys: every scale is
+    one masked block), 12 (144 / 36 / 9 keys), 36 (1296 keys = a full split of 1024 + a split of 272 with a masked tail block; 324;
+    81) and 64 (4096 keys = four full splits; 1024; 256)."""
+    m = M.MultiScaleQFormerProjector(sam_dim, 512, pad_to_square=True, target_square_side=6).to(DEV)
+    x = rnd((B, grid * grid, sam_dim), 17 + grid).to(DEV).bfloat16()
+    y = m(x)
+    ref = path_a.msqp_forward(sd_cpu(m), x.float().cpu(), target_square_side=6)
+    assert y.shape == ref.shape == (B, 36, 512) and rel_err(y, ref) < 1.5e-2
+
+
 def test_msqp_rejects_non_square_token_count():
     m = M.MultiScaleQFormerProjector(256, 64).to(DEV)
     with pytest.raises(ValueError, match="perfect square"):
@@ -407,6 +419,25 @@ def test_prompt_encoder_and_mask_decoder_against_reference_golden(grid):
     assert (m1.cpu() - g["masks1"]).abs().max().item() <= LOGIT_TOL / 4
     with pytest.raises(NotImplementedError):  # level 1 needs image_feature_scale_num = 2
         dec(emb, pe, sparse, dense, False, 1, previous_masks=m1)
+
+
+def test_mask_decoder_shared_layer0_projections_equal_per_prompt_ones():
+    """wg_mask_decoder_forward_images: with fewer images than prompts, layer 0 of the two-way transformer projects every IMAGE's keys once
+    and the attention kernels reach them through prompt_img.  The same (image, text) pairs run with one private copy of the image
+    per prompt (n_images == P: nothing is shared) must give the same bits -- 3 images with 3 / 0 / 2 prompts."""
+    g = load("decoder_ms_g32")
+    pe_m = load_into(M.PromptEncoder(256, (32, 32), (448, 448), 16), specs.make_state_dict(specs.prompt_encoder_spec(256, 16), seed=g["seed_prompt"]))
+    dec = load_into(M.MaskDecoderMultiScale(), specs.make_state_dict(specs.mask_decoder_multiscale_spec(), seed=g["seed_dec"]))
+    pe = pe_m.get_dense_pe()
+    sparse, dense = pe_m(None, None, None, rnd((5, 1, 256), 41).to(DEV))
+    dec(rnd(g["emb_shape"], g["emb_seed"]).to(DEV), pe, sparse[:1], dense[:1], False, 0)      # packs + binds the prompt constants (grid 32)
+    emb = M.to_split(rnd((3, 1024, 256), 42).to(DEV))
+    txt = sparse.reshape(5, 256).float().contiguous()
+    pimg = torch.tensor([0, 0, 0, 2, 2], dtype=torch.int32, device=DEV)
+    low_s, iou_s, pool_s = dec.run(emb, txt, pimg, True, want_depth_pool=False)
+    low_p, iou_p, _ = dec.run(emb[pimg.long()].contiguous(), txt, torch.arange(5, dtype=torch.int32, device=DEV), True)
+    assert torch.equal(low_s, low_p) and torch.equal(iou_s, iou_p)
+    assert low_s.shape == (5, 4, 64, 64) and bool(torch.isfinite(low_s).all())
 
 
 def test_mask_decoder_token_mlp_gemm_path_matches_in_kernel_path():
