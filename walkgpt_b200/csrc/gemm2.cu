@@ -37,23 +37,94 @@ __device__ long long g_gemm2_epi[16][8];  // per tile of pair 5: MMA warp {0 wai
 #define TRE(i, slot) do { } while (0)
 #endif
 
-template <int STAGES>
+constexpr int F32_WARP_BUF_BYTES = 32 * 32 * 4;  // WG_OUT_F32_TMA: one [32 rows x 32 columns] fp32 box, 128-byte rows under the 128B swizzle
+
+template <int STAGES, int EPI = WG_OUT_BF16>
 struct SmemLayout2 {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
     static constexpr int OFF_C = OFF_B + STAGES * B_HALF_BYTES;
-    static constexpr int OFF_BAR = OFF_C + 2 * C_BUF_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 6;
+    // WG_OUT_F32_TMA: two boxes (ping-pong) for each of the 8 epilogue warps, and one mbarrier per box for the residual loads
+    static constexpr int C_BYTES = EPI == WG_OUT_F32_TMA ? 8 * 2 * F32_WARP_BUF_BYTES : 2 * C_BUF_BYTES;
+    static constexpr int OFF_BAR = OFF_C + C_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 6 + (EPI == WG_OUT_F32_TMA ? 16 : 0);
     static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
 };
 
+// fp32 epilogue (+ fp32 residual, possibly in place) without per-thread global accesses.  A warp owns 32 rows x 32-column chunks of its
+// CTA's accumulator tile (the two epilogue groups take alternate chunks): the chunk's residual box is fetched by TMA into one of the
+// warp's two shared-memory boxes one chunk AHEAD (across tile boundaries too), the row-owning thread adds its accumulator row (+ bias,
+// activation) in place with conflict-free 16-byte accesses (TMA's 128-byte swizzle = the XOR pattern the row owners use), and the box
+// leaves as a TMA store; rows past M are zero-filled on the way in and clipped on the way out.  The round-1 epilogue transposed every
+// chunk through shared memory to reach coalesced LDG / STG.128 and was the critical path of the K = 1024 out-proj GEMM (16 000 cycles per
+// tile against a 10 000-cycle main loop).  `cc` = chunks this warp has processed (box = cc & 1, barrier phase = (cc >> 1) & 1).
+struct F32TmaNext {
+    int m0, n0;   // the CTA's next tile (prefetch of its first residual box), valid if ok
+    bool ok;
+};
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_f32_tma(const GemmParams& p, const CUtensorMap& tmC, const CUtensorMap& tmR, uint8_t* wbuf, uint64_t* rbar,
+                                                      uint32_t& cc, uint32_t taddr, int m0, int n0, int q, int grp, int lane, const F32TmaNext& nx) {
+    const int row = m0 + q * 32 + lane;
+    const int wrow0 = m0 + q * 32;
+    const bool has_res = p.resid_f32 != nullptr;
+    constexpr int NCH = BN / 64;  // chunks per group
+#pragma unroll 1
+    for (int i = 0; i < NCH; ++i) {
+        const int c = grp + 2 * i;
+        const uint32_t b = cc & 1;
+        uint32_t v[32];
+        float f[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        add_bias32(v, f, p, row, n0 + c * 32);
+        if (p.act != WG_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        uint8_t* box = wbuf + b * F32_WARP_BUF_BYTES;
+        if (has_res) {
+            // the following chunk's residual box (next chunk of this tile, or the first one of the CTA's next tile) into the other box,
+            // whose last store (chunk cc - 1) has had the whole TMEM load + bias phase to finish reading it
+            const bool more = i + 1 < NCH;
+            if (lane == 0 && (more || nx.ok)) {
+                tma_store_wait_read<0>();
+                mbar_arrive_expect_tx(&rbar[b ^ 1], F32_WARP_BUF_BYTES);
+                if (more) tma_load_2d(wbuf + (b ^ 1) * F32_WARP_BUF_BYTES, &tmR, &rbar[b ^ 1], n0 + (c + 2) * 32, wrow0);
+                else tma_load_2d(wbuf + (b ^ 1) * F32_WARP_BUF_BYTES, &tmR, &rbar[b ^ 1], nx.n0 + grp * 32, nx.m0 + q * 32);
+            }
+            mbar_wait(&rbar[b], (cc >> 1) & 1);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                float4* slot = reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4));
+                float4 r4 = *slot;
+                r4.x += f[g * 4]; r4.y += f[g * 4 + 1]; r4.z += f[g * 4 + 2]; r4.w += f[g * 4 + 3];
+                *slot = r4;
+            }
+        } else {
+            if (lane == 0) tma_store_wait_read<1>();  // the store of chunk cc - 2 (this box) has read it
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(&tmC, box, n0 + c * 32, wrow0);
+            tma_store_commit();
+        }
+        ++cc;
+    }
+}
+
 template <int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-    using L = SmemLayout2<STAGES>;
-    constexpr bool F32_EPI = EPI == WG_OUT_F32 || EPI == WG_OUT_F32_LN;
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+    using L = SmemLayout2<STAGES, EPI>;
+    constexpr bool F32_EPI = EPI == WG_OUT_F32 || EPI == WG_OUT_F32_LN;  // per-thread global stores (no TMA store to drain)
     constexpr int TMEM_COLS = 2 * BN2;
     constexpr uint32_t IDESC = umma_idesc_bf16(2 * BM, BN2, false, false);
     constexpr uint32_t STAGE_TX_BYTES = A_STAGE_BYTES + B_HALF_BYTES;  // per CTA
@@ -66,6 +137,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint64_t* epi_done = bars + 2 * STAGES + 4;  // [2] local: this CTA's 8 epilogue warps have drained accumulator a
+    uint64_t* resid_bar = bars + 2 * STAGES + 6;  // WG_OUT_F32_TMA: [8 warps][2 boxes] residual box has landed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
@@ -81,6 +153,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (!F32_EPI) tma_prefetch_desc(&tmC);
+        if (EPI == WG_OUT_F32_TMA) tma_prefetch_desc(&tmR);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -91,6 +164,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 2);   // one (forwarded) arrival per CTA of the pair
             mbar_init(&epi_done[a], 8);     // one arrival per epilogue warp of this CTA
+        }
+        if (EPI == WG_OUT_F32_TMA) {
+            for (int i = 0; i < 16; ++i) mbar_init(&resid_bar[i], 1);
         }
         fence_mbar_init();
     }
@@ -179,6 +255,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int epi_tid = threadIdx.x - (4 + 4 * grp) * 32;  // index inside the group
         uint8_t* cbufs = smem + L::OFF_C;
         int iter = 0;
+        // WG_OUT_F32_TMA: this warp's two boxes, their barriers, its chunk counter; the first residual box of the first tile is requested here
+        uint8_t* wbuf = cbufs + (grp * 4 + q) * (2 * F32_WARP_BUF_BYTES);
+        uint64_t* rbar = resid_bar + (grp * 4 + q) * 2;
+        uint32_t cc = 0;
+        if (EPI == WG_OUT_F32_TMA && p.resid_f32 != nullptr && pair < p.num_tiles && lane == 0) {
+            mbar_arrive_expect_tx(&rbar[0], F32_WARP_BUF_BYTES);
+            tma_load_2d(wbuf, &tmR, &rbar[0], (pair % p.num_n_tiles) * BN2 + grp * 32, (pair / p.num_n_tiles) * (2 * BM) + rank * BM + q * 32);
+        }
         for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
@@ -196,7 +280,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
 
             LnRowStats ln;
-            epilogue_tile<BN2, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid, &ln);
+            if constexpr (EPI == WG_OUT_F32_TMA) {
+                const int nt_ = tile + num_pairs;
+                const F32TmaNext nx = {(nt_ / p.num_n_tiles) * (2 * BM) + (int)rank * BM, (nt_ % p.num_n_tiles) * BN2, nt_ < p.num_tiles};
+                epilogue_tile_f32_tma<BN2>(p, tmC, tmR, wbuf, rbar, cc, taddr, m0, n0, q, grp, lane, nx);
+            } else {
+                epilogue_tile<BN2, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid, &ln);
+            }
             tc_fence_before();
             __syncwarp();
 #ifdef GEMM2_TRACE
@@ -207,7 +297,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // normalising pass run beside the next tile's main loop
             if constexpr (EPI == WG_OUT_F32_LN) ln_pass2<BN2>(p, m0, n0, q, grp, lane, epi_tid, ln);
         }
-        if (!F32_EPI && epi_tid == 0) tma_store_wait_all<0>();
+        if (!F32_EPI && EPI != WG_OUT_F32_TMA && epi_tid == 0) tma_store_wait_all<0>();
+        if (EPI == WG_OUT_F32_TMA && lane == 0) tma_store_wait_all<0>();  // every warp's elected lane drains its own stores
     } else if (warp == 3 && lane == 0) {
         // ===================== forwards "accumulator drained" to the leader's MMA warp =====================
         int iter = 0;
@@ -229,15 +320,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <int STAGES, int EPI>
 int launch2(const wg_gemm_args* a, cudaStream_t stream, const GemmLnFuse* fuse = nullptr) {
-    using L = SmemLayout2<STAGES>;
-    constexpr bool F32_EPI = EPI == WG_OUT_F32 || EPI == WG_OUT_F32_LN;
-    CUtensorMap tmA, tmB, tmC;
+    using L = SmemLayout2<STAGES, EPI>;
+    constexpr bool F32_EPI = EPI == WG_OUT_F32 || EPI == WG_OUT_F32_LN || EPI == WG_OUT_F32_TMA;
+    CUtensorMap tmA, tmB, tmC, tmR;
     WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->a_k_wrap > 0 ? a->a_k_wrap : a->K, a->lda, BM, BK));
     WG_TRY(make_tmap_2d_bf16(&tmB, a->W, a->N, a->K, a->ldw, 128, BK));
     if (!F32_EPI) {
         WG_TRY(make_tmap_2d_bf16(&tmC, a->out, a->M, a->split_out ? 2 * a->N : a->N, a->ldo, BM, 64));
     } else {
         tmC = tmA;
+    }
+    tmR = tmA;
+    if (EPI == WG_OUT_F32_TMA) {  // fp32 [M, N] as boxes of 32 rows x 32 columns (128-byte rows, 128B swizzle)
+        uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+        uint64_t strides[1] = {(uint64_t)a->ldo * 4};
+        uint32_t box[2] = {32, 32};
+        WG_TRY(make_tensor_map(&tmC, a->out, 4, 2, dims, strides, box));
+        if (a->resid) WG_TRY(make_tensor_map(&tmR, a->resid, 4, 2, dims, strides, box));
     }
     GemmParams p;
     p.M = a->M;
@@ -276,13 +375,13 @@ int launch2(const wg_gemm_args* a, cudaStream_t stream, const GemmLnFuse* fuse =
     // pair's epilogue for a whole main loop, and the delay spreads through the groups): a multiple of the n-tile count of pairs
     if (EPI == WG_OUT_F32_LN) max_pairs = (max_pairs / p.num_n_tiles) * p.num_n_tiles;
     const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
-    static const char* kname = EPI == WG_OUT_BF16 ? "gemm2_bf16" : EPI == WG_OUT_F32 ? "gemm2_f32" : EPI == WG_OUT_F32_LN ? "gemm2_f32_ln" : "gemm2_bf16ln";
+    static const char* kname = EPI == WG_OUT_BF16 ? "gemm2_bf16" : (EPI == WG_OUT_F32 || EPI == WG_OUT_F32_TMA) ? "gemm2_f32" : EPI == WG_OUT_F32_LN ? "gemm2_f32_ln" : "gemm2_bf16ln";
     const double out_bytes = (double)a->M * a->N * (F32_EPI ? (a->resid ? 8.0 : 4.0) + (EPI == WG_OUT_F32_LN ? 2.0 : 0.0) : (a->resid ? 4.0 : 2.0));
     // ALGORITHMIC flops: a split-bf16 operand ([hi | lo | hi] against [W_hi | W_hi | W_lo], K = 2C or 3C executed) stands for ONE
     // fp32-accurate product over C = a_k_wrap / 2 columns
     const double k_alg = a->a_k_wrap > 0 ? 0.5 * a->a_k_wrap : (double)a->K;
     Prof prof(kname, stream, 2.0 * a->M * a->N * k_alg, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
-    kern<<<2 * pairs, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, p);
+    kern<<<2 * pairs, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -307,7 +406,14 @@ int launch_gemm_pair_ln(const wg_gemm_args* a, const GemmLnFuse* f, cudaStream_t
 int launch_gemm_pair(const wg_gemm_args* a, cudaStream_t stream) {
     switch (a->out_mode) {
         case WG_OUT_BF16: return launch2<6, WG_OUT_BF16>(a, stream);
-        case WG_OUT_F32: return launch2<6, WG_OUT_F32>(a, stream);
+        case WG_OUT_F32: {
+            // TMA epilogue (5 stages + 64 KB of output boxes) unless WG_GEMM_F32_TMA=0 or the row pitch is not a multiple of 16 bytes
+            static const bool tma_epi = [] { const char* e = getenv("WG_GEMM_F32_TMA"); return e == nullptr || atoi(e) != 0; }();
+            // short K only: there the epilogue is the critical path (K = 1024 out-proj 0.175 -> 0.143 ms); the K = 4096 fc2 GEMM hides its
+            // epilogue behind the main loop and prefers the sixth operand stage (0.386 vs 0.408 ms)
+            const bool ok = tma_epi && a->K <= 2048 && a->ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0;
+            return ok ? launch2<5, WG_OUT_F32_TMA>(a, stream) : launch2<6, WG_OUT_F32>(a, stream);
+        }
         default: set_error("launch_gemm_pair: unsupported out_mode %d", a->out_mode); return WG_ERR_INVALID;
     }
 }

@@ -43,6 +43,8 @@ struct GemmParams {
     unsigned ln_epoch;       // unique (> 0) per launch since the flags were zeroed
 };
 
+constexpr int WG_OUT_F32_TMA = 17;  // internal out mode of the pair kernel: WG_OUT_F32 whose residual tiles arrive and whose output tiles leave as TMA
+                                    // bulk transfers through per-warp shared-memory buffers (epilogue_tile_f32_tma in gemm2.cu)
 constexpr int WG_OUT_F32_LN = 16;  // internal out mode: WG_OUT_F32 + residual + fused LayerNorm over the full row (launch_gemm_pair_ln)
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
