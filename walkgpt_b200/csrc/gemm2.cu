@@ -38,6 +38,8 @@ __device__ long long g_gemm2_epi[16][8];  // per tile of pair 5: MMA warp {0 wai
 #endif
 
 constexpr int F32_WARP_BUF_BYTES = 32 * 32 * 4;  // WG_OUT_F32_TMA: one [32 rows x 32 columns] fp32 box, 128-byte rows under the 128B swizzle
+constexpr int F32_NBOX = 2;                      // boxes per epilogue warp: residual boxes are requested F32_NBOX - 1 chunks ahead (3 boxes with 4
+                                                 // operand stages measured the same 0.143 ms on the out-proj GEMM: the depth is not the limit)
 
 template <int STAGES, int EPI = WG_OUT_BF16>
 struct SmemLayout2 {
@@ -45,9 +47,9 @@ struct SmemLayout2 {
     static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
     static constexpr int OFF_C = OFF_B + STAGES * B_HALF_BYTES;
     // WG_OUT_F32_TMA: two boxes (ping-pong) for each of the 8 epilogue warps, and one mbarrier per box for the residual loads
-    static constexpr int C_BYTES = EPI == WG_OUT_F32_TMA ? 8 * 2 * F32_WARP_BUF_BYTES : 2 * C_BUF_BYTES;
+    static constexpr int C_BYTES = EPI == WG_OUT_F32_TMA ? 8 * F32_NBOX * F32_WARP_BUF_BYTES : 2 * C_BUF_BYTES;
     static constexpr int OFF_BAR = OFF_C + C_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 6 + (EPI == WG_OUT_F32_TMA ? 16 : 0);
+    static constexpr int NUM_BARS = 2 * STAGES + 6 + (EPI == WG_OUT_F32_TMA ? 8 * F32_NBOX : 0);
     static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
 };
@@ -60,9 +62,29 @@ struct SmemLayout2 {
 // chunk through shared memory to reach coalesced LDG / STG.128 and was the critical path of the K = 1024 out-proj GEMM (16 000 cycles per
 // tile against a 10 000-cycle main loop).  `cc` = chunks this warp has processed (box = cc & 1, barrier phase = (cc >> 1) & 1).
 struct F32TmaNext {
-    int m0, n0;   // the CTA's next tile (prefetch of its first residual box), valid if ok
+    int m0, n0;   // the CTA's next tile (prefetch of its first residual boxes), valid if ok
     bool ok;
 };
+// box / barrier of the warp's chunk number x (running count over all tiles)
+__device__ __forceinline__ uint32_t f32_box(uint32_t x) { return x % F32_NBOX; }
+// request the residual box of the warp's chunk `i` of tile (m0, n0) -- or, past the tile's last chunk, of the next tile -- as chunk number x
+template <int BN>
+__device__ __forceinline__ void f32_tma_request(const CUtensorMap& tmR, uint8_t* wbuf, uint64_t* rbar, uint32_t x, int i, int m0, int n0, int q, int grp,
+                                                const F32TmaNext& nx) {
+    constexpr int NCH = BN / 64;
+    const uint32_t b = f32_box(x);
+    int col, rowc;
+    if (i < NCH) {
+        col = n0 + (grp + 2 * i) * 32;
+        rowc = m0 + q * 32;
+    } else {
+        if (!nx.ok) return;
+        col = nx.n0 + (grp + 2 * (i - NCH)) * 32;
+        rowc = nx.m0 + q * 32;
+    }
+    mbar_arrive_expect_tx(&rbar[b], F32_WARP_BUF_BYTES);
+    tma_load_2d(wbuf + b * F32_WARP_BUF_BYTES, &tmR, &rbar[b], col, rowc);
+}
 template <int BN>
 __device__ __forceinline__ void epilogue_tile_f32_tma(const GemmParams& p, const CUtensorMap& tmC, const CUtensorMap& tmR, uint8_t* wbuf, uint64_t* rbar,
                                                       uint32_t& cc, uint32_t taddr, int m0, int n0, int q, int grp, int lane, const F32TmaNext& nx) {
@@ -70,10 +92,11 @@ __device__ __forceinline__ void epilogue_tile_f32_tma(const GemmParams& p, const
     const int wrow0 = m0 + q * 32;
     const bool has_res = p.resid_f32 != nullptr;
     constexpr int NCH = BN / 64;  // chunks per group
+    static_assert(F32_NBOX - 1 <= NCH, "prefetch distance within one tile ahead");
 #pragma unroll 1
     for (int i = 0; i < NCH; ++i) {
         const int c = grp + 2 * i;
-        const uint32_t b = cc & 1;
+        const uint32_t b = f32_box(cc);
         uint32_t v[32];
         float f[32];
         tmem_ld_32x32b_x32(taddr + c * 32, v);
@@ -85,16 +108,13 @@ __device__ __forceinline__ void epilogue_tile_f32_tma(const GemmParams& p, const
         }
         uint8_t* box = wbuf + b * F32_WARP_BUF_BYTES;
         if (has_res) {
-            // the following chunk's residual box (next chunk of this tile, or the first one of the CTA's next tile) into the other box,
-            // whose last store (chunk cc - 1) has had the whole TMEM load + bias phase to finish reading it
-            const bool more = i + 1 < NCH;
-            if (lane == 0 && (more || nx.ok)) {
+            // the residual box F32_NBOX - 1 chunks ahead goes into the box whose store (chunk cc - 1) was issued last: it has had the
+            // whole TMEM load + bias phase to finish reading
+            if (lane == 0) {
                 tma_store_wait_read<0>();
-                mbar_arrive_expect_tx(&rbar[b ^ 1], F32_WARP_BUF_BYTES);
-                if (more) tma_load_2d(wbuf + (b ^ 1) * F32_WARP_BUF_BYTES, &tmR, &rbar[b ^ 1], n0 + (c + 2) * 32, wrow0);
-                else tma_load_2d(wbuf + (b ^ 1) * F32_WARP_BUF_BYTES, &tmR, &rbar[b ^ 1], nx.n0 + grp * 32, nx.m0 + q * 32);
+                f32_tma_request<BN>(tmR, wbuf, rbar, cc + F32_NBOX - 1, i + F32_NBOX - 1, m0, n0, q, grp, nx);
             }
-            mbar_wait(&rbar[b], (cc >> 1) & 1);
+            mbar_wait(&rbar[b], (cc / F32_NBOX) & 1);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 float4* slot = reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4));
@@ -103,7 +123,7 @@ __device__ __forceinline__ void epilogue_tile_f32_tma(const GemmParams& p, const
                 *slot = r4;
             }
         } else {
-            if (lane == 0) tma_store_wait_read<1>();  // the store of chunk cc - 2 (this box) has read it
+            if (lane == 0) tma_store_wait_read<F32_NBOX - 1>();  // the store of chunk cc - F32_NBOX (this box) has read it
             __syncwarp();
 #pragma unroll
             for (int g = 0; g < 8; ++g)
@@ -137,7 +157,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint64_t* epi_done = bars + 2 * STAGES + 4;  // [2] local: this CTA's 8 epilogue warps have drained accumulator a
-    uint64_t* resid_bar = bars + 2 * STAGES + 6;  // WG_OUT_F32_TMA: [8 warps][2 boxes] residual box has landed
+    uint64_t* resid_bar = bars + 2 * STAGES + 6;  // WG_OUT_F32_TMA: [8 warps][F32_NBOX boxes] residual box has landed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
@@ -166,7 +186,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&epi_done[a], 8);     // one arrival per epilogue warp of this CTA
         }
         if (EPI == WG_OUT_F32_TMA) {
-            for (int i = 0; i < 16; ++i) mbar_init(&resid_bar[i], 1);
+            for (int i = 0; i < 8 * F32_NBOX; ++i) mbar_init(&resid_bar[i], 1);
         }
         fence_mbar_init();
     }
@@ -256,12 +276,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint8_t* cbufs = smem + L::OFF_C;
         int iter = 0;
         // WG_OUT_F32_TMA: this warp's two boxes, their barriers, its chunk counter; the first residual box of the first tile is requested here
-        uint8_t* wbuf = cbufs + (grp * 4 + q) * (2 * F32_WARP_BUF_BYTES);
-        uint64_t* rbar = resid_bar + (grp * 4 + q) * 2;
+        uint8_t* wbuf = cbufs + (grp * 4 + q) * (F32_NBOX * F32_WARP_BUF_BYTES);
+        uint64_t* rbar = resid_bar + (grp * 4 + q) * F32_NBOX;
         uint32_t cc = 0;
         if (EPI == WG_OUT_F32_TMA && p.resid_f32 != nullptr && pair < p.num_tiles && lane == 0) {
-            mbar_arrive_expect_tx(&rbar[0], F32_WARP_BUF_BYTES);
-            tma_load_2d(wbuf, &tmR, &rbar[0], (pair % p.num_n_tiles) * BN2 + grp * 32, (pair / p.num_n_tiles) * (2 * BM) + rank * BM + q * 32);
+            const F32TmaNext none = {0, 0, false};
+            for (int i = 0; i < F32_NBOX - 1; ++i)
+                f32_tma_request<BN2>(tmR, wbuf, rbar, i, i, (pair / p.num_n_tiles) * (2 * BM) + (int)rank * BM, (pair % p.num_n_tiles) * BN2, q, grp, none);
         }
         for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++iter) {
             const int acc = iter & 1;
