@@ -19,8 +19,9 @@ using namespace gemm_detail;
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-    using L = SmemLayout<BN, STAGES>;
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+    using L = SmemLayout<BN, STAGES, EPI>;
+    static_assert(WG_OUT_F32_TMA == 17 && F32_NBOX == 2 && F32_WARP_BUF_BYTES == 4096, "SmemLayout's WG_OUT_F32_TMA sizes");
     constexpr int B_STAGE_BYTES = L::B_STAGE_BYTES;
     constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 256 or 512)
     constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, false, false);
@@ -32,6 +33,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint64_t* resid_bar = bars + 2 * STAGES + 4;  // WG_OUT_F32_TMA: [8 warps][F32_NBOX] residual box has landed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
     const int warp = threadIdx.x >> 5;
@@ -41,6 +43,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (EPI != WG_OUT_F32) tma_prefetch_desc(&tmC);
+        if (EPI == WG_OUT_F32_TMA) tma_prefetch_desc(&tmR);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -50,6 +53,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
+        }
+        if (EPI == WG_OUT_F32_TMA) {
+            for (int i = 0; i < 8 * F32_NBOX; ++i) mbar_init(&resid_bar[i], 1);
         }
         fence_mbar_init();
     }
@@ -127,6 +133,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int epi_tid = threadIdx.x - (4 + 4 * grp) * 32;  // index inside the group
         uint8_t* cbufs = smem + L::OFF_C;
         int iter = 0;
+        // WG_OUT_F32_TMA (epilogue_tile_f32_tma): this warp's boxes, their barriers, its chunk counter, the first residual request
+        uint8_t* wbuf = cbufs + (grp * 4 + q) * (F32_NBOX * F32_WARP_BUF_BYTES);
+        uint64_t* rbar = resid_bar + (grp * 4 + q) * F32_NBOX;
+        uint32_t cc = 0;
+        if (EPI == WG_OUT_F32_TMA && p.resid_f32 != nullptr && (int)blockIdx.x < p.num_tiles && lane == 0) {
+            const F32TmaNext none = {0, 0, false};
+            for (int i = 0; i < F32_NBOX - 1; ++i)
+                f32_tma_request<BN>(tmR, wbuf, rbar, i, i, ((int)blockIdx.x / p.num_n_tiles) * BM, ((int)blockIdx.x % p.num_n_tiles) * BN, q, grp, none);
+        }
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
@@ -136,12 +151,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-            epilogue_tile<BN, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid);
+            if constexpr (EPI == WG_OUT_F32_TMA) {
+                const int nt_ = tile + (int)gridDim.x;
+                const F32TmaNext nx = {(nt_ / p.num_n_tiles) * BM, (nt_ % p.num_n_tiles) * BN, nt_ < p.num_tiles};
+                epilogue_tile_f32_tma<BN>(p, tmC, tmR, wbuf, rbar, cc, taddr, m0, n0, q, grp, lane, nx);
+            } else {
+                epilogue_tile<BN, EPI>(p, tmC, cbufs, taddr, m0, n0, q, grp, lane, epi_tid);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (EPI != WG_OUT_F32 && epi_tid == 0) tma_store_wait_all<0>();
+        if (EPI != WG_OUT_F32 && EPI != WG_OUT_F32_TMA && epi_tid == 0) tma_store_wait_all<0>();
+        if (EPI == WG_OUT_F32_TMA && lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -154,8 +176,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, int STAGES, int EPI>
 int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
-    using L = SmemLayout<BN, STAGES>;
-    CUtensorMap tmA, tmB, tmC;
+    using L = SmemLayout<BN, STAGES, EPI>;
+    constexpr bool F32_ANY = EPI == WG_OUT_F32 || EPI == WG_OUT_F32_TMA;
+    CUtensorMap tmA, tmB, tmC, tmR;
     if (a->conv_grid > 0) {
         const uint64_t g = (uint64_t)a->conv_grid, terms = a->a_k_wrap > 0 ? 2 : (uint64_t)a->K / (9 * (uint64_t)a->conv_channels);
         uint64_t dims[4] = {terms * (uint64_t)a->conv_channels, g, g, (uint64_t)a->M / (g * g)};
@@ -166,10 +189,18 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
         WG_TRY(make_tmap_2d_bf16(&tmA, a->A, a->M, a->a_k_wrap > 0 ? a->a_k_wrap : a->K, a->lda, BM, BK));
     }
     WG_TRY(make_tmap_2d_bf16(&tmB, a->W, a->N, a->K, a->ldw, BN, BK));
-    if (EPI != WG_OUT_F32) {
+    if (!F32_ANY) {
         WG_TRY(make_tmap_2d_bf16(&tmC, a->out, a->M, a->split_out ? 2 * a->N : a->N, a->ldo, BM, 64));
     } else {
         tmC = tmA;
+    }
+    tmR = tmA;
+    if (EPI == WG_OUT_F32_TMA) {  // fp32 [M, N] as boxes of 32 rows x 32 columns (128-byte rows, 128B swizzle)
+        uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+        uint64_t strides[1] = {(uint64_t)a->ldo * 4};
+        uint32_t box[2] = {32, 32};
+        WG_TRY(make_tensor_map(&tmC, a->out, 4, 2, dims, strides, box));
+        if (a->resid) WG_TRY(make_tensor_map(&tmR, a->resid, 4, 2, dims, strides, box));
     }
     GemmParams p;
     p.M = a->M;
@@ -181,8 +212,8 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     p.bias = a->bias;
     p.bias_period = a->bias_period;
     p.act = a->act;
-    p.out_f32 = (EPI == WG_OUT_F32) ? static_cast<float*>(a->out) : nullptr;
-    p.resid_f32 = (EPI == WG_OUT_F32) ? static_cast<const float*>(a->resid) : nullptr;
+    p.out_f32 = F32_ANY ? static_cast<float*>(a->out) : nullptr;
+    p.resid_f32 = F32_ANY ? static_cast<const float*>(a->resid) : nullptr;
     p.resid_bf16 = (EPI == WG_OUT_BF16_LN) ? static_cast<const __nv_bfloat16*>(a->resid) : nullptr;
     p.ldo = a->ldo;
     p.ln_gamma = a->ln_gamma;
@@ -191,20 +222,21 @@ int launch_gemm(const wg_gemm_args* a, cudaStream_t stream) {
     p.a_k_wrap = a->a_k_wrap;
     p.conv_g = a->conv_grid;
     p.conv_c = a->conv_channels;
-    p.split_out = (EPI != WG_OUT_F32) ? a->split_out : 0;
+    p.split_out = !F32_ANY ? a->split_out : 0;
+    p.ln_out = nullptr; p.ln_stats = nullptr; p.ln_flags = nullptr; p.ln_epoch = 0;
 
     auto kern = gemm_bf16_kernel<BN, STAGES, EPI>;
     WG_SMEM_OPT_IN(kern, L::DYN_BYTES);  // per instantiation and device
     int sms = device_sm_count();
     int grid = p.num_tiles < sms ? p.num_tiles : sms;
     static const char* kname = EPI == WG_OUT_BF16 ? (BN == 256 ? "gemm_bf16_bn256" : "gemm_bf16_bn128")
-                               : EPI == WG_OUT_F32 ? (BN == 256 ? "gemm_f32_bn256" : "gemm_f32_bn128") : "gemm_bf16ln_bn256";
-    const double out_bytes = (double)a->M * a->N * (EPI == WG_OUT_F32 ? (a->resid ? 8.0 : 4.0) : (a->resid ? 4.0 : 2.0));
+                               : F32_ANY ? (BN == 256 ? "gemm_f32_bn256" : "gemm_f32_bn128") : "gemm_bf16ln_bn256";
+    const double out_bytes = (double)a->M * a->N * (F32_ANY ? (a->resid ? 8.0 : 4.0) : (a->resid ? 4.0 : 2.0));
     // ALGORITHMIC flops: a split-bf16 operand ([hi | lo | hi] against [W_hi | W_hi | W_lo], K = 2C or 3C executed) stands for ONE
     // fp32-accurate product over C = a_k_wrap / 2 columns
     const double k_alg = a->a_k_wrap > 0 ? 0.5 * a->a_k_wrap : (double)a->K;
     Prof prof(kname, stream, 2.0 * a->M * a->N * k_alg, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + out_bytes);
-    kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, p);
+    kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
     WG_CHECK_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -257,7 +289,11 @@ extern "C" int wg_gemm(const wg_gemm_args* a, void* stream_) {
         case WG_OUT_F32: {
             if (use_pair) return launch_gemm_pair(a, stream);
             bool use256 = (a->N % 256 == 0) && tiles256 >= device_sm_count();
-            return use256 ? launch_gemm<256, 4, WG_OUT_F32>(a, stream) : launch_gemm<128, 6, WG_OUT_F32>(a, stream);
+            if (use256) return launch_gemm<256, 4, WG_OUT_F32>(a, stream);
+            // 128-wide tiles: TMA epilogue (epilogue_tile_f32_tma) for short K, where the epilogue is the critical path
+            static const bool tma_epi = [] { const char* e = getenv("WG_GEMM_F32_TMA"); return e == nullptr || atoi(e) != 0; }();
+            if (tma_epi && a->K <= 2048 && a->N % 32 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0) return launch_gemm<128, 5, WG_OUT_F32_TMA>(a, stream);
+            return launch_gemm<128, 6, WG_OUT_F32>(a, stream);
         }
         case WG_OUT_BF16_LN:
             WG_REQUIRE(a->N == 256, "wg_gemm: WG_OUT_BF16_LN requires N == 256 (got %d)", a->N);

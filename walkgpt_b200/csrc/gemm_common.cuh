@@ -56,14 +56,15 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI = 0>
 struct SmemLayout {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
     static constexpr int OFF_C = OFF_B + STAGES * B_STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_C + 2 * C_BUF_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 4;
+    // WG_OUT_F32_TMA (= 17): F32_NBOX (= 2) boxes of 4 KB per epilogue warp + one mbarrier per box
+    static constexpr int OFF_BAR = OFF_C + (EPI == 17 ? 8 * 2 * 4096 : 2 * C_BUF_BYTES);
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + (EPI == 17 ? 16 : 0);
     static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
 };
@@ -410,6 +411,96 @@ __device__ __forceinline__ void ln_pass2(const GemmParams& p, int m0, int n0, in
                 *reinterpret_cast<uint2*>(p.ln_out + (size_t)grow * p.N + gcol) = u;
             }
         }
+    }
+}
+
+constexpr int F32_WARP_BUF_BYTES = 32 * 32 * 4;  // WG_OUT_F32_TMA: one [32 rows x 32 columns] fp32 box, 128-byte rows under the 128B swizzle
+constexpr int F32_NBOX = 2;                      // boxes per epilogue warp: residual boxes are requested F32_NBOX - 1 chunks ahead (3 boxes with 4
+                                                 // operand stages measured the same 0.143 ms on the out-proj GEMM: the depth is not the limit)
+
+
+// fp32 epilogue (+ fp32 residual, possibly in place) without per-thread global accesses.  A warp owns 32 rows x 32-column chunks of its
+// CTA's accumulator tile (the two epilogue groups take alternate chunks): the chunk's residual box is fetched by TMA into one of the
+// warp's two shared-memory boxes one chunk AHEAD (across tile boundaries too), the row-owning thread adds its accumulator row (+ bias,
+// activation) in place with conflict-free 16-byte accesses (TMA's 128-byte swizzle = the XOR pattern the row owners use), and the box
+// leaves as a TMA store; rows past M are zero-filled on the way in and clipped on the way out.  The round-1 epilogue transposed every
+// chunk through shared memory to reach coalesced LDG / STG.128 and was the critical path of the K = 1024 out-proj GEMM (16 000 cycles per
+// tile against a 10 000-cycle main loop).  `cc` = chunks this warp has processed (box = cc & 1, barrier phase = (cc >> 1) & 1).
+struct F32TmaNext {
+    int m0, n0;   // the CTA's next tile (prefetch of its first residual boxes), valid if ok
+    bool ok;
+};
+// box / barrier of the warp's chunk number x (running count over all tiles)
+__device__ __forceinline__ uint32_t f32_box(uint32_t x) { return x % F32_NBOX; }
+// request the residual box of the warp's chunk `i` of tile (m0, n0) -- or, past the tile's last chunk, of the next tile -- as chunk number x
+template <int BN>
+__device__ __forceinline__ void f32_tma_request(const CUtensorMap& tmR, uint8_t* wbuf, uint64_t* rbar, uint32_t x, int i, int m0, int n0, int q, int grp,
+                                                const F32TmaNext& nx) {
+    constexpr int NCH = BN / 64;
+    const uint32_t b = f32_box(x);
+    int col, rowc;
+    if (i < NCH) {
+        col = n0 + (grp + 2 * i) * 32;
+        rowc = m0 + q * 32;
+    } else {
+        if (!nx.ok) return;
+        col = nx.n0 + (grp + 2 * (i - NCH)) * 32;
+        rowc = nx.m0 + q * 32;
+    }
+    mbar_arrive_expect_tx(&rbar[b], F32_WARP_BUF_BYTES);
+    tma_load_2d(wbuf + b * F32_WARP_BUF_BYTES, &tmR, &rbar[b], col, rowc);
+}
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_f32_tma(const GemmParams& p, const CUtensorMap& tmC, const CUtensorMap& tmR, uint8_t* wbuf, uint64_t* rbar,
+                                                      uint32_t& cc, uint32_t taddr, int m0, int n0, int q, int grp, int lane, const F32TmaNext& nx) {
+    const int row = m0 + q * 32 + lane;
+    const int wrow0 = m0 + q * 32;
+    const bool has_res = p.resid_f32 != nullptr;
+    constexpr int NCH = BN / 64;  // chunks per group
+    static_assert(F32_NBOX - 1 <= NCH, "prefetch distance within one tile ahead");
+#pragma unroll 1
+    for (int i = 0; i < NCH; ++i) {
+        const int c = grp + 2 * i;
+        const uint32_t b = f32_box(cc);
+        uint32_t v[32];
+        float f[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        add_bias32(v, f, p, row, n0 + c * 32);
+        if (p.act != WG_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        uint8_t* box = wbuf + b * F32_WARP_BUF_BYTES;
+        if (has_res) {
+            // the residual box F32_NBOX - 1 chunks ahead goes into the box whose store (chunk cc - 1) was issued last: it has had the
+            // whole TMEM load + bias phase to finish reading
+            if (lane == 0) {
+                tma_store_wait_read<0>();
+                f32_tma_request<BN>(tmR, wbuf, rbar, cc + F32_NBOX - 1, i + F32_NBOX - 1, m0, n0, q, grp, nx);
+            }
+            mbar_wait(&rbar[b], (cc / F32_NBOX) & 1);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                float4* slot = reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4));
+                float4 r4 = *slot;
+                r4.x += f[g * 4]; r4.y += f[g * 4 + 1]; r4.z += f[g * 4 + 2]; r4.w += f[g * 4 + 3];
+                *slot = r4;
+            }
+        } else {
+            if (lane == 0) tma_store_wait_read<F32_NBOX - 1>();  // the store of chunk cc - F32_NBOX (this box) has read it
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(&tmC, box, n0 + c * 32, wrow0);
+            tma_store_commit();
+        }
+        ++cc;
     }
 }
 
