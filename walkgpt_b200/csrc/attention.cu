@@ -42,6 +42,8 @@ constexpr int OFF_XCH = OFF_KMASK + (ATT_MAX_T / 32) * 4;  // SPLIT = 2: row max
 constexpr int ATT_SMEM_BYTES = OFF_XCH + (4 + 2) * 128 * 4;
 constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr int ATT_SPLIT_DEFAULT = 1;
+constexpr int ATT_Q4_DEFAULT = 1;
+constexpr int ATT_Q4_POLY_DEFAULT = 0;  // the q4 kernel is no longer helped by polynomial exponentials (B200: 0 -> 0.399, 2 -> 0.399, 3 -> 0.411 ms)  // 1: attention_d64_q4_kernel (four CTAs per SM, 64-key blocks)
 constexpr int ATT_POLY_DEFAULT = 3;  // of every 8 exponentials, evaluated on the FMA pipe (B200: 0 -> 0.556 ms, 3 -> 0.545 ms)
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: the running scale is refreshed only when the row max grew by > 2^8
 
@@ -879,6 +881,313 @@ attention_d64_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Four CTAs per SM (round 2, fourth session).  The kernels above are bound by the per-key-block dependency chain
+// (S ready -> tcgen05.ld -> max -> exp -> P -> PV), not by a pipe: two co-resident CTAs give every scheduler two softmax warps,
+// and a lone CTA needs ~2800 cycles per 128-key block of which the MUFU unit is busy for < 1000.  This variant buys more
+// independent chains per scheduler instead of shortening one: 64-key blocks need only 64 fp32 S columns, P (bf16 pairs, 32
+// columns) is written IN PLACE over the S columns its thread has already pulled into registers, O takes 64 columns -> 128 TMEM
+// columns per CTA, 64 live S registers per softmax thread, 50 KB of shared memory -> FOUR CTAs per SM (four softmax warps per
+// scheduler).  Because P aliases S, the tensor pipe's in-order execution is the only ordering needed between PV_j and S_{j+1}
+// (issued back to back by the same thread), and one commit behind S_{j+1} tells the softmax threads both "S_{j+1} is there" and
+// "PV_j is done, O is quiescent": no s_free / p_free barriers.  The same warp issues the TMA loads: K stage s is free once S_j has
+// completed and V stage s once PV_j has -- both are implied by p_ready(j) / p_ready(j+1) -- so there are no empty barriers either,
+// and the CTA is 5 warps (160 threads, 102 registers per thread at four CTAs per SM).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int Q4_BKV = 64;
+constexpr int Q4_KV_BYTES = Q4_BKV * ATT_D * 2;  // 8 KB: a [64 x 64] bf16 tile
+constexpr int Q4_OFF_Q = 0;
+constexpr int Q4_OFF_K = Q4_OFF_Q + TILE_BYTES;        // 2 stages
+constexpr int Q4_OFF_V = Q4_OFF_K + 2 * Q4_KV_BYTES;   // 2 stages
+constexpr int Q4_OFF_BAR = Q4_OFF_V + 2 * Q4_KV_BYTES;
+constexpr int Q4_NUM_BARS = 8;
+constexpr int Q4_OFF_KMASK = Q4_OFF_BAR + Q4_NUM_BARS * 8 + 16;
+constexpr int Q4_SMEM_BYTES = Q4_OFF_KMASK + (ATT_MAX_T / 32) * 4;
+constexpr int Q4_TMEM_COLS = 128;  // S: [0,64) (P bf16 pairs over [0,32))  O: [64,128)
+constexpr int Q4_THREADS = 160;    // warp 0: TMA + MMA issue, warps 1..4: softmax (TMEM lane quarter = warp & 3)
+
+// One 64-key block for one query row: S row -> registers, online softmax with the lazily refreshed scale, P row (bf16 pairs) back
+// into the first columns of the S row.  PV_{j-1} has completed before S_j became visible, so O may be rescaled without a wait.
+template <int NCH, int POLY>
+__device__ __forceinline__ void softmax_block_q4(SoftmaxState& st, int j, const AttnParams& p, const uint32_t* kmask, uint32_t tS, uint32_t tO,
+                                                 uint64_t* p_ready) {
+    constexpr int NG = NCH * 4;  // groups of 8 columns
+    uint32_t sv2[NCH][32];
+#define sv(i) sv2[(i) >> 5][(i) & 31]
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv2[c]);
+    tmem_ld_wait();
+    if (kmask != nullptr) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint32_t word = kmask[j * (Q4_BKV / 32) + c];
+            if (word != 0xffffffffu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sv(c * 32 + i) = ((word >> i) & 1u) ? sv(c * 32 + i) : 0xff800000u;  // -inf
+            }
+        }
+    }
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < NCH * 32; i += 8) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(fmaxf(mx4[c], __uint_as_float(sv(i + 2 * c))), __uint_as_float(sv(i + 2 * c + 1)));
+    }
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    float alpha = 1.0f;
+    bool refresh = false;
+    if (j == 0) {
+        st.m_ref = (mx == -INFINITY) ? 0.f : mx;
+    } else if ((mx - st.m_ref) * p.scale_log2 > RESCALE_THRESHOLD) {
+        alpha = ex2_approx((st.m_ref - mx) * p.scale_log2);
+        st.m_ref = mx;
+        refresh = true;
+    }
+    if (j > 0 && __any_sync(0xffffffffu, refresh)) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {  // 16 columns at a time: the S row occupies 64 registers
+            uint32_t ov[16];
+            tmem_ld_32x32b_x16(tO + c * 16, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32b_x16(tO + c * 16, ov);
+        }
+    }
+    const float scale = p.scale_log2;
+    const float neg_m = -st.m_ref * scale;
+    const uint64_t SC2 = pk2(scale, scale), NM2 = pk2(neg_m, neg_m);
+    uint64_t rsA = pk2(0.f, 0.f), rsB = pk2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g <= NG; ++g) {
+        if (g < NG) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = g * 8 + k * 2;
+                float x0, x1, e0, e1;
+                upk2(ffma2(pk2(__uint_as_float(sv(i)), __uint_as_float(sv(i + 1))), SC2, NM2), x0, x1);
+                if (use_poly((g & 1) * 4 + k, POLY)) {
+                    exp2_poly2(x0, x1, e0, e1);
+                } else {
+                    e0 = ex2_approx(x0);
+                    e1 = ex2_approx(x1);
+                }
+                sv(i) = __float_as_uint(e0);
+                sv(i + 1) = __float_as_uint(e1);
+            }
+        }
+        if (g >= 1) {  // row sum + bf16 packing + TMEM store of the previous group, in the shadow of this group's exponentials
+            const int b = (g - 1) * 8;
+            rsA = fadd2(rsA, pk2(__uint_as_float(sv(b + 0)), __uint_as_float(sv(b + 1))));
+            rsB = fadd2(rsB, pk2(__uint_as_float(sv(b + 2)), __uint_as_float(sv(b + 3))));
+            rsA = fadd2(rsA, pk2(__uint_as_float(sv(b + 4)), __uint_as_float(sv(b + 5))));
+            rsB = fadd2(rsB, pk2(__uint_as_float(sv(b + 6)), __uint_as_float(sv(b + 7))));
+            const uint32_t w0 = pack_bf16x2(__uint_as_float(sv(b + 0)), __uint_as_float(sv(b + 1)));
+            const uint32_t w1 = pack_bf16x2(__uint_as_float(sv(b + 2)), __uint_as_float(sv(b + 3)));
+            const uint32_t w2 = pack_bf16x2(__uint_as_float(sv(b + 4)), __uint_as_float(sv(b + 5)));
+            const uint32_t w3 = pack_bf16x2(__uint_as_float(sv(b + 6)), __uint_as_float(sv(b + 7)));
+            tmem_st_32x32b_x4(tS + (g - 1) * 4, w0, w1, w2, w3);
+        }
+    }
+    float rs0, rs1;
+    upk2(fadd2(rsA, rsB), rs0, rs1);
+    st.l_run = st.l_run * alpha + (rs0 + rs1);
+    tmem_st_wait();  // P (and a rescaled O) are in tensor memory
+    tc_fence_before();
+    mbar_arrive(p_ready);
+#undef sv
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(Q4_THREADS, 4)
+attention_d64_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO,
+                        const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q4_OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;   // [2]
+    uint64_t* v_full = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;   // S_j visible (and PV_{j-1} complete); its last phase: the final O is complete
+    uint64_t* p_ready = bars + 6;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Q4_NUM_BARS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+    const int HD = p.heads * ATT_D;
+    const int nkb = p.num_kv_blocks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmKV);
+            tma_prefetch_desc(&tmO);
+            mbar_init(q_full, 1);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&k_full[s], 1);
+                mbar_init(&v_full[s], 1);
+            }
+            mbar_init(s_full, 1);
+            mbar_init(p_ready, 128);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<Q4_TMEM_COLS>(tmem_ptr_smem);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base;       // P over its first 32 columns
+    const uint32_t tmem_O = tmem_base + 64;
+
+    if (warp == 0) {
+        // ===================== TMA loads + MMA issue (warp-uniform protocol, one elected lane issues) =====================
+        constexpr uint32_t IDESC_S = umma_idesc_bf16(128, Q4_BKV, false, false);  // Q (K-major) x K (K-major)
+        constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 64, false, true);       // P (TMEM, K-major) x V (MN-major)
+        const uint32_t idesc_s_last = umma_idesc_bf16(128, p.n_last, false, false);
+        const int pv_steps_last = p.n_last / 16;
+        const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + Q4_OFF_Q));
+        const uint64_t k_desc0 = umma_desc_sw128(smem_u32(smem + Q4_OFF_K));
+        const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + Q4_OFF_V));
+        const int kcol = HD + head * ATT_D, vcol = 2 * HD + head * ATT_D;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tma_load_3d(smem + Q4_OFF_Q, &tmQ, q_full, head * ATT_D, qt * ATT_BQ, img);
+            mbar_arrive_expect_tx(&k_full[0], Q4_KV_BYTES);
+            tma_load_3d(smem + Q4_OFF_K, &tmKV, &k_full[0], kcol, 0, img);
+            mbar_arrive_expect_tx(&v_full[0], Q4_KV_BYTES);
+            tma_load_3d(smem + Q4_OFF_V, &tmKV, &v_full[0], vcol, 0, img);
+            if (nkb > 1) {
+                mbar_arrive_expect_tx(&k_full[1], Q4_KV_BYTES);
+                tma_load_3d(smem + Q4_OFF_K + Q4_KV_BYTES, &tmKV, &k_full[1], kcol, Q4_BKV, img);
+            }
+        }
+        __syncwarp();
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t idesc = nkb == 1 ? idesc_s_last : IDESC_S;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc + k * 2, k_desc0 + k * 2, idesc, k != 0);
+            umma_commit(s_full);
+        }
+        __syncwarp();
+        for (int j = 0; j < nkb; ++j) {
+            const int s = j & 1, s1 = s ^ 1;
+            const bool last = j + 1 == nkb;
+            // S_j visible => S_j and PV_{j-1} are complete: K stage s and V stage s1 are free.  Their next loads (V_{j+1}, K_{j+2}) go out
+            // here, a whole softmax block before p_ready(j), i.e. about two block periods before the tensor core needs them.
+            mbar_wait(s_full, j & 1);
+            if (elect_one()) {
+                if (!last) {
+                    mbar_arrive_expect_tx(&v_full[s1], Q4_KV_BYTES);
+                    tma_load_3d(smem + Q4_OFF_V + s1 * Q4_KV_BYTES, &tmKV, &v_full[s1], vcol, (j + 1) * Q4_BKV, img);
+                }
+                if (j + 2 < nkb) {
+                    mbar_arrive_expect_tx(&k_full[s], Q4_KV_BYTES);
+                    tma_load_3d(smem + Q4_OFF_K + s * Q4_KV_BYTES, &tmKV, &k_full[s], kcol, (j + 2) * Q4_BKV, img);
+                }
+            }
+            __syncwarp();
+            if (!last) mbar_wait(&k_full[s1], ((j + 1) >> 1) & 1);
+            mbar_wait(&v_full[s], (j >> 1) & 1);
+            mbar_wait(p_ready, j & 1);  // P_j is in tensor memory
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t v_desc = v_desc0 + s * (Q4_KV_BYTES >> 4);
+                const int pv_steps = last ? pv_steps_last : Q4_BKV / 16;
+#pragma unroll
+                for (int k = 0; k < Q4_BKV / 16; ++k) {
+                    if (k < pv_steps) umma_f16_ts(tmem_O, tmem_S + k * 8, v_desc + k * (2048 >> 4), IDESC_O, (j | k) != 0);
+                }
+                if (!last) {
+                    const uint64_t k_desc = k_desc0 + s1 * (Q4_KV_BYTES >> 4);
+                    const uint32_t idesc = (j + 2 == nkb) ? idesc_s_last : IDESC_S;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S, q_desc + k * 2, k_desc + k * 2, idesc, k != 0);
+                }
+                umma_commit(s_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax warps: one thread per query row =====================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t* kmask = nullptr;
+        if (p.key_valid != nullptr || (p.T % Q4_BKV) != 0) {
+            uint32_t* words = reinterpret_cast<uint32_t*>(smem + Q4_OFF_KMASK);
+            const uint8_t* kvalid = p.key_valid ? p.key_valid + (size_t)img * p.T : nullptr;
+            for (int w = warp - 1; w < nkb * (Q4_BKV / 32); w += 4) {
+                const int key = w * 32 + lane;
+                const bool ok = key < p.T && (kvalid == nullptr || kvalid[key] != 0);
+                const uint32_t word = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) words[w] = word;
+            }
+            named_bar_sync(1, 128);
+            kmask = words;
+        }
+        const bool warp_active = qt * ATT_BQ + quarter * 32 < p.T;
+        SoftmaxState st{0.f, 0.f, 0.f};
+        for (int j = 0; j < nkb; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            if (!warp_active) {
+                tc_fence_before();
+                mbar_arrive(p_ready);
+                continue;
+            }
+            const bool last = j + 1 == nkb;
+            const uint32_t* km = (p.key_valid != nullptr || last) ? kmask : nullptr;
+            if (!last || p.n_last > 32) softmax_block_q4<2, POLY>(st, j, p, km, tmem_S + lane_off, tmem_O + lane_off, p_ready);
+            else softmax_block_q4<1, POLY>(st, j, p, km, tmem_S + lane_off, tmem_O + lane_off, p_ready);
+        }
+        // ---- epilogue: O / l, bf16, staged in the (finished) Q tile, TMA store
+        mbar_wait(s_full, nkb & 1);
+        tc_fence_after();
+        const float inv_l = st.l_run > 0.f ? 1.0f / st.l_run : 0.f;
+        uint8_t* o_row = smem + Q4_OFF_Q + r * 128;
+        if (warp_active) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv_l, __uint_as_float(ov[g * 8 + 1]) * inv_l);
+                    u.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv_l, __uint_as_float(ov[g * 8 + 3]) * inv_l);
+                    u.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv_l, __uint_as_float(ov[g * 8 + 5]) * inv_l);
+                    u.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv_l, __uint_as_float(ov[g * 8 + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(o_row + (((c * 4 + g) ^ (r & 7)) * 16)) = u;
+                }
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 32) {
+            tma_store_3d(&tmO, smem + Q4_OFF_Q, head * ATT_D, qt * ATT_BQ, img);
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<Q4_TMEM_COLS>(tmem_base);
+    }
+}
+
 }  // namespace
 }  // namespace wg
 
@@ -919,13 +1228,14 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     // tuning knobs (defaults measured on B200): WG_ATTN_POLY = exponentials per 8 evaluated on the FMA pipe,
     // WG_ATTN_SPLIT = softmax threads per query row
-    struct Knobs { int poly, split, smem_pad, persist, extra; };
+    struct Knobs { int poly, split, smem_pad, persist, extra, q4, poly_set; };
     static const Knobs knobs = [] {  // read once (C++11 guarantees a thread-safe initialisation)
         Knobs k;
         const char* pad = getenv("WG_ATTN_SMEM_PAD");  // debug: extra dynamic smem (forces one CTA per SM when large)
         k.smem_pad = pad ? atoi(pad) : 0;
         const char* e = getenv("WG_ATTN_POLY");
         k.poly = e ? atoi(e) : ATT_POLY_DEFAULT;
+        k.poly_set = e != nullptr;
         if (k.poly < 0 || k.poly > 4) k.poly = ATT_POLY_DEFAULT;
         e = getenv("WG_ATTN_SPLIT");
         k.split = e ? atoi(e) : ATT_SPLIT_DEFAULT;
@@ -934,6 +1244,8 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
         k.persist = (e == nullptr || atoi(e) != 0) ? 1 : 0;
         e = getenv("WG_ATTN_EXTRA_KEY");  // 0: the 1025th key gets its own (narrow) key block, as in round 1
         k.extra = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+        e = getenv("WG_ATTN_Q4");  // four CTAs per SM with 64-key blocks (attention_d64_q4_kernel)
+        k.q4 = e ? atoi(e) : ATT_Q4_DEFAULT;
         return k;
     }();
     const int poly = knobs.poly, split = knobs.split, smem_pad = knobs.smem_pad, persist = knobs.persist;
@@ -943,6 +1255,31 @@ extern "C" int wg_attention_d64(const void* qkv, void* out, const uint8_t* key_v
     // once more) 0.53 ms; the leftover key folded into every row on CUDA cores instead of a ninth key block 0.55 ms; the last
     // row folded into the producer warps 0.65-0.83 ms.
     Prof prof("attention_d64", stream, 4.0 * B * heads * (double)T * T * ATT_D, 2.0 * 4.0 * B * (double)T * heads * ATT_D);
+    if (knobs.q4 && split == 1) {
+        CUtensorMap tmKV;
+        uint64_t dims[3] = {3 * HD, (uint64_t)T, (uint64_t)B};
+        uint64_t strides[2] = {3 * HD * 2, (uint64_t)T * 3 * HD * 2};
+        uint32_t box[3] = {ATT_D, Q4_BKV, 1};
+        WG_TRY(make_tensor_map(&tmKV, qkv, 2, 3, dims, strides, box));
+        p.num_kv_blocks = (T + Q4_BKV - 1) / Q4_BKV;
+        p.n_last = ((T - (p.num_kv_blocks - 1) * Q4_BKV) + 15) / 16 * 16;
+        dim3 grid((T + ATT_BQ - 1) / ATT_BQ, heads, B);
+#define WG_ATT_Q4LAUNCH(P)                                                                                                      \
+    do {                                                                                                                        \
+        WG_SMEM_OPT_IN(attention_d64_q4_kernel<P>, Q4_SMEM_BYTES);                                                              \
+        attention_d64_q4_kernel<P><<<grid, Q4_THREADS, Q4_SMEM_BYTES, stream>>>(tmQKV, tmKV, tmO, p);                          \
+    } while (0)
+        switch (knobs.poly_set ? poly : ATT_Q4_POLY_DEFAULT) {
+            case 1: WG_ATT_Q4LAUNCH(1); break;
+            case 2: WG_ATT_Q4LAUNCH(2); break;
+            case 3: WG_ATT_Q4LAUNCH(3); break;
+            case 4: WG_ATT_Q4LAUNCH(4); break;
+            default: WG_ATT_Q4LAUNCH(0); break;
+        }
+#undef WG_ATT_Q4LAUNCH
+        WG_CHECK_CUDA(cudaGetLastError());
+        return WG_OK;
+    }
     // persistent kernel (two CTAs per SM walking the work list) from 4 key blocks per tile on; WG_ATTN_PERSIST=0 falls back to one
     // CTA per (tile, head, image)
     const long long n_items = (long long)B * heads * ((T + ATT_BQ - 1) / ATT_BQ);
