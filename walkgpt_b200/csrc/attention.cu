@@ -1033,6 +1033,18 @@ attention_d64_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             mbar_init(s_full, 1);
             mbar_init(p_ready, 128);
             fence_mbar_init();
+            // the first loads go out before the tensor-memory allocation and the CTA-wide barrier: their round trip overlaps the set-up
+            const int kcol0 = HD + head * ATT_D, vcol0 = 2 * HD + head * ATT_D;
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tma_load_3d(smem + Q4_OFF_Q, &tmQ, q_full, head * ATT_D, qt * ATT_BQ, img);
+            mbar_arrive_expect_tx(&k_full[0], Q4_KV_BYTES);
+            tma_load_3d(smem + Q4_OFF_K, &tmKV, &k_full[0], kcol0, 0, img);
+            mbar_arrive_expect_tx(&v_full[0], Q4_KV_BYTES);
+            tma_load_3d(smem + Q4_OFF_V, &tmKV, &v_full[0], vcol0, 0, img);
+            if (nkb > 1) {
+                mbar_arrive_expect_tx(&k_full[1], Q4_KV_BYTES);
+                tma_load_3d(smem + Q4_OFF_K + Q4_KV_BYTES, &tmKV, &k_full[1], kcol0, Q4_BKV, img);
+            }
         }
         __syncwarp();
         tmem_alloc<Q4_TMEM_COLS>(tmem_ptr_smem);
@@ -1054,19 +1066,6 @@ attention_d64_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const uint64_t k_desc0 = umma_desc_sw128(smem_u32(smem + Q4_OFF_K));
         const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + Q4_OFF_V));
         const int kcol = HD + head * ATT_D, vcol = 2 * HD + head * ATT_D;
-        if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, TILE_BYTES);
-            tma_load_3d(smem + Q4_OFF_Q, &tmQ, q_full, head * ATT_D, qt * ATT_BQ, img);
-            mbar_arrive_expect_tx(&k_full[0], Q4_KV_BYTES);
-            tma_load_3d(smem + Q4_OFF_K, &tmKV, &k_full[0], kcol, 0, img);
-            mbar_arrive_expect_tx(&v_full[0], Q4_KV_BYTES);
-            tma_load_3d(smem + Q4_OFF_V, &tmKV, &v_full[0], vcol, 0, img);
-            if (nkb > 1) {
-                mbar_arrive_expect_tx(&k_full[1], Q4_KV_BYTES);
-                tma_load_3d(smem + Q4_OFF_K + Q4_KV_BYTES, &tmKV, &k_full[1], kcol, Q4_BKV, img);
-            }
-        }
-        __syncwarp();
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
@@ -1176,7 +1175,7 @@ attention_d64_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (threadIdx.x == 32) {
             tma_store_3d(&tmO, smem + Q4_OFF_Q, head * ATT_D, qt * ATT_BQ, img);
             tma_store_commit();
-            tma_store_wait_all<0>();
+            tma_store_wait_read<0>();  // the staging tile has been read; the writes complete on their own
         }
     }
 
