@@ -129,13 +129,14 @@ def _attn_ref(qkv, heads, scale, kv=None):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, heads * 64)
 
 
-# T = 1025 / 130 / 5 / 1 / 300 / 264 / 1032 end in a partial query tile and a narrow last key block; masked cases exercise the
-# key-validity words in every key block.  Sequences of >= 4 key blocks run the persistent kernel: (2, 1025, 16) gives every CTA one
-# item, (6, 1025, 16) and (9, 640, 8) several items per CTA with the image (and, when masked, the validity words) changing between
-# items, (40, 512, 8) ten items per CTA without a partial tile; shorter sequences run one CTA per tile.
+# The default kernel (attention_d64_q4_kernel: one CTA per 128-query tile, four per SM, 64-key blocks) sees: T = 1025 / 130 / 5 / 1 /
+# 300 / 264 / 1032 / 17 / 33 / 97 ending in a partial query tile and a narrow last key block (16, 32 or 48 keys: both softmax widths),
+# T = 64 / 65 / 128 / 1024 on the block boundaries, masked cases exercising the key-validity words in every key block, and grids of a few
+# CTAs up to several waves ((40, 512, 8): 1280 CTAs on 592 slots).
 @pytest.mark.parametrize("B,T,H,masked", [(1, 128, 1, False), (1, 1, 2, False), (2, 1025, 16, False), (2, 1025, 16, True), (1, 300, 3, True),
                                           (2, 130, 2, True), (1, 5, 2, False), (1, 264, 1, False), (1, 1024, 4, False), (1, 1032, 2, True),
-                                          (6, 1025, 16, True), (6, 1025, 16, False), (9, 640, 8, True), (40, 512, 8, False)])
+                                          (6, 1025, 16, True), (6, 1025, 16, False), (9, 640, 8, True), (40, 512, 8, False),
+                                          (2, 64, 3, False), (2, 65, 3, True), (1, 17, 1, True), (3, 33, 2, False), (2, 97, 5, True)])
 def test_attention(B, T, H, masked):
     torch.manual_seed(3)
     qkv = torch.randn(B, T, 3 * H * 64, device=DEV).bfloat16()
@@ -143,6 +144,23 @@ def test_attention(B, T, H, masked):
     if masked:
         kv = (torch.rand(B, T, device=DEV) > 0.3).to(torch.uint8)
         kv[:, 0] = 1  # the CLS key is always valid in the reference (llava_arch.py:182-190)
+    assert rel_err(ops.attention_d64(qkv, H, 0.125, kv), _attn_ref(qkv, H, 0.125, kv)) < 1e-2
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 300, 2), (1, 1025, 3)])
+def test_attention_lazy_rescale_path(B, T, H):
+    """The running softmax scale is only refreshed (O and l rescaled through tensor memory) when a row's maximum grows by more than 2^8;
+    with N(0, 1) inputs that never happens after the first key block.  Here the keys grow with their position, so that the maximum of
+    almost every row jumps by far more than the threshold in every key block, and one image has its largest keys masked."""
+    torch.manual_seed(5)
+    qkv = torch.randn(B, T, 3 * H * 64, device=DEV)
+    growth = 1.0 + 3.0 * (torch.arange(T, device=DEV) // 48).float()          # steps inside and across the 64- / 128-key blocks
+    qkv[:, :, H * 64:2 * H * 64] *= growth[None, :, None]
+    qkv = qkv.bfloat16()
+    out = ops.attention_d64(qkv, H, 0.125)
+    assert rel_err(out, _attn_ref(qkv, H, 0.125)) < 1e-2
+    kv = torch.ones(B, T, device=DEV, dtype=torch.uint8)
+    kv[0, T // 2:] = 0
     assert rel_err(ops.attention_d64(qkv, H, 0.125, kv), _attn_ref(qkv, H, 0.125, kv)) < 1e-2
 
 

@@ -1,8 +1,13 @@
 // Fused flash-style multi-head attention for the CLIP ViT-L/14@448 tower: head_dim 64,
 // T = 1025 tokens, optional key-padding mask (custom_clip.py:27-38 semantics: masked KEYS never receive weight).
 //
+// DEFAULT: attention_d64_q4_kernel (bottom of the file) -- FOUR CTAs per SM, 64-key blocks, P written in place over S, 128 TMEM columns
+// and 5 warps per CTA (B200, B=64, T=1025: 0.395 ms = 697 TFLOP/s; T=1024: 0.346 ms = 795 TFLOP/s).  The two-CTAs-per-SM kernels
+// described next are what it replaced (0.51 ms); they stay reachable with WG_ATTN_Q4=0 as the A/B baseline and are still covered by the
+// attention tests when that variable is set.
+//
 // Two CTAs co-reside per SM so that one CTA's softmax overlaps the other's tensor work.  From 4 key blocks per tile on they
-// are persistent and walk a list of (image, head, 128-query tile) items (attention_d64_persist_kernel, bottom of the file);
+// are persistent and walk a list of (image, head, 128-query tile) items (attention_d64_persist_kernel);
 // shorter sequences get one CTA per item (attention_d64_kernel).  Per CTA:
 //   warp 0  : TMA producer  (Q once, K/V blocks of 128 keys through 2-stage rings with separate K / V release;
 //             3-D tensor map over [image, token, 3*heads*64] so rows past T are zero-filled by the hardware)
