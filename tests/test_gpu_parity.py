@@ -132,11 +132,13 @@ def _attn_ref(qkv, heads, scale, kv=None):
 # The default kernel (attention_d64_q4_kernel: one CTA per 128-query tile, four per SM, 64-key blocks) sees: T = 1025 / 130 / 5 / 1 /
 # 300 / 264 / 1032 / 17 / 33 / 97 ending in a partial query tile and a narrow last key block (16, 32 or 48 keys: both softmax widths),
 # T = 64 / 65 / 128 / 1024 on the block boundaries, masked cases exercising the key-validity words in every key block, and grids of a few
-# CTAs up to several waves ((40, 512, 8): 1280 CTAs on 592 slots).
+# CTAs up to several waves ((16, 1025, 16): 2304 CTAs on 592 slots, with the one-row ninth tile and -- masked -- a different set of
+# validity words per image).
 @pytest.mark.parametrize("B,T,H,masked", [(1, 128, 1, False), (1, 1, 2, False), (2, 1025, 16, False), (2, 1025, 16, True), (1, 300, 3, True),
                                           (2, 130, 2, True), (1, 5, 2, False), (1, 264, 1, False), (1, 1024, 4, False), (1, 1032, 2, True),
                                           (6, 1025, 16, True), (6, 1025, 16, False), (9, 640, 8, True), (40, 512, 8, False),
-                                          (2, 64, 3, False), (2, 65, 3, True), (1, 17, 1, True), (3, 33, 2, False), (2, 97, 5, True)])
+                                          (2, 64, 3, False), (2, 65, 3, True), (1, 17, 1, True), (3, 33, 2, False), (2, 97, 5, True),
+                                          (16, 1025, 16, True), (16, 1025, 16, False), (20, 200, 16, True)])
 def test_attention(B, T, H, masked):
     torch.manual_seed(3)
     qkv = torch.randn(B, T, 3 * H * 64, device=DEV).bfloat16()
