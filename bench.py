@@ -589,8 +589,18 @@ def main():
     tail = kern.get("postprocess_bilinear_score")
     extra = {}
     if att:
-        extra["attention_d64"] = {"tflops": att["flops_per_step"] / (att["ms_per_step"] * 1e-3) / 1e12, "ms_per_step": att["ms_per_step"],
-                                  "share_of_step": att["ms_per_step"] / tot_ms}
+        a_tf = att["flops_per_step"] / (att["ms_per_step"] * 1e-3) / 1e12
+        extra["attention_d64"] = {"tflops": a_tf, "frac_of_tensor_peak": a_tf / peak, "ms_per_step": att["ms_per_step"], "share_of_step": att["ms_per_step"] / tot_ms}
+        # at head_dim 64 the softmax's exponentials, not the tensor pipe, bound the kernel: one exponential per score (flops / (4 * 64)) against the
+        # MUFU unit's measured 16 results per clock and SM (tools/ubench/xu_rates.cu) at the SM clock sampled under load
+        if clocks and clocks.get("sm_mhz"):
+            mufu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * clocks["sm_mhz"] * 1e6
+            exps = att["flops_per_step"] / 256.0 / (att["ms_per_step"] * 1e-3)
+            extra["attention_d64"].update({"bound": "mufu", "exp_per_s": exps, "mufu_peak_exp_per_s": mufu_peak, "frac_of_mufu_peak": exps / mufu_peak})
+        apath = os.path.join(ROOT, "profiles", "r02ab_attention_q4_summary.json")
+        if os.path.exists(apath):  # one `ncu --set full` capture of attention_d64_q4_kernel at B=64, T=1025, 16 heads
+            extra["attention_d64"]["traffic"] = json.load(open(apath))["dram_bytes"]
+            extra["attention_d64"]["traffic_note"] = "ncu dram bytes of one launch (B=64, T=1025, 16 heads); algorithmic bytes 4 * B * T * 1024 * 2 = 537 MB" 
     if tail:
         gbs = tail["bytes_per_step"] / (tail["ms_per_step"] * 1e-3) / 1e9
         extra["postprocess_bilinear_score"] = {"bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peaks["hbm"], "frac": gbs / peaks["hbm"],
