@@ -166,6 +166,43 @@ def test_attention_lazy_rescale_path(B, T, H):
     assert rel_err(ops.attention_d64(qkv, H, 0.125, kv), _attn_ref(qkv, H, 0.125, kv)) < 1e-2
 
 
+_FALLBACK_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from walkgpt_b200 import ops
+torch.manual_seed(3)
+worst = 0.0
+for B, T, H, masked in [(2, 1025, 16, True), (6, 1025, 16, False), (2, 130, 2, True), (1, 5, 2, False), (9, 640, 8, True)]:
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda").bfloat16()
+    kv = None
+    if masked:
+        kv = (torch.rand(B, T, device="cuda") > 0.3).to(torch.uint8)
+        kv[:, 0] = 1
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if kv is not None:
+        s = s.masked_fill(~kv.bool()[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, H * 64)
+    out = ops.attention_d64(qkv, H, 0.125, kv).float()
+    assert torch.isfinite(out).all()
+    worst = max(worst, ((out - ref).abs().max() / ref.abs().max()).item())
+print("WORST", worst)
+"""
+
+
+@pytest.mark.parametrize("env", [{"WG_ATTN_Q4": "0"}, {"WG_ATTN_Q4": "0", "WG_ATTN_PERSIST": "0"}, {"WG_ATTN_Q4": "0", "WG_ATTN_EXTRA_KEY": "0"}])
+def test_attention_ab_baseline_kernels(env):
+    """The two-CTAs-per-SM kernels the q4 kernel replaced stay in the library as the A/B baseline (WG_ATTN_Q4=0).  The switches are read
+    once per process, so they are exercised in a child process: persistent kernel with and without the extra-key treatment of the 1025th
+    token, and one CTA per tile."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _FALLBACK_SNIPPET, root], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst < 1e-2, worst
+
+
 # ------------------------------------------------------------------------------------------------ SAM ViT encoder (SURVEY 8(f) row 1)
 def _sam_kernel_qkv(q, k, v, heads):
     """q / k / v [units, heads, L, 80] -> the kernel's qkv matrix [units * L, 3 * heads * 80] (bf16), columns
