@@ -844,6 +844,37 @@ def test_full_batch_properties(path_model):
     assert torch.equal(out2["logits"][S:], logits[S:]) and not torch.equal(out2["logits"][:S], logits[:S])
 
 
+@pytest.mark.parametrize("H,S,B", [(4096, 12, 64), (5120, 16, 64)])
+def test_full_batch_properties_other_baseline_configs(H, S, B):
+    """BASELINE.json configs[2] (64 images x 12 [SEG]) and one 64-image micro-batch of configs[4] (H = 5120, 16 [SEG]) at full size: the
+    same model's one-image result is pinned to the fp32 oracle by test_path_a_other_baseline_configs; here every image of the full batch must
+    reproduce its solo result bit for bit (images are independent units of work, prompts only meet their own image), the masks must be the
+    thresholded logits and the scores the reference formula (model/walkgpt.py:541) on those logits; then a RAGGED batch (0 .. S prompts per
+    image, as a real conversation batch has) must agree with the full one on the prompts they share."""
+    m = _round_weights_to_bf16(M.GroundingPath(hidden_size=H, clip_layers=24, seed=2)).to(DEV)
+    px = rnd((B, 3, 448, 448), 51).bfloat16().to(DEV)
+    seg = rnd((B * S, H), 52).bfloat16().to(DEV)
+    offs = list(range(0, B * S + 1, S))
+    out = m(px, seg, offs)
+    logits = out["logits"]
+    assert logits.shape == (B * S, 448, 448) and torch.isfinite(logits).all() and torch.equal(out["masks"].bool(), logits > 0)
+    pos = (logits[:64] > 0).flatten(1)
+    score = (logits[:64].sigmoid().flatten(1) * pos).sum(1) / (pos.sum(1) + 1e-6)
+    assert torch.allclose(out["scores"][:64], score, atol=1e-4)
+    for i in (0, 37, B - 1):
+        solo = m(px[i:i + 1], seg[i * S:(i + 1) * S], [0, S])
+        assert torch.equal(solo["logits"], logits[i * S:(i + 1) * S]) and torch.equal(solo["vis_tokens"], out["vis_tokens"][i:i + 1])
+        assert torch.allclose(solo["iou"], out["iou"][i * S:(i + 1) * S], atol=1e-6)
+    # ragged: image i keeps its first (i % (S + 1)) prompts
+    keep = [i % (S + 1) for i in range(B)]
+    rows = torch.cat([torch.arange(i * S, i * S + k) for i, k in enumerate(keep)]).to(DEV)
+    roffs = [0]
+    for k in keep:
+        roffs.append(roffs[-1] + k)
+    rag = m(px, seg[rows], roffs)
+    assert rag["logits"].shape[0] == roffs[-1] and torch.equal(rag["logits"], logits[rows]) and torch.allclose(rag["scores"], out["scores"][rows], atol=1e-6)
+
+
 def test_llm_hidden_states_feed_the_path():
     """BASELINE config 5's composition (bench.py --config 5) at a small LLM width: the path's own MSQP tokens, resampled 6x6 -> 16x16, take the
     <image> slot of an HF Llama prefill (the reference's LLM is a subclass of this class and stays PyTorch); [SEG] rows are extracted with the
